@@ -1,0 +1,582 @@
+// diffndm_b200 engine: HBM workspace, weight packing, forward orchestration and the C ABI (include/diffndm_b200.h).
+#include "../../include/diffndm_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_tn.cuh"
+#include "edge_mlp.cuh"
+#include "graph.cuh"
+#include "node_kernels.cuh"
+
+using namespace dndm;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU_CHECK(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess)                                                                        \
+            return set_err(DNDM_ECUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor creation through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+// bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128-byte swizzle.
+static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return DNDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// engine state
+// ------------------------------------------------------------------------------------------------
+struct LayerWeights {
+    __nv_bfloat16 *wproj_e, *wproj_c, *w2_e, *w2_c, *w2_x, *w3, *w4;   // device bf16
+    float *bias_e, *bias_c, *b3, *b4, *w1e_e, *w1e_c, *w1e_x;          // device fp32
+    CUtensorMap tm_proj_e, tm_proj_c, tm_w2_e, tm_w2_c, tm_w2_x, tm_w3, tm_w4;
+    EdgeConsts c_e, c_c, c_x;                                            // host copies (kernel parameters)
+    float att_bias;
+};
+
+struct DndmEngine {
+    DndmConfig cfg;
+    int num_sms = 148;
+    bool weights_loaded = false;
+    // workspace
+    float *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *pq = nullptr, *agg = nullptr, *tile_head = nullptr;
+    float *r0 = nullptr, *phi = nullptr, *psi = nullptr, *pocket_sum = nullptr;
+    __nv_bfloat16 *hcat = nullptr, *hid = nullptr;
+    int *node_sample = nullptr, *lig_ptr = nullptr, *pok_ptr = nullptr, *deg = nullptr, *row_ptr = nullptr;
+    int *ecol = nullptr, *erow = nullptr, *scalars = nullptr;
+    unsigned* flags = nullptr;
+    CUtensorMap tm_hcat, tm_hid;
+    // weights
+    std::vector<LayerWeights> layers;
+    std::vector<void*> weight_allocs;
+    EncoderWeights enc_l{}, enc_p{};
+    DecoderWeights dec_l{}, dec_p{};
+    // last call
+    int last_n_lig = 0, last_n_nodes = 0;
+    float* x_final = nullptr;
+    // trace
+    float *h_trace = nullptr, *x_trace = nullptr;
+    int max_trace_nodes = 0;
+};
+
+template <class T>
+static int dev_alloc(T** p, size_t n) {
+    CU_CHECK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+    return DNDM_OK;
+}
+#define RET_IF(x)              \
+    do {                       \
+        int _r = (x);          \
+        if (_r != DNDM_OK) return _r; \
+    } while (0)
+
+extern "C" const char* dndm_version(void) { return "diffndm_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+extern "C" const char* dndm_last_error(void) { return g_err; }
+
+extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
+    if (!cfg || !out) return set_err(DNDM_EINVAL, "null argument");
+    if (cfg->hidden_nf != EK_H) return set_err(DNDM_EINVAL, "hidden_nf=%d unsupported (compiled for %d)", cfg->hidden_nf, EK_H);
+    if (cfg->atom_nf < 1 || cfg->atom_nf > 29 || cfg->residue_nf < 1 || cfg->residue_nf > 29)
+        return set_err(DNDM_EINVAL, "atom_nf/residue_nf must be in [1,29]");
+    if (2 * cfg->atom_nf > 32 || 2 * cfg->residue_nf > 32) return set_err(DNDM_EINVAL, "encoder hidden width > 32 unsupported");
+    if (cfg->max_nodes < 1 || cfg->max_edges < 1 || cfg->max_samples < 1) return set_err(DNDM_EINVAL, "bad capacities");
+    CU_CHECK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return set_err(DNDM_ECUDA, "device sm_%d%d is not Blackwell sm_100", prop.major, prop.minor);
+    DndmEngine* e = new DndmEngine();
+    e->cfg = *cfg;
+    e->num_sms = prop.multiProcessorCount;
+    const size_t N = (size_t)((cfg->max_nodes + 127) / 128) * 128, E = cfg->max_edges, B = cfg->max_samples;
+    const size_t tiles = (E + EK_TILE - 1) / EK_TILE + 1;
+    RET_IF(dev_alloc(&e->x0, N * 3)); RET_IF(dev_alloc(&e->xa, N * 3)); RET_IF(dev_alloc(&e->xb, N * 3));
+    RET_IF(dev_alloc(&e->h, N * 256)); RET_IF(dev_alloc(&e->pq, N * 1536)); RET_IF(dev_alloc(&e->agg, N * 256));
+    RET_IF(dev_alloc(&e->tile_head, tiles * 256));
+    RET_IF(dev_alloc(&e->r0, E)); RET_IF(dev_alloc(&e->phi, E)); RET_IF(dev_alloc(&e->psi, E));
+    RET_IF(dev_alloc(&e->pocket_sum, B * 3));
+    RET_IF(dev_alloc(&e->hcat, N * 512)); RET_IF(dev_alloc(&e->hid, N * 256));
+    RET_IF(dev_alloc(&e->node_sample, N)); RET_IF(dev_alloc(&e->lig_ptr, B + 1)); RET_IF(dev_alloc(&e->pok_ptr, B + 1));
+    RET_IF(dev_alloc(&e->deg, N)); RET_IF(dev_alloc(&e->row_ptr, N + 1));
+    RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 4));
+    RET_IF(dev_alloc(&e->flags, 1));
+    CU_CHECK(cudaMemset(e->flags, 0, 4));
+    CU_CHECK(cudaMemset(e->hcat, 0, N * 512 * 2));
+    CU_CHECK(cudaMemset(e->hid, 0, N * 256 * 2));
+    RET_IF(make_tmap_bf16(&e->tm_hcat, e->hcat, N, 512, 512, GEMM_BM));
+    RET_IF(make_tmap_bf16(&e->tm_hid, e->hid, N, 256, 256, GEMM_BM));
+    CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
+    *out = e;
+    return DNDM_OK;
+}
+
+static void free_weights(DndmEngine* e) {
+    for (void* p : e->weight_allocs) cudaFree(p);
+    e->weight_allocs.clear();
+    e->layers.clear();
+    e->weights_loaded = false;
+}
+
+extern "C" void dndm_engine_destroy(DndmEngine* e) {
+    if (!e) return;
+    free_weights(e);
+    void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->agg, e->tile_head, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
+                    e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->flags};
+    for (void* p : bufs) cudaFree(p);
+    delete e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+struct HostW {
+    const float* d;
+    int rows, cols;
+};
+static __nv_bfloat16 f2bf(float f) { return __float2bfloat16_rn(f); }
+
+template <class T>
+static int upload(DndmEngine* e, const std::vector<T>& host, T** dev) {
+    void* p = nullptr;
+    CU_CHECK(cudaMalloc(&p, host.size() * sizeof(T)));
+    e->weight_allocs.push_back(p);
+    CU_CHECK(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = reinterpret_cast<T*>(p);
+    return DNDM_OK;
+}
+
+extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights, int32_t n_weights) {
+    if (!e || !weights) return set_err(DNDM_EINVAL, "null argument");
+    CU_CHECK(cudaSetDevice(e->cfg.device));
+    CU_CHECK(cudaDeviceSynchronize());
+    free_weights(e);
+    std::map<std::string, HostW> W;
+    for (int i = 0; i < n_weights; ++i) W[weights[i].name] = HostW{weights[i].data, weights[i].rows, weights[i].cols};
+    auto need = [&](const std::string& k, int rows, int cols, const float** out) -> int {
+        auto it = W.find(k);
+        if (it == W.end()) return set_err(DNDM_EWEIGHTS, "missing weight '%s'", k.c_str());
+        if (it->second.rows != rows || it->second.cols != cols)
+            return set_err(DNDM_EWEIGHTS, "weight '%s' has shape [%d,%d], expected [%d,%d]", k.c_str(), it->second.rows,
+                           it->second.cols, rows, cols);
+        *out = it->second.d;
+        return DNDM_OK;
+    };
+    const int H = e->cfg.hidden_nf, J = e->cfg.joint_nf, A = e->cfg.atom_nf, R = e->cfg.residue_nf;
+    const int DE = 2, KIN = 2 * H + DE;
+
+    // ---- encoder (+ embedding) and decoder (+ embedding_out), pre-composed in fp64 ----
+    const float *emb_w, *emb_b, *out_w, *out_b;
+    RET_IF(need("egnn.embedding.weight", H, J + 1, &emb_w));
+    RET_IF(need("egnn.embedding.bias", H, 1, &emb_b));
+    RET_IF(need("egnn.embedding_out.weight", J + 1, H, &out_w));
+    RET_IF(need("egnn.embedding_out.bias", J + 1, 1, &out_b));
+    auto pack_encoder = [&](const char* pre, int nf, EncoderWeights* ew) -> int {
+        const float *w1, *b1, *w2, *b2;
+        const int hid = 2 * nf;
+        RET_IF(need(std::string(pre) + ".0.weight", hid, nf, &w1));
+        RET_IF(need(std::string(pre) + ".0.bias", hid, 1, &b1));
+        RET_IF(need(std::string(pre) + ".2.weight", J, hid, &w2));
+        RET_IF(need(std::string(pre) + ".2.bias", J, 1, &b2));
+        std::vector<float> hw1(w1, w1 + hid * nf), hb1(b1, b1 + hid), wc2((size_t)H * hid), bc(H), wt(H);
+        for (int k = 0; k < H; ++k) {
+            for (int j = 0; j < hid; ++j) {
+                double s = 0;
+                for (int m = 0; m < J; ++m) s += (double)emb_w[k * (J + 1) + m] * (double)w2[m * hid + j];
+                wc2[(size_t)k * hid + j] = (float)s;
+            }
+            double s = emb_b[k];
+            for (int m = 0; m < J; ++m) s += (double)emb_w[k * (J + 1) + m] * (double)b2[m];
+            bc[k] = (float)s;
+            wt[k] = emb_w[k * (J + 1) + J];
+        }
+        float *d1, *d2, *d3, *d4, *d5;
+        RET_IF(upload(e, hw1, &d1)); RET_IF(upload(e, hb1, &d2)); RET_IF(upload(e, wc2, &d3));
+        RET_IF(upload(e, bc, &d4)); RET_IF(upload(e, wt, &d5));
+        *ew = EncoderWeights{d1, d2, d3, d4, d5, nf, hid};
+        return DNDM_OK;
+    };
+    RET_IF(pack_encoder("atom_encoder", A, &e->enc_l));
+    RET_IF(pack_encoder("residue_encoder", R, &e->enc_p));
+    auto pack_decoder = [&](const char* pre, int nf, DecoderWeights* dw) -> int {
+        const float *w0, *b0, *w2, *b2;
+        const int hid = 2 * nf;
+        RET_IF(need(std::string(pre) + ".0.weight", hid, J, &w0));
+        RET_IF(need(std::string(pre) + ".0.bias", hid, 1, &b0));
+        RET_IF(need(std::string(pre) + ".2.weight", nf, hid, &w2));
+        RET_IF(need(std::string(pre) + ".2.bias", nf, 1, &b2));
+        std::vector<float> wc((size_t)hid * H), bc(hid), hw2(w2, w2 + nf * hid), hb2(b2, b2 + nf);
+        for (int j = 0; j < hid; ++j) {
+            for (int k = 0; k < H; ++k) {
+                double s = 0;
+                for (int m = 0; m < J; ++m) s += (double)w0[j * J + m] * (double)out_w[m * H + k];
+                wc[(size_t)j * H + k] = (float)s;
+            }
+            double s = b0[j];
+            for (int m = 0; m < J; ++m) s += (double)w0[j * J + m] * (double)out_b[m];
+            bc[j] = (float)s;
+        }
+        float *d1, *d2, *d3, *d4;
+        RET_IF(upload(e, wc, &d1)); RET_IF(upload(e, bc, &d2)); RET_IF(upload(e, hw2, &d3)); RET_IF(upload(e, hb2, &d4));
+        *dw = DecoderWeights{d1, d2, d3, d4, nf, hid};
+        return DNDM_OK;
+    };
+    RET_IF(pack_decoder("atom_decoder", A, &e->dec_l));
+    RET_IF(pack_decoder("residue_decoder", R, &e->dec_p));
+
+    // ---- per-block weights ----
+    e->layers.resize(e->cfg.n_layers);
+    for (int l = 0; l < e->cfg.n_layers; ++l) {
+        LayerWeights& L = e->layers[l];
+        const std::string p = "egnn.e_block_" + std::to_string(l) + ".";
+        const float *e0w, *e0b, *e2w, *e2b, *n0w, *n0b, *n2w, *n2b, *aw, *ab;
+        const float *c0w, *c0b, *c2w, *c2b, *c4w, *x0w, *x0b, *x2w, *x2b, *x4w;
+        RET_IF(need(p + "gcl_0.edge_mlp.0.weight", H, KIN, &e0w)); RET_IF(need(p + "gcl_0.edge_mlp.0.bias", H, 1, &e0b));
+        RET_IF(need(p + "gcl_0.edge_mlp.2.weight", H, H, &e2w)); RET_IF(need(p + "gcl_0.edge_mlp.2.bias", H, 1, &e2b));
+        RET_IF(need(p + "gcl_0.node_mlp.0.weight", H, 2 * H, &n0w)); RET_IF(need(p + "gcl_0.node_mlp.0.bias", H, 1, &n0b));
+        RET_IF(need(p + "gcl_0.node_mlp.2.weight", H, H, &n2w)); RET_IF(need(p + "gcl_0.node_mlp.2.bias", H, 1, &n2b));
+        RET_IF(need(p + "gcl_0.att_mlp.0.weight", 1, H, &aw)); RET_IF(need(p + "gcl_0.att_mlp.0.bias", 1, 1, &ab));
+        RET_IF(need(p + "gcl_equiv.coord_mlp.0.weight", H, KIN, &c0w)); RET_IF(need(p + "gcl_equiv.coord_mlp.0.bias", H, 1, &c0b));
+        RET_IF(need(p + "gcl_equiv.coord_mlp.2.weight", H, H, &c2w)); RET_IF(need(p + "gcl_equiv.coord_mlp.2.bias", H, 1, &c2b));
+        RET_IF(need(p + "gcl_equiv.coord_mlp.4.weight", 1, H, &c4w));
+        RET_IF(need(p + "gcl_equiv.cross_product_mlp.0.weight", H, KIN, &x0w));
+        RET_IF(need(p + "gcl_equiv.cross_product_mlp.0.bias", H, 1, &x0b));
+        RET_IF(need(p + "gcl_equiv.cross_product_mlp.2.weight", H, H, &x2w));
+        RET_IF(need(p + "gcl_equiv.cross_product_mlp.2.bias", H, 1, &x2b));
+        RET_IF(need(p + "gcl_equiv.cross_product_mlp.4.weight", 1, H, &x4w));
+
+        auto split_first = [&](const float* w, std::vector<__nv_bfloat16>& dst, size_t row_off_a, size_t row_off_b) {
+            for (int o = 0; o < H; ++o)
+                for (int k = 0; k < H; ++k) {
+                    dst[(row_off_a + o) * H + k] = f2bf(w[(size_t)o * KIN + k]);
+                    dst[(row_off_b + o) * H + k] = f2bf(w[(size_t)o * KIN + H + k]);
+                }
+        };
+        auto edge_cols = [&](const float* w) {
+            std::vector<float> v(2 * H);
+            for (int o = 0; o < H; ++o) {
+                v[o] = w[(size_t)o * KIN + 2 * H];          // coefficient of the current radial
+                v[H + o] = w[(size_t)o * KIN + 2 * H + 1];  // coefficient of the input radial
+            }
+            return v;
+        };
+        auto to_bf = [&](const float* w, size_t n) {
+            std::vector<__nv_bfloat16> v(n);
+            for (size_t i = 0; i < n; ++i) v[i] = f2bf(w[i]);
+            return v;
+        };
+        std::vector<__nv_bfloat16> pe((size_t)2 * H * H), pc((size_t)4 * H * H);
+        split_first(e0w, pe, 0, H);
+        split_first(c0w, pc, 0, 2 * H);
+        split_first(x0w, pc, H, 3 * H);
+        std::vector<float> be(2 * H, 0.f), bcv(4 * H, 0.f);
+        for (int o = 0; o < H; ++o) { be[o] = e0b[o]; bcv[o] = c0b[o]; bcv[H + o] = x0b[o]; }
+        RET_IF(upload(e, pe, &L.wproj_e)); RET_IF(upload(e, pc, &L.wproj_c));
+        RET_IF(upload(e, be, &L.bias_e)); RET_IF(upload(e, bcv, &L.bias_c));
+        RET_IF(upload(e, edge_cols(e0w), &L.w1e_e)); RET_IF(upload(e, edge_cols(c0w), &L.w1e_c));
+        RET_IF(upload(e, edge_cols(x0w), &L.w1e_x));
+        RET_IF(upload(e, to_bf(e2w, (size_t)H * H), &L.w2_e)); RET_IF(upload(e, to_bf(c2w, (size_t)H * H), &L.w2_c));
+        RET_IF(upload(e, to_bf(x2w, (size_t)H * H), &L.w2_x));
+        RET_IF(upload(e, to_bf(n0w, (size_t)H * 2 * H), &L.w3)); RET_IF(upload(e, to_bf(n2w, (size_t)H * H), &L.w4));
+        RET_IF(upload(e, std::vector<float>(n0b, n0b + H), &L.b3)); RET_IF(upload(e, std::vector<float>(n2b, n2b + H), &L.b4));
+        for (int o = 0; o < H; ++o) {
+            L.c_e.b2[o] = e2b[o]; L.c_e.wout[o] = aw[o];
+            L.c_c.b2[o] = c2b[o]; L.c_c.wout[o] = c4w[o];
+            L.c_x.b2[o] = x2b[o]; L.c_x.wout[o] = x4w[o];
+        }
+        L.att_bias = ab[0];
+        RET_IF(make_tmap_bf16(&L.tm_proj_e, L.wproj_e, 2 * H, H, H, GEMM_BN));
+        RET_IF(make_tmap_bf16(&L.tm_proj_c, L.wproj_c, 4 * H, H, H, GEMM_BN));
+        RET_IF(make_tmap_bf16(&L.tm_w3, L.w3, H, 2 * H, 2 * H, GEMM_BN));
+        RET_IF(make_tmap_bf16(&L.tm_w4, L.w4, H, H, H, GEMM_BN));
+        RET_IF(make_tmap_bf16(&L.tm_w2_e, L.w2_e, H, H, H, 256));
+        RET_IF(make_tmap_bf16(&L.tm_w2_c, L.w2_c, H, H, H, 256));
+        RET_IF(make_tmap_bf16(&L.tm_w2_x, L.w2_x, H, H, H, 256));
+    }
+    e->weights_loaded = true;
+    return DNDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, int M, int Nout, int K, int a_col0,
+                       const GemmEpilogue& ep) {
+    if (M <= 0) return DNDM_OK;
+    dim3 grid((M + GEMM_BM - 1) / GEMM_BM, Nout / GEMM_BN);
+    gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tw, M, K, a_col0, ep);
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
+static int prepare_batch(DndmEngine* e, const int64_t* lig_mask, const int64_t* pocket_mask, int n_lig, int n_pocket,
+                         int n_samples, cudaStream_t st) {
+    if (n_lig < 1 || n_pocket < 0 || n_samples < 1) return set_err(DNDM_EINVAL, "empty batch");
+    if (n_lig + n_pocket > e->cfg.max_nodes || n_samples > e->cfg.max_samples)
+        return set_err(DNDM_ECAPACITY, "batch (%d nodes, %d samples) exceeds engine capacity (%d, %d)", n_lig + n_pocket,
+                       n_samples, e->cfg.max_nodes, e->cfg.max_samples);
+    {
+        const int n = n_lig > n_samples + 1 ? n_lig : n_samples + 1;
+        mask_to_ptr_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(lig_mask), n_lig, n_samples,
+                                                            e->lig_ptr, e->node_sample);
+    }
+    {
+        const int n = n_pocket > n_samples + 1 ? n_pocket : n_samples + 1;
+        mask_to_ptr_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(pocket_mask), n_pocket,
+                                                            n_samples, e->pok_ptr, e->node_sample + n_lig);
+    }
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
+static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, cudaStream_t st) {
+    GraphParams gp;
+    gp.x = x; gp.lig_ptr = e->lig_ptr; gp.pok_ptr = e->pok_ptr; gp.node_sample = e->node_sample;
+    gp.n_lig = n_lig; gp.n_nodes = n_nodes;
+    auto sq = [](float c) { return c < 0.f ? -1.f : c * c; };
+    gp.cut2_l = sq(e->cfg.edge_cutoff_ligand); gp.cut2_p = sq(e->cfg.edge_cutoff_pocket);
+    gp.cut2_i = sq(e->cfg.edge_cutoff_interaction);
+    const int blocks = (n_nodes * 32 + 255) / 256;
+    graph_rows_kernel<false><<<blocks, 256, 0, st>>>(gp, e->deg, nullptr, nullptr, nullptr, nullptr, e->cfg.max_edges);
+    graph_scan_kernel<<<1, 1024, 0, st>>>(e->deg, e->row_ptr, n_nodes, n_lig, e->cfg.max_edges, e->scalars, e->flags);
+    graph_rows_kernel<true><<<blocks, 256, 0, st>>>(gp, nullptr, e->row_ptr, e->ecol, e->erow, e->r0, e->cfg.max_edges);
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float* xh_pocket, const float* t, int32_t t_len,
+                                 const int64_t* lig_mask, const int64_t* pocket_mask, int32_t n_lig, int32_t n_pocket,
+                                 int32_t n_samples, float* out_lig, float* out_pocket, void* stream) {
+    if (!e || !xh_lig || !t || !lig_mask || !out_lig || (n_pocket > 0 && (!xh_pocket || !pocket_mask)))
+        return set_err(DNDM_EINVAL, "null argument");
+    if (!e->weights_loaded) return set_err(DNDM_EWEIGHTS, "dndm_engine_load_weights has not been called");
+    if (t_len != 1 && t_len != n_samples) return set_err(DNDM_EINVAL, "t_len must be 1 or n_samples");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    RET_IF(prepare_batch(e, lig_mask, pocket_mask, n_lig, n_pocket, n_samples, st));
+    const int N = n_lig + n_pocket;
+    const int A = e->cfg.atom_nf, R = e->cfg.residue_nf;
+    const int node_blocks = (N * 32 + 255) / 256;
+
+    encode_embed_kernel<<<node_blocks, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len, e->node_sample,
+                                                     e->enc_l, e->enc_p, e->x0, e->xa, e->xb, e->h, e->hcat);
+    pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, st>>>(e->x0, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
+    RET_IF(build_graph(e, e->x0, n_lig, N, st));
+
+    float* x_cur = e->xa;
+    float* x_next = e->xb;
+    const float inv_norm = 1.0f / e->cfg.normalization_factor;
+
+    auto proj_e = [&](int l) -> int {
+        GemmEpilogue ep{e->layers[l].bias_e, 0, nullptr, 0, e->pq, 1536, nullptr, 0};
+        return launch_gemm(st, e->tm_hcat, e->layers[l].tm_proj_e, N, 512, 256, 0, ep);
+    };
+    RET_IF(proj_e(0));
+    for (int l = 0; l < e->cfg.n_layers; ++l) {
+        LayerWeights& L = e->layers[l];
+        // ---- GCL edge model + attention + deterministic aggregation ----
+        EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->agg, e->tile_head};
+        EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
+        edge_mlp_kernel<true><<<dim3(e->num_sms, 1), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_e, L.tm_w2_e, L.c_e, L.c_e, g,
+                                                                                      pe, pe);
+        agg_finalize_kernel<<<node_blocks, 256, 0, st>>>(e->agg, e->tile_head, e->row_ptr, N, e->hcat);
+        // ---- node MLP with residual ----
+        {
+            GemmEpilogue ep1{L.b3, 1, nullptr, 0, nullptr, 0, e->hid, 256};
+            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_w3, N, 256, 512, 0, ep1));
+            GemmEpilogue ep2{L.b4, 0, e->h, 256, e->h, 256, e->hcat, 512};
+            RET_IF(launch_gemm(st, e->tm_hid, L.tm_w4, N, 256, 256, 0, ep2));
+        }
+        // ---- node projections for this block's coordinate heads and the next block's edge model ----
+        {
+            GemmEpilogue ep{L.bias_c, 0, nullptr, 0, e->pq + 512, 1536, nullptr, 0};
+            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, N, 1024, 256, 0, ep));
+        }
+        if (l + 1 < e->cfg.n_layers) RET_IF(proj_e(l + 1));
+        // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
+        {
+            EdgeGraph gh{e->erow, e->ecol, e->r0, x_cur, e->scalars + 1, 1536, nullptr, nullptr};
+            EdgeProblem pc{e->pq + 512, e->pq + 1024, L.w1e_c, e->phi, 0.f, e->cfg.coords_range};
+            EdgeProblem px{e->pq + 768, e->pq + 1280, L.w1e_x, e->psi, 0.f, e->cfg.coords_range};
+            const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
+            edge_mlp_kernel<false><<<dim3(gx, 2), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_c, L.tm_w2_x, L.c_c, L.c_x, gh, pc,
+                                                                                   px);
+            coord_update_kernel<<<(n_lig * 32 + 255) / 256, 256, 0, st>>>(x_cur, x_next, e->row_ptr, e->ecol, e->phi, e->psi,
+                                                                          e->node_sample, e->lig_ptr, e->pok_ptr,
+                                                                          e->pocket_sum, n_lig, e->cfg.norm_constant, inv_norm);
+            float* tmp = x_cur; x_cur = x_next; x_next = tmp;
+        }
+        if (e->h_trace && N <= e->max_trace_nodes)
+            CU_CHECK(cudaMemcpyAsync(e->h_trace + (size_t)l * e->max_trace_nodes * 256, e->h, (size_t)N * 256 * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+        if (e->x_trace && N <= e->max_trace_nodes)
+            CU_CHECK(cudaMemcpyAsync(e->x_trace + (size_t)l * e->max_trace_nodes * 3, x_cur, (size_t)N * 3 * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+        CU_CHECK(cudaGetLastError());
+    }
+    // ---- embedding_out + decoders + velocity ----
+    {
+        const int n_out = out_pocket ? N : n_lig;
+        decode_kernel<<<(n_out * 32 + 255) / 256, 256, 0, st>>>(e->h, x_cur, e->x0, n_lig, n_out, 0, e->dec_l, e->dec_p, out_lig,
+                                                                out_pocket, e->flags);
+    }
+    CU_CHECK(cudaGetLastError());
+    e->last_n_lig = n_lig;
+    e->last_n_nodes = N;
+    e->x_final = x_cur;
+    return DNDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// radius graph on its own
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_xyz_kernel(const float* xh_lig, const float* xh_pok, int n_lig, int n_nodes, int ld_lig, int ld_pok,
+                                  float* x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes * 3) return;
+    const int node = i / 3, d = i % 3;
+    x[i] = node < n_lig ? xh_lig[(size_t)node * ld_lig + d] : xh_pok[(size_t)(node - n_lig) * ld_pok + d];
+}
+
+extern "C" int dndm_radius_graph(DndmEngine* e, const float* xh_lig, const float* xh_pocket, const int64_t* lig_mask,
+                                 const int64_t* pocket_mask, int32_t n_lig, int32_t n_pocket, int32_t n_samples,
+                                 int32_t* row_ptr, int32_t* col, int32_t edge_capacity, int32_t* n_edges_host, void* stream) {
+    if (!e || !xh_lig || !lig_mask) return set_err(DNDM_EINVAL, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    RET_IF(prepare_batch(e, lig_mask, pocket_mask, n_lig, n_pocket, n_samples, st));
+    const int N = n_lig + n_pocket;
+    gather_xyz_kernel<<<(N * 3 + 255) / 256, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + e->cfg.atom_nf, 3 + e->cfg.residue_nf,
+                                                           e->x0);
+    RET_IF(build_graph(e, e->x0, n_lig, N, st));
+    int sc[2] = {0, 0};
+    CU_CHECK(cudaMemcpyAsync(sc, e->scalars, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (n_edges_host) *n_edges_host = sc[0];
+    if (row_ptr) CU_CHECK(cudaMemcpyAsync(row_ptr, e->row_ptr, (size_t)(N + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    if (col) {
+        const int n = sc[0] < edge_capacity ? sc[0] : edge_capacity;
+        CU_CHECK(cudaMemcpyAsync(col, e->ecol, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    e->last_n_lig = n_lig;
+    e->last_n_nodes = N;
+    return DNDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler step
+// ------------------------------------------------------------------------------------------------
+extern "C" int dndm_sampler_step(DndmEngine* e, const float* z_in, const float* eps, const float* noise,
+                                 const float* xh_pocket_in, const float* coef, const float* grad, float lambda,
+                                 const int64_t* lig_mask, const int64_t* pocket_mask, int32_t n_lig, int32_t n_pocket,
+                                 int32_t n_samples, float* z_out, float* xh_pocket_out, void* stream) {
+    if (!e || !z_in || !noise || !coef || !lig_mask || !z_out) return set_err(DNDM_EINVAL, "null argument");
+    if (e->cfg.atom_nf != e->cfg.residue_nf) return set_err(DNDM_EINVAL, "sampler step requires atom_nf == residue_nf");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    RET_IF(prepare_batch(e, lig_mask, pocket_mask, n_lig, n_pocket, n_samples, st));
+    sampler_step_kernel<<<n_samples, 128, 0, st>>>(z_in, eps ? eps : noise, noise, xh_pocket_in, coef, grad, lambda, e->lig_ptr,
+                                                   e->pok_ptr, e->cfg.atom_nf, z_out, xh_pocket_out, e->flags);
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
+extern "C" int dndm_read_flags(DndmEngine* e, uint32_t* flags_host, void* stream) {
+    if (!e || !flags_host) return set_err(DNDM_EINVAL, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CU_CHECK(cudaMemcpyAsync(flags_host, e->flags, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemsetAsync(e->flags, 0, 4, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    return DNDM_OK;
+}
+
+extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64_t dst_bytes, void* stream) {
+    if (!e || !dst) return set_err(DNDM_EINVAL, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const void* src = nullptr;
+    int64_t bytes = 0;
+    const int64_t N = e->last_n_nodes;
+    switch (what) {
+        case 0: src = e->h; bytes = N * 256 * 4; break;
+        case 1: src = e->x_final ? e->x_final : e->x0; bytes = N * 3 * 4; break;
+        case 2: src = e->row_ptr; bytes = (N + 1) * 4; break;
+        case 3: {
+            int sc[2];
+            CU_CHECK(cudaMemcpyAsync(sc, e->scalars, 8, cudaMemcpyDeviceToHost, st));
+            CU_CHECK(cudaStreamSynchronize(st));
+            src = e->ecol; bytes = (int64_t)sc[0] * 4;
+            break;
+        }
+        case 4: src = e->scalars; bytes = 8; break;
+        default: return set_err(DNDM_EINVAL, "unknown buffer id %d", what);
+    }
+    if (bytes > dst_bytes) bytes = dst_bytes;
+    CU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+    return bytes;
+}
+
+extern "C" int dndm_set_trace(DndmEngine* e, float* h_trace, float* x_trace, int32_t max_trace_nodes) {
+    if (!e) return set_err(DNDM_EINVAL, "null argument");
+    e->h_trace = h_trace; e->x_trace = x_trace; e->max_trace_nodes = max_trace_nodes;
+    return DNDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM self-test
+// ------------------------------------------------------------------------------------------------
+extern "C" int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const float* bias, int32_t act, int32_t M, int32_t N,
+                              int32_t K, float* out, void* stream) {
+    if (!a_bf16 || !w_bf16 || !out) return set_err(DNDM_EINVAL, "null argument");
+    if (K % GEMM_BK != 0 || N % GEMM_BN != 0 || M < 1) return set_err(DNDM_EINVAL, "need K %% 64 == 0 and N %% 128 == 0");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ta, tw;
+    RET_IF(make_tmap_bf16(&ta, a_bf16, M, K, K, GEMM_BM));
+    RET_IF(make_tmap_bf16(&tw, w_bf16, N, K, K, GEMM_BN));
+    CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    GemmEpilogue ep{bias, act, nullptr, 0, out, N, nullptr, 0};
+    return launch_gemm(st, ta, tw, M, N, K, 0, ep);
+}

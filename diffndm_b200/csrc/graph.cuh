@@ -1,0 +1,139 @@
+// Radius graph of EGNNDynamics.get_edges (dynamics.py:169-187) as receiver-sorted CSR.
+//
+// Node order is the reference's: all ligand atoms (sample-major), then all pocket atoms.  Row i lists, in
+// ascending global index, the same-sample ligand atoms passing the ligand rule followed by the same-sample
+// pocket atoms passing the pocket / interaction rule -- exactly the order torch.where() yields on the block
+// adjacency, self loops included.  Distance decisions use fp32 direct differences with one rounding per
+// operation ((dx*dx + dy*dy) + dz*dz <= cutoff^2), the arithmetic the oracle pins (oracle/egnn_oracle.py:pair_d2).
+//
+// v1 scans all same-sample candidates per row (warp per row, ballot compaction keeps the order for free);
+// a sample is at most ~750 atoms so this is ~25 candidate chunks per row.
+#pragma once
+#include "common.cuh"
+
+namespace dndm {
+
+struct GraphParams {
+    const float* x;          // [N,3]  (ligand rows first)
+    const int* lig_ptr;      // [B+1]
+    const int* pok_ptr;      // [B+1]
+    const int* node_sample;  // [N]
+    int n_lig, n_nodes;
+    float cut2_l, cut2_p, cut2_i;   // squared cutoffs; negative = no cutoff (fully connected within sample)
+};
+
+DNDM_DEVICE float dist2_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// One warp per row.  kFill=false: deg[i] = number of neighbours.  kFill=true: write col / erow / r0.
+template <bool kFill>
+__global__ void __launch_bounds__(256)
+graph_rows_kernel(GraphParams p, int* deg, const int* row_ptr, int* ecol, int* erow, float* r0, int max_edges) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.n_nodes) return;
+    const int i = warp;
+    const int b = p.node_sample[i];
+    const bool i_lig = i < p.n_lig;
+    const float xi = p.x[3 * i], yi = p.x[3 * i + 1], zi = p.x[3 * i + 2];
+    int out = kFill ? row_ptr[i] : 0;
+    int count = 0;
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+        const int beg = part == 0 ? p.lig_ptr[b] : p.n_lig + p.pok_ptr[b];
+        const int end = part == 0 ? p.lig_ptr[b + 1] : p.n_lig + p.pok_ptr[b + 1];
+        const float cut2 = part == 0 ? (i_lig ? p.cut2_l : p.cut2_i) : (i_lig ? p.cut2_i : p.cut2_p);
+        for (int j0 = beg; j0 < end; j0 += 32) {
+            const int j = j0 + lane;
+            bool ok = false;
+            float d2 = 0.f;
+            if (j < end) {
+                d2 = dist2_rn(xi, yi, zi, p.x[3 * j], p.x[3 * j + 1], p.x[3 * j + 2]);
+                ok = (cut2 < 0.f) || (d2 <= cut2);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (kFill) {
+                if (ok) {
+                    const int pos = out + __popc(m & ((1u << lane) - 1u));
+                    if (pos < max_edges) {
+                        ecol[pos] = j;
+                        erow[pos] = i;
+                        r0[pos] = d2;
+                    }
+                }
+                out += __popc(m);
+            } else {
+                count += __popc(m);
+            }
+        }
+    }
+    if (!kFill && lane == 0) deg[i] = count;
+}
+
+// Exclusive scan of deg[0..n) -> row_ptr[0..n], single CTA (n is ~1e4..1e5).  Also publishes
+// scalars[0] = E, scalars[1] = E_lig = row_ptr[n_lig] and raises flag bit 2 when E exceeds capacity.
+__global__ void __launch_bounds__(1024)
+graph_scan_kernel(const int* deg, int* row_ptr, int n, int n_lig, int max_edges, int* scalars, unsigned* flags) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int beg = min(tid * per, n), end = min(beg + per, n);
+    int s = 0;
+    for (int i = beg; i < end; ++i) s += deg[i];
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_sums[lane] = wi - w;     // exclusive
+        if (lane == 31) carry = wi;
+    }
+    __syncthreads();
+    int run = warp_sums[warp] + incl - s;
+    for (int i = beg; i < end; ++i) {
+        row_ptr[i] = run;
+        run += deg[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int E = carry;
+        row_ptr[n] = E;
+        scalars[0] = min(E, max_edges);
+        if (E > max_edges) atomicOr(flags, 4u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // E_lig = row_ptr[n_lig]; all row_ptr entries were written above by this CTA
+        scalars[1] = min(n_lig < n ? row_ptr[n_lig] : carry, max_edges);
+    }
+}
+
+// Per-sample start offsets from a sorted int64 batch mask (utils.py:145-153 layout) + int32 sample id per node.
+__global__ void mask_to_ptr_kernel(const long long* mask, int n, int n_samples, int* ptr, int* node_sample) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_samples) {
+        int lo = 0, hi = n;      // first index with mask[idx] >= i
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (mask[mid] < (long long)i) lo = mid + 1; else hi = mid;
+        }
+        ptr[i] = lo;
+    }
+    if (i < n) node_sample[i] = (int)mask[i];
+}
+
+}  // namespace dndm

@@ -1,0 +1,308 @@
+// Node-side kernels of the denoiser: encoder+embedding, aggregation finalize, coordinate update,
+// output embedding+decoder, and the fused p(z_s | z_t) sampler step.
+#pragma once
+#include "common.cuh"
+
+namespace dndm {
+
+// ------------------------------------------------------------------------------------------------
+// (a3) atom/residue encoder + time channel + EGNN embedding  (dynamics.py:89-111, egnn_new.py:233)
+//   h = W_emb [enc2(SiLU(enc1(h_in))) ; t] + b_emb  with the two linear maps around the 128-d joint space
+//   pre-composed on the host: h = Wc2 s + w_t t + bc,  s = SiLU(W1 h_in + b1) in R^20.
+// Also assembles x = [x_lig ; x_pocket] (both coordinate buffers) -- one warp per node.
+// ------------------------------------------------------------------------------------------------
+struct EncoderWeights {
+    const float* w1;    // [hid, nf]
+    const float* b1;    // [hid]
+    const float* wc2;   // [256, hid]   = W_emb[:, :J] W_enc2
+    const float* bc;    // [256]        = W_emb[:, :J] b_enc2 + b_emb
+    const float* wt;    // [256]        = W_emb[:, J]
+    int nf, hid;
+};
+
+__global__ void __launch_bounds__(256)
+encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ xh_pok, int n_lig, int n_nodes,
+                    int ld_lig, int ld_pok, const float* __restrict__ t, int t_len, const int* __restrict__ node_sample,
+                    EncoderWeights wl, EncoderWeights wp, float* __restrict__ x0, float* __restrict__ xa,
+                    float* __restrict__ xb, float* __restrict__ h, __nv_bfloat16* __restrict__ hcat) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (node >= n_nodes) return;
+    const bool is_lig = node < n_lig;
+    const float* src = is_lig ? xh_lig + (size_t)node * ld_lig : xh_pok + (size_t)(node - n_lig) * ld_pok;
+    const EncoderWeights& w = is_lig ? wl : wp;
+    if (lane < 3) {
+        const float c = src[lane];
+        x0[3 * node + lane] = c;
+        xa[3 * node + lane] = c;
+        xb[3 * node + lane] = c;
+    }
+    // hidden layer: lane j < hid computes s_j
+    float s = 0.f;
+    if (lane < w.hid) {
+        float a = w.b1[lane];
+        for (int k = 0; k < w.nf; ++k) a = fmaf(w.w1[lane * w.nf + k], src[3 + k], a);
+        s = silu_f(a);
+    }
+    const float tv = t[t_len == 1 ? 0 : node_sample[node]];
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = 64 * i + 2 * lane;
+        o[2 * i] = fmaf(w.wt[k], tv, w.bc[k]);
+        o[2 * i + 1] = fmaf(w.wt[k + 1], tv, w.bc[k + 1]);
+    }
+    for (int j = 0; j < w.hid; ++j) {
+        const float sj = __shfl_sync(0xffffffffu, s, j);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = 64 * i + 2 * lane;
+            o[2 * i] = fmaf(w.wc2[k * w.hid + j], sj, o[2 * i]);
+            o[2 * i + 1] = fmaf(w.wc2[(k + 1) * w.hid + j], sj, o[2 * i + 1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = 64 * i + 2 * lane;
+        *reinterpret_cast<float2*>(h + (size_t)node * 256 + k) = make_float2(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<uint32_t*>(hcat + (size_t)node * 512 + k) = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (a8) finish the deterministic segment sum: add, in tile order, the leading partials of receivers whose
+// edge range crosses 128-edge tile boundaries, and emit the bf16 operand [h | agg] of the node MLP.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+agg_finalize_kernel(const float* __restrict__ agg, const float* __restrict__ tile_head, const int* __restrict__ row_ptr,
+                    int n_nodes, __nv_bfloat16* __restrict__ hcat) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (node >= n_nodes) return;
+    const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (e1 > e0) {
+        const float* ap = agg + (size_t)node * 256 + 8 * lane;
+        a = *reinterpret_cast<const float4*>(ap);
+        b = *reinterpret_cast<const float4*>(ap + 4);
+        const int t0 = e0 >> 7, t1 = (e1 - 1) >> 7;
+        for (int t = t0 + 1; t <= t1; ++t) {
+            const float* hp = tile_head + (size_t)t * 256 + 8 * lane;
+            const float4 c = *reinterpret_cast<const float4*>(hp);
+            const float4 d = *reinterpret_cast<const float4*>(hp + 4);
+            a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+            b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+        }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(hcat + (size_t)node * 512 + 256 + 8 * lane) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (a5,a7) coordinate update of the ligand atoms (pocket atoms are frozen: update_coords_mask, dynamics.py:130-132)
+//   x_i += sum_j ( n_ij phi_ij + c_ij psi_ij ) / norm       egnn_new.py:96-123, coord2diff :296-302, coord2cross :305-316
+// One warp per ligand atom; lanes stride the CSR row, fixed-order shuffle reduction (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+coord_update_kernel(const float* __restrict__ x_cur, float* __restrict__ x_next, const int* __restrict__ row_ptr,
+                    const int* __restrict__ ecol, const float* __restrict__ phi, const float* __restrict__ psi,
+                    const int* __restrict__ node_sample, const int* __restrict__ lig_ptr, const int* __restrict__ pok_ptr,
+                    const float* __restrict__ pocket_sum, int n_lig, float norm_constant, float inv_norm) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_lig) return;
+    const int b = node_sample[i];
+    // per-sample mean over ligand + pocket atoms of the CURRENT coordinates (coord2cross)
+    const int l0 = lig_ptr[b], l1 = lig_ptr[b + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int j = l0 + lane; j < l1; j += 32) {
+        sx += x_cur[3 * j]; sy += x_cur[3 * j + 1]; sz += x_cur[3 * j + 2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    const float cnt = (float)((l1 - l0) + (pok_ptr[b + 1] - pok_ptr[b]));
+    const float mx = (sx + pocket_sum[3 * b]) / cnt, my = (sy + pocket_sum[3 * b + 1]) / cnt,
+                mz = (sz + pocket_sum[3 * b + 2]) / cnt;
+    const float xi = x_cur[3 * i], yi = x_cur[3 * i + 1], zi = x_cur[3 * i + 2];
+    const float ax = xi - mx, ay = yi - my, az = zi - mz;
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
+    for (int e = e0 + lane; e < e1; e += 32) {
+        const int j = ecol[e];
+        const float xj = x_cur[3 * j], yj = x_cur[3 * j + 1], zj = x_cur[3 * j + 2];
+        const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
+        const float r = dx * dx + dy * dy + dz * dz;
+        const float inv = 1.0f / (sqrtf(r + 1e-8f) + norm_constant);
+        const float bx = xj - mx, by = yj - my, bz = zj - mz;
+        float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+        const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + norm_constant);
+        const float f = phi[e] * inv, gq = psi[e] * cinv;
+        tx += dx * f + cx * gq;
+        ty += dy * f + cy * gq;
+        tz += dz * f + cz * gq;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tx += __shfl_xor_sync(0xffffffffu, tx, o);
+        ty += __shfl_xor_sync(0xffffffffu, ty, o);
+        tz += __shfl_xor_sync(0xffffffffu, tz, o);
+    }
+    if (lane == 0) {
+        x_next[3 * i] = xi + tx * inv_norm;
+        x_next[3 * i + 1] = yi + ty * inv_norm;
+        x_next[3 * i + 2] = zi + tz * inv_norm;
+    }
+}
+
+// per-sample sum of the (frozen) pocket coordinates, one warp per sample, fixed order
+__global__ void pocket_sum_kernel(const float* __restrict__ x, const int* __restrict__ pok_ptr, int n_lig, int n_samples,
+                                  float* __restrict__ pocket_sum) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= n_samples) return;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int j = n_lig + pok_ptr[b] + lane; j < n_lig + pok_ptr[b + 1]; j += 32) {
+        sx += x[3 * j]; sy += x[3 * j + 1]; sz += x[3 * j + 2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    if (lane == 0) {
+        pocket_sum[3 * b] = sx; pocket_sum[3 * b + 1] = sy; pocket_sum[3 * b + 2] = sz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (a3,a4 tail) embedding_out + decoder + velocity  (egnn_new.py:241, dynamics.py:136-167)
+//   out_h = W2 SiLU(Wc h + bc) + b2 with Wc = W_dec0 W_out[:J], bc = W_dec0 b_out[:J] + b_dec0 pre-composed;
+//   out_x = x_final - x_in (ligand) / exactly 0 (pocket).  NaN in the velocity raises flag bit 0.
+// ------------------------------------------------------------------------------------------------
+struct DecoderWeights {
+    const float* wc;    // [hid, 256]
+    const float* bc;    // [hid]
+    const float* w2;    // [nf, hid]
+    const float* b2;    // [nf]
+    int nf, hid;
+};
+
+__global__ void __launch_bounds__(256)
+decode_kernel(const float* __restrict__ h, const float* __restrict__ x_final, const float* __restrict__ x0, int n_lig,
+              int n_nodes, int first_node, DecoderWeights wl, DecoderWeights wp, float* __restrict__ out_lig,
+              float* __restrict__ out_pok, unsigned* __restrict__ flags) {
+    const int node = first_node + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (node >= n_nodes) return;
+    const bool is_lig = node < n_lig;
+    const DecoderWeights& w = is_lig ? wl : wp;
+    float hv[8];
+    {
+        const float4 a = *reinterpret_cast<const float4*>(h + (size_t)node * 256 + 4 * lane);
+        const float4 b = *reinterpret_cast<const float4*>(h + (size_t)node * 256 + 128 + 4 * lane);
+        hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
+    }
+    float s = 0.f;     // lane j keeps hidden unit j
+    for (int j = 0; j < w.hid; ++j) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w.wc + (size_t)j * 256 + 4 * lane));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(w.wc + (size_t)j * 256 + 128 + 4 * lane));
+        float d = a.x * hv[0] + a.y * hv[1] + a.z * hv[2] + a.w * hv[3] + b.x * hv[4] + b.y * hv[5] + b.z * hv[6] +
+                  b.w * hv[7];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == j) s = silu_f(d + w.bc[j]);
+    }
+    float* dst = is_lig ? out_lig + (size_t)node * (3 + w.nf) : out_pok + (size_t)(node - n_lig) * (3 + w.nf);
+    float o = 0.f;
+    for (int j = 0; j < w.hid; ++j) {
+        const float sj = __shfl_sync(0xffffffffu, s, j);
+        if (lane < w.nf) o = fmaf(w.w2[lane * w.hid + j], sj, o);
+    }
+    if (lane < w.nf) dst[3 + lane] = o + w.b2[lane];
+    if (lane < 3) {
+        const float v = is_lig ? (x_final[3 * node + lane] - x0[3 * node + lane]) : 0.f;
+        if (v != v) atomicOr(flags, 1u);
+        dst[lane] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (a9,a10) fused sampler step  (conditional_model.py:483-540, 165-186, 1793-1801)
+//   mode 0: z_s = z_t * c_z[b] - c_eps[b] * eps + c_noise[b] * xi        p(z_s | z_t)
+//           (c_z = 1/alpha_ts, c_eps = sigma2_ts/alpha_ts/sigma_t, c_noise = sigma_ts sigma_s / sigma_t)
+//   then the per-sample LIGAND centre of mass of the new coordinates is removed from ligand AND pocket.
+//   An optional guidance term  + lambda * grad  (SPSA, :801-806) is applied to the coordinates before the
+//   projection.  One CTA per sample; fixed-order reductions.  |COM| drift of the INPUT z_t relative to its
+//   largest coordinate above 1e-2 raises flag bit 1 (assert_mean_zero_with_mask, en_diffusion.py:930-935).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sampler_step_kernel(const float* z_t, const float* eps, const float* noise, const float* xh_pok_in,
+                    const float* __restrict__ coef /*[B][3]*/, const float* grad /*[N_l][3] or null*/, float lambda,
+                    const int* __restrict__ lig_ptr, const int* __restrict__ pok_ptr, int nf, float* z_out,
+                    float* xh_pok_out, unsigned* flags) {   // z_out / xh_pok_out may alias the inputs (in place)
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int D = 3 + nf;
+    const int l0 = lig_ptr[b], l1 = lig_ptr[b + 1];
+    const float cz = coef[3 * b], ce = coef[3 * b + 1], cn = coef[3 * b + 2];
+    __shared__ float red[4][128];
+    __shared__ float com[3];
+    float s[3] = {0.f, 0.f, 0.f}, si[3] = {0.f, 0.f, 0.f}, mx = 0.f;
+    for (int i = l0 + tid; i < l1; i += blockDim.x) {
+        for (int d = 0; d < D; ++d) {
+            const size_t o = (size_t)i * D + d;
+            const float zin = z_t[o];
+            float v = zin * cz - ce * eps[o] + cn * noise[o];
+            if (d < 3) {
+                if (grad) v += lambda * grad[3 * i + d];
+                s[d] += v;
+                si[d] += zin;
+                mx = fmaxf(mx, fabsf(zin));
+            }
+            z_out[o] = v;
+        }
+    }
+    red[0][tid] = s[0]; red[1][tid] = s[1]; red[2][tid] = s[2];
+    __syncthreads();
+    if (tid < 3) {
+        float a = 0.f;
+        for (int k = 0; k < (int)blockDim.x; ++k) a += red[tid][k];
+        com[tid] = a / (float)(l1 - l0);
+    }
+    __syncthreads();
+    // COM-drift check of the input (reference asserts on z_t after the step)
+    red[0][tid] = si[0]; red[1][tid] = si[1]; red[2][tid] = si[2]; red[3][tid] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, m = 0.f;
+        for (int k = 0; k < (int)blockDim.x; ++k) {
+            a0 += red[0][k]; a1 += red[1][k]; a2 += red[2][k]; m = fmaxf(m, red[3][k]);
+        }
+        const float err = fmaxf(fabsf(a0), fmaxf(fabsf(a1), fabsf(a2)));
+        if (err / (m + 1e-10f) >= 1e-2f) atomicOr(flags, 2u);
+    }
+    const float c0 = com[0], c1 = com[1], c2 = com[2];
+    for (int i = l0 + tid; i < l1; i += blockDim.x) {
+        z_out[(size_t)i * D] -= c0;
+        z_out[(size_t)i * D + 1] -= c1;
+        z_out[(size_t)i * D + 2] -= c2;
+    }
+    const int p0 = pok_ptr[b], p1 = pok_ptr[b + 1];
+    for (int i = p0 + tid; i < p1; i += blockDim.x) {
+        const size_t o = (size_t)i * D;
+        xh_pok_out[o] = xh_pok_in[o] - c0;
+        xh_pok_out[o + 1] = xh_pok_in[o + 1] - c1;
+        xh_pok_out[o + 2] = xh_pok_in[o + 2] - c2;
+        if (xh_pok_out != xh_pok_in)
+            for (int d = 3; d < D; ++d) xh_pok_out[o + d] = xh_pok_in[o + d];
+    }
+}
+
+}  // namespace dndm
