@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ligands/sec for 500-step fullatom_cond conditional sampling (BASELINE.json).
+
+A *step* is one pass of the hot path over one batch: one reverse-diffusion step = EGNN denoiser forward
+(radius graph + 6 equivariant blocks) + fused p(z_s|z_t) update, for one synthetic CrossDocked-shaped pocket
+replicated over B ligands (configs[1] of BASELINE.json: 100 ligands per pocket, pockets sharded over GPUs; rank r
+works on pocket r).  A 500-step trajectory makes 501 denoiser calls, so
+
+    value [ligands/s] = n_gpus * B / (501 * seconds_per_step)
+
+`value` is measured with the state resident in HBM and the step captured in a CUDA graph; `e2e` runs the same step
+through the public Python API with HOST (pinned) buffers, copying the step inputs H2D and the result D2H inside the
+timed region.  `roofline` times the dominant kernel (fused GCL edge kernel) with CUDA events in an eager pass over
+the same inputs.  `cpu_baseline` / `--impl reference` time the numpy oracle (a restatement of the reference's PyTorch
+CPU path; the reference itself cannot travel to the GPU box) on the host cores on a bounded sample.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STEPS = 500
+CALLS_PER_TRAJ = T_STEPS + 1
+EXEC_FLOP_PER_EDGE_GCL = 2 * 256 * 256                     # second edge-MLP layer, the GEMM the kernel runs
+REF_FLOP_PER_EDGE_GCL = 2 * 514 * 256 + 2 * 256 * 256 + 512  # reference formulation of the same MLP
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=100, help='ligands per pocket (BASELINE configs[1]: 100)')
+    ap.add_argument('--cpu-batch', type=int, default=8, help='ligands in the bounded CPU sample')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def make_inputs(rank, batch):
+    from diffndm_b200 import synthetic
+    px, pt = synthetic.synthetic_pocket(rank)
+    sizes = synthetic.synthetic_ligand_sizes(rank, batch)
+    return px, pt, sizes, synthetic.make_batch(px, pt, sizes, rank)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_step_seconds(batch, n_steps, warmup, rank=0):
+    from oracle import egnn_oracle as O
+    from diffndm_b200.weights import DynamicsConfig, random_init
+    W = random_init(DynamicsConfig(), 0, 0.3)
+    px, pt, sizes, b = make_inputs(rank, batch)
+    cfg = O.OracleConfig()
+    g = O.gamma_table(T_STEPS, cfg.noise_precision, 2.0)
+    rng = np.random.default_rng(0)
+    z, xp = b['xh_lig'], b['xh_pocket']
+    times = []
+    s = T_STEPS - 1
+    for i in range(warmup + n_steps):
+        t0 = time.perf_counter()
+        tt = np.full((batch, 1), (s + 1) / T_STEPS, np.float32)
+        eps, _ = O.dynamics_forward(W, z, xp, tt, b['lig_mask'], b['pocket_mask'], cfg)
+        noise = rng.standard_normal(z.shape).astype(np.float32)
+        z, xp = O.sample_p_zs_given_zt(z, xp, eps, noise, np.full(batch, g[s]), np.full(batch, g[s + 1]),
+                                       b['lig_mask'], b['pocket_mask'])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        s = max(s - 1, 0)
+    return float(np.mean(times)), len(b['pocket_mask']) // batch
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    sec, n_p = cpu_step_seconds(args.cpu_batch, args.steps, min(args.warmup, 2))
+    val = args.cpu_batch / (CALLS_PER_TRAJ * sec)
+    sample = (f'{args.steps} denoising steps (numpy oracle forward + p(z_s|z_t)) on {args.cpu_batch} ligands of the same '
+              f'synthetic pocket ({n_p} atoms); per-step cost scaled to 501 calls per trajectory')
+    line = {
+        'impl': 'reference', 'metric': 'ligands/sec (500-step fullatom_cond sampling)', 'value': val, 'unit': 'ligands/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.batch),
+        'cpu_baseline': {'value': val, 'unit': 'ligands/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'ligands/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch):
+    return {'workload': f'crossdocked_fullatom_cond conditional sampling, synthetic CrossDocked-shaped pockets x {batch} '
+                        f'ligands, {T_STEPS} steps (BASELINE configs[1]); one pocket per GPU, random-init weights',
+            'ligands_per_pocket': batch, 'timesteps': T_STEPS,
+            'l2': 'per-step working set (node projections + activations) exceeds the 126 MB L2; no explicit flush'}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for l in self.proc.stdout:
+            self.lines.append((time.time(), l.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, l in self.lines:
+            p = [x.strip() for x in l.split(',')]
+            if len(p) < 7:
+                continue
+            try:
+                smax = float(p[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(p[0]))
+                    for n, v in zip(names, p[3:7]):
+                        if v.lower().startswith('active'):
+                            reasons.add(n)
+            except ValueError:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from diffndm_b200 import engine as E
+    from diffndm_b200.sampler import ConditionalSampler
+    from diffndm_b200.weights import DynamicsConfig, random_init
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    B = args.batch
+    px, pt, sizes, b = make_inputs(rank, B)
+    n_l, n_p = len(b['lig_mask']), len(b['pocket_mask'])
+    N = n_l + n_p
+    cfg = DynamicsConfig()
+    dyn = E.B200EGNNDynamics(cfg, random_init(cfg, 0, 0.3), max_nodes=N + 256, max_edges=int(N * 40) + 4096,
+                             max_samples=B, check_nan=False)
+    dyn.compute_pocket_output = False            # every conditional caller discards it (`eps, _ =`)
+    eng = dyn.engine
+    smp = ConditionalSampler(dyn, timesteps=T_STEPS)
+
+    # per-step scalars for every s (device tables): t, coefficients
+    gam = smp.gamma
+    coef_tab = smp.step_coefficients(gam[:-1], gam[1:]).to(dev)                 # [T,3]  step s -> s+1
+    t_tab = (torch.arange(1, T_STEPS + 1, dtype=torch.float32) / T_STEPS).to(dev)  # t of step s
+
+    z0 = torch.from_numpy(b['xh_lig']).to(dev)
+    p0 = torch.from_numpy(b['xh_pocket']).to(dev)
+    lig_mask = torch.from_numpy(b['lig_mask']).to(dev)
+    pocket_mask = torch.from_numpy(b['pocket_mask']).to(dev)
+    z, xp = z0.clone(), p0.clone()
+    t_buf = torch.zeros(B, 1, device=dev)
+    coef_buf = torch.zeros(B, 3, device=dev)
+    eps = torch.zeros_like(z)
+    noise = torch.zeros_like(z)
+
+    def body():
+        noise.normal_()
+        eng.forward(z, xp, t_buf, lig_mask, pocket_mask, B, out_lig=eps, want_pocket=False)
+        eng.sampler_step(z, eps, noise, xp, coef_buf, lig_mask, pocket_mask, B, z_out=z, pocket_out=xp)
+
+    def set_step(s):
+        t_buf.copy_(t_tab[s].expand(B, 1))
+        coef_buf.copy_(coef_tab[s].expand(B, 3))
+
+    graph = None
+    l0 = E.launch_count()
+    set_step(T_STEPS - 1)
+    body()                                   # eager warm-up (also sizes torch's caches)
+    torch.cuda.synchronize()
+    launches_per_step = E.launch_count() - l0
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+
+    def step(s):
+        set_step(s)
+        if graph is not None:
+            graph.replay()
+        else:
+            body()
+
+    def reset():
+        z.copy_(z0)
+        xp.copy_(p0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then EXACTLY K timed steps of a real trajectory (s = T-1, T-2, ...) ----
+    reset()
+    s = T_STEPS - 1
+    for _ in range(max(args.warmup, 3)):
+        step(s)
+        s = max(s - 1, 0)
+    barrier()
+    clocks = ClockSampler(local)
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step(s)
+        s = max(s - 1, 0)
+    e1.record()
+    barrier()
+    w1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop(w0, w1)
+    flags = eng.read_flags()
+    if flags & (E.FLAG_EDGE_OVERFLOW | E.FLAG_NAN):
+        raise RuntimeError(f'engine flags {flags} during the timed region')
+    E_edges, E_lig = eng.graph_stats()
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = tmax.item() / args.steps
+    value = world * B / (CALLS_PER_TRAJ * ms_per_step * 1e-3)
+
+    # ---- roofline: the dominant kernel, CUDA events around every launch, eager pass over the same state ----
+    roof = None
+    prof = None
+    if rank == 0:
+        eng.set_profile(True)
+        s2 = max(s, 0)
+        n_prof = min(args.steps, 20)
+        for _ in range(n_prof):
+            set_step(s2)
+            body()
+            s2 = max(s2 - 1, 0)
+        prof = eng.get_profile()
+        eng.set_profile(False)
+        g_ms, g_n = prof['gcl_edge_kernel']
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = peaks.get('bf16_tflops_sustained')
+        peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+        if peak is None:
+            peak, peak_src = 1590.0, 'fallback (B200_PROFILING.md)'
+        t_launch = g_ms / max(g_n, 1) * 1e-3
+        achieved = E_edges * EXEC_FLOP_PER_EDGE_GCL / t_launch / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'edge_mlp_kernel<GCL>', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'us_per_launch': t_launch * 1e6, 'edges_per_launch': E_edges,
+                'flop_per_edge_executed': EXEC_FLOP_PER_EDGE_GCL,
+                'achieved_reference_equivalent': E_edges * REF_FLOP_PER_EDGE_GCL / t_launch / 1e12,
+                'step_share_ms': {k: v[0] / n_prof for k, v in prof.items()}}
+
+    # ---- e2e: same step through the public API with HOST buffers (H2D of the step inputs, D2H of the result) ----
+    e2e = None
+    if not args.no_e2e:
+        hz = z0.cpu().pin_memory()
+        hp = p0.cpu().pin_memory()
+        hm_l, hm_p = lig_mask.cpu().pin_memory(), pocket_mask.cpu().pin_memory()
+        hout = torch.empty_like(hz).pin_memory()
+        ht = torch.zeros(B, 1).pin_memory()
+        hc = torch.zeros(B, 3).pin_memory()
+        coef_cpu, t_cpu = coef_tab.cpu(), t_tab.cpu()
+        n_e2e = min(args.steps, 50)
+
+        def e2e_step(s):
+            ht.copy_(t_cpu[s].expand(B, 1))
+            hc.copy_(coef_cpu[s].expand(B, 3))
+            dz = hz.to(dev, non_blocking=True)
+            dp = hp.to(dev, non_blocking=True)
+            dt_ = ht.to(dev, non_blocking=True)
+            dc = hc.to(dev, non_blocking=True)
+            dml = hm_l.to(dev, non_blocking=True)
+            dmp = hm_p.to(dev, non_blocking=True)
+            e_, _ = dyn(dz, dp, dt_, dml, dmp, n_samples=B)
+            nz = torch.randn_like(dz)
+            zo, po = eng.sampler_step(dz, e_, nz, dp, dc, dml, dmp, B)
+            hout.copy_(zo, non_blocking=True)
+            hp.copy_(po, non_blocking=True)
+            torch.cuda.synchronize()
+            hz.copy_(hout)
+
+        s3 = T_STEPS - 1
+        for _ in range(3):
+            e2e_step(s3)
+            s3 -= 1
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_e2e):
+            e2e_step(s3)
+            s3 = max(s3 - 1, 0)
+        a1.record()
+        barrier()
+        t_e2e = torch.tensor([a0.elapsed_time(a1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        ms_e2e = t_e2e.item() / n_e2e
+        h2d = hz.numel() * 4 + p0.numel() * 4 + B * 4 * 4 + (n_l + n_p) * 8
+        d2h = hz.numel() * 4 + p0.numel() * 4
+        e2e = {'value': world * B / (CALLS_PER_TRAJ * ms_e2e * 1e-3), 'unit': 'ligands/s', 'h2d_bytes_per_step': int(h2d),
+               'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms_e2e, 'steps': n_e2e}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, _ = cpu_step_seconds(args.cpu_batch, 6, 1)
+        cpu = {'value': args.cpu_batch / (CALLS_PER_TRAJ * sec), 'unit': 'ligands/s', 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': f'6 denoising steps of the numpy oracle on {args.cpu_batch} ligands of the rank-0 pocket '
+                         f'({n_p // B} atoms), {sec:.2f} s/step, scaled to 501 calls per trajectory'}
+
+    if rank == 0:
+        cfgd = workload_config(B)
+        cfgd.update({'pocket_atoms_rank0': n_p // B, 'ligand_atoms_rank0': n_l, 'nodes': N, 'edges': E_edges,
+                     'ligand_receiver_edges': E_lig, 'cuda_graph': graph is not None})
+        line = {
+            'metric': 'ligands/sec (500-step fullatom_cond sampling)', 'value': value, 'unit': 'ligands/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': cfgd, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps),
+            'gpu_launches_per_step': int(launches_per_step), 'roofline': roof, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

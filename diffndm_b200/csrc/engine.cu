@@ -21,6 +21,8 @@ using namespace dndm;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+static long long g_launches = 0;   // kernels of this library launched (or captured) so far
+#define COUNT_LAUNCH(n) (g_launches += (n))
 static int set_err(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -101,6 +103,32 @@ struct DndmEngine {
     // trace
     float *h_trace = nullptr, *x_trace = nullptr;
     int max_trace_nodes = 0;
+    // per-section CUDA-event profiling (off by default; never used under graph capture)
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Section { int cat; cudaEvent_t a, b; };
+    std::vector<Section> sections;
+    size_t ev_used = 0;
+};
+
+enum { PROF_GCL = 0, PROF_HEAD = 1, PROF_GEMM = 2, PROF_GRAPH = 3, PROF_NODE = 4, PROF_NCAT = 5 };
+
+static cudaEvent_t prof_event(DndmEngine* e) {
+    if (e->ev_used == e->ev_pool.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->ev_pool.push_back(ev);
+    }
+    return e->ev_pool[e->ev_used++];
+}
+struct ProfScope {
+    DndmEngine* e; cudaStream_t st; cudaEvent_t a, b; int cat; bool on;
+    ProfScope(DndmEngine* e_, int cat_, cudaStream_t st_) : e(e_), st(st_), cat(cat_), on(e_->profile) {
+        if (on) { a = prof_event(e); b = prof_event(e); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(b, st); e->sections.push_back({cat, a, b}); }
+    }
 };
 
 template <class T>
@@ -116,6 +144,7 @@ static int dev_alloc(T** p, size_t n) {
 
 extern "C" const char* dndm_version(void) { return "diffndm_b200 0.1 (sm_100a, tcgen05/TMA)"; }
 extern "C" const char* dndm_last_error(void) { return g_err; }
+extern "C" int64_t dndm_launch_count(void) { return g_launches; }
 
 extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     if (!cfg || !out) return set_err(DNDM_EINVAL, "null argument");
@@ -165,6 +194,7 @@ static void free_weights(DndmEngine* e) {
 extern "C" void dndm_engine_destroy(DndmEngine* e) {
     if (!e) return;
     free_weights(e);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->agg, e->tile_head, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
                     e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->flags};
     for (void* p : bufs) cudaFree(p);
@@ -349,6 +379,7 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
     if (M <= 0) return DNDM_OK;
     dim3 grid((M + GEMM_BM - 1) / GEMM_BM, Nout / GEMM_BN);
     gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tw, M, K, a_col0, ep);
+    COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
 }
@@ -369,6 +400,7 @@ static int prepare_batch(DndmEngine* e, const int64_t* lig_mask, const int64_t* 
         mask_to_ptr_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(pocket_mask), n_pocket,
                                                             n_samples, e->pok_ptr, e->node_sample + n_lig);
     }
+    COUNT_LAUNCH(2);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
 }
@@ -384,6 +416,7 @@ static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, cu
     graph_rows_kernel<false><<<blocks, 256, 0, st>>>(gp, e->deg, nullptr, nullptr, nullptr, nullptr, e->cfg.max_edges);
     graph_scan_kernel<<<1, 1024, 0, st>>>(e->deg, e->row_ptr, n_nodes, n_lig, e->cfg.max_edges, e->scalars, e->flags);
     graph_rows_kernel<true><<<blocks, 256, 0, st>>>(gp, nullptr, e->row_ptr, e->ecol, e->erow, e->r0, e->cfg.max_edges);
+    COUNT_LAUNCH(3);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
 }
@@ -404,16 +437,24 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     const int A = e->cfg.atom_nf, R = e->cfg.residue_nf;
     const int node_blocks = (N * 32 + 255) / 256;
 
-    encode_embed_kernel<<<node_blocks, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len, e->node_sample,
-                                                     e->enc_l, e->enc_p, e->x0, e->xa, e->xb, e->h, e->hcat);
-    pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, st>>>(e->x0, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
-    RET_IF(build_graph(e, e->x0, n_lig, N, st));
+    {
+        ProfScope ps(e, PROF_NODE, st);
+        encode_embed_kernel<<<node_blocks, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len, e->node_sample,
+                                                         e->enc_l, e->enc_p, e->x0, e->xa, e->xb, e->h, e->hcat);
+        pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, st>>>(e->x0, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
+        COUNT_LAUNCH(2);
+    }
+    {
+        ProfScope ps(e, PROF_GRAPH, st);
+        RET_IF(build_graph(e, e->x0, n_lig, N, st));
+    }
 
     float* x_cur = e->xa;
     float* x_next = e->xb;
     const float inv_norm = 1.0f / e->cfg.normalization_factor;
 
     auto proj_e = [&](int l) -> int {
+        ProfScope ps(e, PROF_GEMM, st);
         GemmEpilogue ep{e->layers[l].bias_e, 0, nullptr, 0, e->pq, 1536, nullptr, 0};
         return launch_gemm(st, e->tm_hcat, e->layers[l].tm_proj_e, N, 512, 256, 0, ep);
     };
@@ -423,11 +464,19 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         // ---- GCL edge model + attention + deterministic aggregation ----
         EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->agg, e->tile_head};
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
-        edge_mlp_kernel<true><<<dim3(e->num_sms, 1), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_e, L.tm_w2_e, L.c_e, L.c_e, g,
-                                                                                      pe, pe);
-        agg_finalize_kernel<<<node_blocks, 256, 0, st>>>(e->agg, e->tile_head, e->row_ptr, N, e->hcat);
+        {
+            ProfScope ps(e, PROF_GCL, st);
+            edge_mlp_kernel<true><<<dim3(e->num_sms, 1), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_e, L.tm_w2_e, L.c_e, L.c_e,
+                                                                                          g, pe, pe);
+        }
+        {
+            ProfScope ps(e, PROF_NODE, st);
+            agg_finalize_kernel<<<node_blocks, 256, 0, st>>>(e->agg, e->tile_head, e->row_ptr, N, e->hcat);
+        }
+        COUNT_LAUNCH(2);
         // ---- node MLP with residual ----
         {
+            ProfScope ps(e, PROF_GEMM, st);
             GemmEpilogue ep1{L.b3, 1, nullptr, 0, nullptr, 0, e->hid, 256};
             RET_IF(launch_gemm(st, e->tm_hcat, L.tm_w3, N, 256, 512, 0, ep1));
             GemmEpilogue ep2{L.b4, 0, e->h, 256, e->h, 256, e->hcat, 512};
@@ -435,6 +484,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         }
         // ---- node projections for this block's coordinate heads and the next block's edge model ----
         {
+            ProfScope ps(e, PROF_GEMM, st);
             GemmEpilogue ep{L.bias_c, 0, nullptr, 0, e->pq + 512, 1536, nullptr, 0};
             RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, N, 1024, 256, 0, ep));
         }
@@ -445,11 +495,16 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             EdgeProblem pc{e->pq + 512, e->pq + 1024, L.w1e_c, e->phi, 0.f, e->cfg.coords_range};
             EdgeProblem px{e->pq + 768, e->pq + 1280, L.w1e_x, e->psi, 0.f, e->cfg.coords_range};
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
-            edge_mlp_kernel<false><<<dim3(gx, 2), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_c, L.tm_w2_x, L.c_c, L.c_x, gh, pc,
-                                                                                   px);
+            {
+                ProfScope ps(e, PROF_HEAD, st);
+                edge_mlp_kernel<false><<<dim3(gx, 2), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_c, L.tm_w2_x, L.c_c, L.c_x, gh,
+                                                                                       pc, px);
+            }
+            ProfScope ps2(e, PROF_NODE, st);
             coord_update_kernel<<<(n_lig * 32 + 255) / 256, 256, 0, st>>>(x_cur, x_next, e->row_ptr, e->ecol, e->phi, e->psi,
                                                                           e->node_sample, e->lig_ptr, e->pok_ptr,
                                                                           e->pocket_sum, n_lig, e->cfg.norm_constant, inv_norm);
+            COUNT_LAUNCH(2);
             float* tmp = x_cur; x_cur = x_next; x_next = tmp;
         }
         if (e->h_trace && N <= e->max_trace_nodes)
@@ -463,8 +518,10 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     // ---- embedding_out + decoders + velocity ----
     {
         const int n_out = out_pocket ? N : n_lig;
+        ProfScope ps(e, PROF_NODE, st);
         decode_kernel<<<(n_out * 32 + 255) / 256, 256, 0, st>>>(e->h, x_cur, e->x0, n_lig, n_out, 0, e->dec_l, e->dec_p, out_lig,
                                                                 out_pocket, e->flags);
+        COUNT_LAUNCH(1);
     }
     CU_CHECK(cudaGetLastError());
     e->last_n_lig = n_lig;
@@ -493,6 +550,7 @@ extern "C" int dndm_radius_graph(DndmEngine* e, const float* xh_lig, const float
     const int N = n_lig + n_pocket;
     gather_xyz_kernel<<<(N * 3 + 255) / 256, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + e->cfg.atom_nf, 3 + e->cfg.residue_nf,
                                                            e->x0);
+    COUNT_LAUNCH(1);
     RET_IF(build_graph(e, e->x0, n_lig, N, st));
     int sc[2] = {0, 0};
     CU_CHECK(cudaMemcpyAsync(sc, e->scalars, 8, cudaMemcpyDeviceToHost, st));
@@ -521,6 +579,7 @@ extern "C" int dndm_sampler_step(DndmEngine* e, const float* z_in, const float* 
     RET_IF(prepare_batch(e, lig_mask, pocket_mask, n_lig, n_pocket, n_samples, st));
     sampler_step_kernel<<<n_samples, 128, 0, st>>>(z_in, eps ? eps : noise, noise, xh_pocket_in, coef, grad, lambda, e->lig_ptr,
                                                    e->pok_ptr, e->cfg.atom_nf, z_out, xh_pocket_out, e->flags);
+    COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
 }
@@ -557,6 +616,28 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
     if (bytes > dst_bytes) bytes = dst_bytes;
     CU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
     return bytes;
+}
+
+extern "C" int dndm_set_profile(DndmEngine* e, int32_t on) {
+    if (!e) return set_err(DNDM_EINVAL, "null argument");
+    e->profile = on != 0;
+    e->sections.clear();
+    e->ev_used = 0;
+    return DNDM_OK;
+}
+
+extern "C" int dndm_get_profile(DndmEngine* e, double* ms_per_category, int32_t* launches_per_category, int32_t n_cat) {
+    if (!e || !ms_per_category || !launches_per_category) return set_err(DNDM_EINVAL, "null argument");
+    CU_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < n_cat; ++i) { ms_per_category[i] = 0.0; launches_per_category[i] = 0; }
+    for (auto& s : e->sections) {
+        float ms = 0.f;
+        CU_CHECK(cudaEventElapsedTime(&ms, s.a, s.b));
+        if (s.cat < n_cat) { ms_per_category[s.cat] += ms; launches_per_category[s.cat] += 1; }
+    }
+    e->sections.clear();
+    e->ev_used = 0;
+    return DNDM_OK;
 }
 
 extern "C" int dndm_set_trace(DndmEngine* e, float* h_trace, float* x_trace, int32_t max_trace_nodes) {

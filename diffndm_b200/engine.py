@@ -26,9 +26,9 @@ FLAG_COM_DRIFT = 2
 FLAG_EDGE_OVERFLOW = 4
 
 EXPORTED_SYMBOLS = [
-    'dndm_version', 'dndm_last_error', 'dndm_engine_create', 'dndm_engine_destroy', 'dndm_engine_load_weights',
+    'dndm_version', 'dndm_last_error', 'dndm_launch_count', 'dndm_engine_create', 'dndm_engine_destroy', 'dndm_engine_load_weights',
     'dndm_egnn_forward', 'dndm_radius_graph', 'dndm_sampler_step', 'dndm_read_flags', 'dndm_debug_copy',
-    'dndm_set_trace', 'dndm_test_gemm',
+    'dndm_set_trace', 'dndm_set_profile', 'dndm_get_profile', 'dndm_test_gemm',
 ]
 
 
@@ -64,6 +64,7 @@ def load_library() -> ctypes.CDLL:
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
     lib.dndm_version.restype = ctypes.c_char_p
     lib.dndm_last_error.restype = ctypes.c_char_p
+    lib.dndm_launch_count.restype = ctypes.c_int64
     lib.dndm_engine_create.argtypes = [ctypes.POINTER(DndmConfig), ctypes.POINTER(vp)]
     lib.dndm_engine_destroy.argtypes = [vp]
     lib.dndm_engine_destroy.restype = None
@@ -75,6 +76,8 @@ def load_library() -> ctypes.CDLL:
     lib.dndm_debug_copy.argtypes = [vp, i32, vp, i64, vp]
     lib.dndm_debug_copy.restype = i64
     lib.dndm_set_trace.argtypes = [vp, vp, vp, i32]
+    lib.dndm_set_profile.argtypes = [vp, i32]
+    lib.dndm_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32), i32]
     lib.dndm_test_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     _lib = lib
     return lib
@@ -225,12 +228,30 @@ class Engine:
         self._trace = None
         self.lib.dndm_set_trace(self._h, None, None, 0)
 
+    PROFILE_CATEGORIES = ('gcl_edge_kernel', 'head_edge_kernel', 'node_gemm', 'radius_graph', 'node_other')
+
+    def set_profile(self, on: bool):
+        _check(self.lib, self.lib.dndm_set_profile(self._h, int(on)), 'dndm_set_profile')
+
+    def get_profile(self):
+        """{category: (total_ms, timed_sections)} since the last call (synchronises the device)."""
+        n = len(self.PROFILE_CATEGORIES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int32 * n)()
+        _check(self.lib, self.lib.dndm_get_profile(self._h, ms, cnt, n), 'dndm_get_profile')
+        return {c: (ms[i], cnt[i]) for i, c in enumerate(self.PROFILE_CATEGORIES)}
+
     def graph_stats(self):
         """(E, E_ligand_receiver) of the last forward / radius_graph call (synchronises)."""
         t = torch.zeros(2, dtype=torch.int32, device=torch.device('cuda', self.device))
         _check(self.lib, self.lib.dndm_debug_copy(self._h, 4, _ptr(t), 8, _stream()), 'dndm_debug_copy')
         e, el = t.cpu().tolist()
         return e, el
+
+
+def launch_count() -> int:
+    """Kernels of libdiffndm_b200 launched (or captured) by this process so far."""
+    return int(load_library().dndm_launch_count())
 
 
 def test_gemm(a_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0):

@@ -1,0 +1,285 @@
+"""Host-side mirror of the reference sampler surface around the CUDA denoiser.
+
+Mirrors (names, argument meaning, outputs) the parts of ``ConditionalDDPM`` (reference
+equivariant_diffusion/conditional_model.py) that sit on the hot path:
+
+* ``sample_p_zs_given_zt``      (:483-540)   one reverse-diffusion step
+* ``sample_p_xh_given_z0``      (:136-160)   final p(x, h | z_0) head
+* ``my_to_x0``                  (:457-468)   x0 look-ahead used by SPSA / ATP
+* ``my_update_z_lig``           (:760-813)   SPSA guidance, with the 2k perturbed copies batched into two
+                                             denoiser calls instead of 4k sequential ones
+* ``sample_given_pocket``       (:886-1489)  the sampling loop (plain / SPSA / ATP)
+
+Loop control, schedule scalars and reward bookkeeping stay Python; every tensor operation is a call into the
+C-ABI engine (``dndm_egnn_forward`` + ``dndm_sampler_step``).  Host chemistry (RDKit / OpenBabel scoring)
+stays outside: guidance takes a ``reward_fn(x_lig, atom_types, lig_mask) -> list[float]`` callable, exactly the
+role ``handle_to_mol`` + ``my_reward_for_SPSA`` / ``my_reward_for_SVDD`` play in the reference.
+
+The reference's per-step host syncs (``.item()`` in assert_mean_zero_with_mask, ``empty_cache()``) are replaced
+by sticky device flags checked once per trajectory (or per step with ``check_every_step=True``).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .engine import B200EGNNDynamics, FLAG_COM_DRIFT, FLAG_EDGE_OVERFLOW, FLAG_NAN
+
+
+def _clip_noise_schedule(alphas2, clip_value=0.001):
+    alphas2 = np.concatenate([np.ones(1), alphas2], axis=0)
+    alphas_step = np.clip(alphas2[1:] / alphas2[:-1], a_min=clip_value, a_max=1.)
+    return np.cumprod(alphas_step, axis=0)
+
+
+def polynomial_gamma(timesteps: int, precision: float, power: float) -> torch.Tensor:
+    """gamma[T+1] of PredefinedNoiseSchedule('polynomial_<power>') -- en_diffusion.py:1146-1191."""
+    steps = timesteps + 1
+    x = np.linspace(0, steps, steps)
+    alphas2 = (1 - np.power(x / steps, power)) ** 2
+    alphas2 = _clip_noise_schedule(alphas2, clip_value=0.001)
+    alphas2 = (1 - 2 * precision) * alphas2 + precision
+    sigmas2 = 1 - alphas2
+    return torch.from_numpy(-(np.log(alphas2) - np.log(sigmas2))).float()
+
+
+class ConditionalSampler:
+    """Sampler over a ``B200EGNNDynamics``; all state lives on the GPU."""
+
+    def __init__(self, dynamics: B200EGNNDynamics, timesteps: int = 500, noise_schedule: str = 'polynomial_2',
+                 noise_precision: float = 5.0e-4, norm_values=(1.0, 4.0), norm_biases=(None, 0.0),
+                 check_every_step: bool = False):
+        assert not dynamics.update_pocket_coords           # conditional_model.py:24
+        self.dynamics = dynamics
+        self.engine = dynamics.engine
+        self.T = timesteps
+        self.n_dims = 3
+        self.atom_nf = dynamics.cfg.atom_nf
+        self.norm_values = norm_values
+        self.norm_biases = norm_biases
+        self.check_every_step = check_every_step
+        assert noise_schedule.startswith('polynomial_')
+        self.gamma = polynomial_gamma(timesteps, noise_precision, float(noise_schedule.split('_')[1]))   # CPU fp32
+        self.device = torch.device('cuda', self.engine.device)
+        self._build_tables()
+
+    # -- schedule scalars (en_diffusion.py:83-108, 870-883), same torch fp32 ops as the reference, once ----------
+    def _build_tables(self):
+        g = self.gamma
+        sig = lambda gm: torch.sqrt(torch.sigmoid(gm))
+        alp = lambda gm: torch.sqrt(torch.sigmoid(-gm))
+        self.sigma_tab = sig(g)
+        self.alpha_tab = alp(g)
+        self.gamma_dev = g.to(self.device)
+
+    def lookup(self, t: torch.Tensor) -> torch.Tensor:
+        """gamma(t) with t in [0,1] -- PredefinedNoiseSchedule.forward, en_diffusion.py:1193-1195 (CPU table)."""
+        return self.gamma[torch.round(t.detach().cpu().float() * self.T).long().reshape(-1)]
+
+    def step_coefficients(self, gamma_s: torch.Tensor, gamma_t: torch.Tensor) -> torch.Tensor:
+        """[B,3] = (1/alpha_ts, sigma2_ts/alpha_ts/sigma_t, sigma_ts*sigma_s/sigma_t) -- conditional_model.py:486-529."""
+        sigma2_ts = -torch.expm1(F.softplus(gamma_s) - F.softplus(gamma_t))
+        alpha_ts = torch.exp(0.5 * (F.logsigmoid(-gamma_t) - F.logsigmoid(-gamma_s)))
+        sigma_ts = torch.sqrt(sigma2_ts)
+        sigma_s = torch.sqrt(torch.sigmoid(gamma_s))
+        sigma_t = torch.sqrt(torch.sigmoid(gamma_t))
+        return torch.stack([1.0 / alpha_ts, sigma2_ts / alpha_ts / sigma_t, sigma_ts * sigma_s / sigma_t], dim=1)
+
+    # -- elementary moves -------------------------------------------------------------------------------------------
+    def _noise(self, n, noise=None):
+        if noise is not None:
+            return noise.to(self.device, torch.float32)
+        return torch.randn((n, self.n_dims + self.atom_nf), device=self.device)    # sample_gaussian, en_diffusion.py:957-960
+
+    def sample_p_zs_given_zt(self, s, t, zt_lig, xh0_pocket, ligand_mask, pocket_mask, noise=None, n_samples=None):
+        """conditional_model.py:483-540 (optimize=0; AdjustNet is training-only and off the sampling path)."""
+        B = int(n_samples if n_samples is not None else t.numel())
+        coef = self.step_coefficients(self.lookup(s), self.lookup(t)).to(self.device)
+        eps, _ = self.dynamics(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, n_samples=B)
+        zs, xp = self.engine.sampler_step(zt_lig, eps, self._noise(len(ligand_mask), noise), xh0_pocket, coef,
+                                          ligand_mask, pocket_mask, B)
+        if self.check_every_step:
+            self._raise_on_flags()
+        return zs, xp
+
+    def sample_p_xh_given_z0(self, z0_lig, xh0_pocket, lig_mask, pocket_mask, batch_size, noise=None):
+        """conditional_model.py:136-160.  Returns x_lig, one-hot h_lig (int64), x_pocket, h_pocket."""
+        B = int(batch_size)
+        t0 = torch.zeros((B, 1), device=self.device)
+        g0 = self.lookup(t0)
+        eps0, _ = self.dynamics(z0_lig, xh0_pocket, t0, lig_mask, pocket_mask, n_samples=B)
+        sigma_x = torch.exp(0.5 * g0)                                   # SNR(-0.5 gamma_0)
+        sigma0, alpha0 = torch.sqrt(torch.sigmoid(g0)), torch.sqrt(torch.sigmoid(-g0))
+        coef = torch.stack([1.0 / alpha0, sigma0 / alpha0, sigma_x], dim=1).to(self.device)   # compute_x_pred
+        xh, xp = self.engine.sampler_step(z0_lig, eps0, self._noise(len(lig_mask), noise), xh0_pocket, coef, lig_mask,
+                                          pocket_mask, B)
+        x_lig = xh[:, :3] * self.norm_values[0]
+        h_lig = z0_lig[:, 3:] * self.norm_values[1] + self.norm_biases[1]
+        x_pocket = xp[:, :3] * self.norm_values[0]
+        h_pocket = xp[:, 3:] * self.norm_values[1] + self.norm_biases[1]
+        h_lig = F.one_hot(torch.argmax(h_lig, dim=1), self.atom_nf)
+        return x_lig, h_lig, x_pocket, h_pocket
+
+    def my_to_x0(self, t, zt_lig, xh0_pocket, ligand_mask, pocket_mask, n_samples, noise=None):
+        """conditional_model.py:457-468: x0 look-ahead (two denoiser calls)."""
+        B = int(n_samples)
+        eps_t, _ = self.dynamics(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, n_samples=B)
+        gt = self.lookup(t)
+        alpha_t = torch.exp(0.5 * F.logsigmoid(-gt)).to(self.device)
+        sigma_t = torch.sqrt(torch.sigmoid(gt)).to(self.device)
+        z0 = (zt_lig - sigma_t[ligand_mask][:, None] * eps_t) / alpha_t[ligand_mask][:, None]
+        return self.sample_p_xh_given_z0(z0, xh0_pocket, ligand_mask, pocket_mask, B, noise=noise)
+
+    def remove_mean_batch(self, x_lig, x_pocket, lig_mask, pocket_mask, n_samples):
+        """conditional_model.py:1793-1801 through the fused kernel (coef = identity)."""
+        B = int(n_samples)
+        z = torch.zeros((x_lig.shape[0], 3 + self.atom_nf), device=self.device)
+        z[:, :3] = x_lig
+        p = torch.zeros((x_pocket.shape[0], 3 + self.atom_nf), device=self.device)
+        p[:, :3] = x_pocket
+        coef = torch.tensor([[1.0, 0.0, 0.0]], device=self.device).repeat(B, 1)
+        zo, po = self.engine.sampler_step(z, None, z, p, coef, lig_mask, pocket_mask, B)
+        return zo[:, :3], po[:, :3]
+
+    def _raise_on_flags(self):
+        flags = self.engine.read_flags()
+        if flags & FLAG_EDGE_OVERFLOW:
+            raise RuntimeError('diffndm_b200: edge capacity exceeded (raise max_edges)')
+        if flags & FLAG_NAN:
+            raise ValueError("NaN detected in EGNN output")                       # dynamics.py:155-159
+        if flags & FLAG_COM_DRIFT:
+            raise AssertionError('Mean is not zero')                              # en_diffusion.py:930-935
+
+    # -- SPSA (conditional_model.py:724-813), 2k perturbed copies batched -------------------------------------------
+    def my_update_z_lig(self, z_lig, xh_pocket, lig_mask, pocket_mask, t_array, n_samples, zeta, reward_fn,
+                        guidance_scale=1e-3, k=10, perturbations=None, x0_noise=None):
+        """Symmetric finite-difference guidance.  The reference runs 2k x my_to_x0 sequentially (:764-800); here the
+        2k copies are concatenated along the batch axis: ONE denoiser call at t and ONE at t=0 on 2k*B samples.
+        ``perturbations`` [k, N_l, 3] / ``x0_noise`` [2k, N_l, 13] may be injected for parity tests."""
+        B, n_l, n_p = int(n_samples), z_lig.shape[0], xh_pocket.shape[0]
+        sizes = torch.bincount(lig_mask, minlength=B)
+        if perturbations is None:                                                   # my_perturbation_for_molecule :724-736
+            noise = torch.randn((k, n_l, 3), device=self.device)
+            mean = torch.zeros((k, B, 3), device=self.device).index_add_(1, lig_mask, noise) / sizes[None, :, None]
+            perturbations = zeta * (noise - mean[:, lig_mask])
+        U = perturbations.to(self.device)
+        reps = 2 * k
+        z_rep = z_lig.unsqueeze(0).repeat(reps, 1, 1)
+        z_rep[:k, :, :3] += U
+        z_rep[k:, :, :3] -= U
+        offs = (torch.arange(reps, device=self.device) * B)
+        big_lig_mask = (lig_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
+        big_pocket_mask = (pocket_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
+        big_pocket = xh_pocket.unsqueeze(0).repeat(reps, 1, 1).reshape(reps * n_p, -1)
+        big_t = t_array.to(self.device).reshape(1, B, 1).repeat(reps, 1, 1).reshape(reps * B, 1)
+        nz = None if x0_noise is None else x0_noise.reshape(reps * n_l, -1)
+        x_l, h_l, _, _ = self.my_to_x0(big_t, z_rep.reshape(reps * n_l, -1), big_pocket, big_lig_mask, big_pocket_mask,
+                                       reps * B, noise=nz)
+        rewards = torch.as_tensor(reward_fn(x_l, h_l.argmax(1), big_lig_mask), dtype=torch.float32,
+                                  device=self.device).reshape(reps, B)
+        f_plus, f_minus = rewards[:k], rewards[k:]
+        dd = (f_plus - f_minus) / (2 * 1e-4)                                         # hard-coded divisor, :799
+        grad = (dd[:, lig_mask, None] * U).mean(0)                                   # :749-758, :801
+        # x += guidance_scale * grad ; COM removal for ligand and pocket  (:803-812)
+        coef = torch.tensor([[1.0, 0.0, 0.0]], device=self.device).repeat(B, 1)
+        return self.engine.sampler_step(z_lig, None, z_lig, xh_pocket, coef, lig_mask, pocket_mask, B, grad=grad,
+                                        lam=float(guidance_scale))
+
+    def _unnormalize_quirk(self, z_lig, xh_pocket, lig_mask, pocket_mask, B):
+        """The reference rescales features by norm_values[1] after every SPSA / ATP event
+        (conditional_model.py:1235-1240, 1253-1258) -- reproduced, not fixed."""
+        z = z_lig.clone()
+        p = xh_pocket.clone()
+        z[:, 3:] = z[:, 3:] * self.norm_values[1] + self.norm_biases[1]
+        p[:, 3:] = p[:, 3:] * self.norm_values[1] + self.norm_biases[1]
+        z[:, :3], p[:, :3] = self.remove_mean_batch(z[:, :3] * self.norm_values[0], p[:, :3] * self.norm_values[0],
+                                                    lig_mask, pocket_mask, B)
+        return z, p
+
+    # -- the sampling loop -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample_given_pocket(self, pocket, num_nodes_lig, timesteps: Optional[int] = None, svdd: int = 0, spsa: int = 0,
+                            reward_fn: Optional[Callable] = None, noise: Optional[torch.Tensor] = None,
+                            spsa_schedule=(30, 2), svdd_schedule=(50, 10), svdd_groups: int = 5, spsa_k: int = 10):
+        """ConditionalDDPM.sample_given_pocket (conditional_model.py:886-1489) without the host chemistry arguments.
+
+        ``pocket``: dict with 'x' [N_p,3], 'one_hot' [N_p,residue_nf], 'size' [B], 'mask' [N_p] (prepare_pocket layout,
+        lightning_modules.py:763-801).  ``noise`` [timesteps+2, N_l, 13] injects the Gaussian draws in the reference's
+        order (z_T, one per step, final head) -- only valid for the unguided path.
+        Returns (xh_lig [N_l, 3+atom_nf] with one-hot features, xh_pocket, lig_mask, pocket_mask) like the reference.
+        """
+        timesteps = self.T if timesteps is None else timesteps
+        dev = self.device
+        B = len(pocket['size'])
+        x_p = pocket['x'].to(dev, torch.float32) / self.norm_values[0]
+        h_p = (pocket['one_hot'].to(dev).float() - self.norm_biases[1]) / self.norm_values[1]
+        pocket_mask = pocket['mask'].to(dev).long()
+        xh0_pocket = torch.cat([x_p, h_p], dim=1).contiguous()
+        sizes = torch.as_tensor(num_nodes_lig, device=dev).long()
+        lig_mask = torch.repeat_interleave(torch.arange(B, device=dev), sizes)          # utils.py:145-153
+        n_l = int(lig_mask.numel())
+        # z_T ~ N(pocket COM, I), projected to the ligand-COM-free subspace (:923-930)
+        cnt = torch.bincount(pocket_mask, minlength=B).clamp(min=1).float()
+        mu_x = torch.zeros((B, 3), device=dev).index_add_(0, pocket_mask, x_p) / cnt[:, None]
+        mu = torch.cat([mu_x, torch.zeros((B, self.atom_nf), device=dev)], dim=1)[lig_mask].contiguous()
+        ident = torch.tensor([[1.0, 0.0, 1.0]], device=dev).repeat(B, 1)
+        z_lig, xh_pocket = self.engine.sampler_step(mu, None, self._noise(n_l, None if noise is None else noise[0]),
+                                                    xh0_pocket, ident, lig_mask, pocket_mask, B)
+        step = 0
+        for s in reversed(range(0, timesteps)):
+            s_array = torch.full((B, 1), fill_value=s, dtype=torch.float32) / timesteps
+            t_array = torch.full((B, 1), fill_value=s + 1, dtype=torch.float32) / timesteps
+            step += 1
+            z_lig, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
+                                                         noise=None if noise is None else noise[step], n_samples=B)
+            if svdd == 1 and s <= svdd_schedule[0] and s % svdd_schedule[1] == 0:
+                z_lig, xh_pocket, lig_mask = self._atp_event(s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
+                                                             B, reward_fn, svdd_groups)
+                z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+            if spsa == 1 and s <= spsa_schedule[0] and s % spsa_schedule[1] == 0:
+                zeta = 1e-3 * (s / 500)                                                   # :1244-1245
+                z_lig, xh_pocket = self.my_update_z_lig(z_lig, xh_pocket, lig_mask, pocket_mask, t_array, B, zeta,
+                                                        reward_fn, guidance_scale=1e-3, k=spsa_k)
+                z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+        x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(
+            z_lig, xh_pocket, lig_mask, pocket_mask, B, noise=None if noise is None else noise[timesteps + 1])
+        self._raise_on_flags()
+        # CoG drift correction (:1431-1438)
+        cog = torch.zeros((B, 3), device=dev).index_add_(0, lig_mask, x_lig).abs().max().item()
+        if cog > 5e-2:
+            x_lig, x_pocket = self.remove_mean_batch(x_lig, x_pocket, lig_mask, pocket_mask, B)
+        return torch.cat([x_lig, h_lig.float()], dim=1), torch.cat([x_pocket, h_pocket], dim=1), lig_mask, pocket_mask
+
+    # -- ATP ("SVDD") event, conditional_model.py:1085-1241 -------------------------------------------------------------
+    def _atp_event(self, s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask, B, reward_fn, n_groups):
+        """Draw n_groups-1 extra candidate next-states from (z, s, t), score the current and x0-look-ahead molecules of
+        all n_groups*B candidates, keep the global top-B (:1203-1232).  The candidate groups are evaluated as ONE batch of
+        n_groups*B samples per denoiser call instead of the reference's sequential calls."""
+        dev = self.device
+        n_l, n_p = z_lig.shape[0], xh_pocket.shape[0]
+        G = n_groups
+        offs = torch.arange(G, device=dev) * B
+        big_lig_mask = (lig_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
+        big_pocket_mask = (pocket_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
+        rep = lambda a, n: a.unsqueeze(0).repeat(n, 1, 1).reshape(n * a.shape[0], -1)
+        # extra candidates: sample_p_zs_given_zt from the same (already denoised) state, :1109-1117
+        zs_extra, xp_extra = self.sample_p_zs_given_zt(
+            s_array.repeat(G - 1, 1), t_array.repeat(G - 1, 1), rep(z_lig, G - 1), rep(xh_pocket, G - 1),
+            big_lig_mask[:(G - 1) * n_l], big_pocket_mask[:(G - 1) * n_p], n_samples=(G - 1) * B)
+        big_z = torch.cat([z_lig, zs_extra], dim=0)
+        big_p = torch.cat([xh_pocket, xp_extra], dim=0)
+        x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(G, 1), big_z, big_p, big_lig_mask, big_pocket_mask, G * B)
+        r0 = torch.as_tensor(reward_fn(x0_l, h0_l.argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
+        r = torch.as_tensor(reward_fn(big_z[:, :3], big_z[:, 3:].argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
+        mixed = r0 * (s / 250) + r * (250 - s / 250)                                  # [sic] :1203
+        _, top_idx = mixed.topk(k=B, largest=True)                                     # :1205
+        new_z, new_p, new_m = [], [], []
+        for rank, idx in enumerate(top_idx.tolist()):                                  # :1212-1227
+            nm = big_lig_mask == idx
+            new_z.append(big_z[nm])
+            new_p.append(big_p[big_pocket_mask == idx])
+            new_m.append(torch.full((int(nm.sum()),), rank, dtype=torch.long, device=dev))
+        return torch.cat(new_z, 0).contiguous(), torch.cat(new_p, 0).contiguous(), torch.cat(new_m, 0)

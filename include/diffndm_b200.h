@@ -65,6 +65,8 @@ typedef struct DndmWeight {
 /* Library / build information. */
 const char* dndm_version(void);
 const char* dndm_last_error(void);
+/* Number of kernels of this library launched (or captured into a CUDA graph) by this process so far. */
+int64_t dndm_launch_count(void);
 
 /* Lifetime.  Replaces EGNNDynamics.__init__ (dynamics.py:11-85): allocates the HBM workspace once. */
 int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out);
@@ -113,6 +115,14 @@ int dndm_read_flags(DndmEngine* e, uint32_t* flags_host, void* stream);
  *         3 = col int32 [E], 4 = scalars int32 [2] (E, E_ligand_rows)
  * Returns the number of bytes copied (>= 0) or a negative error. */
 int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64_t dst_bytes, void* stream);
+
+/* Per-section device timing for the benchmark's roofline line: when on, every forward brackets its sections with
+ * CUDA events on the caller's stream (do not enable under graph capture).  dndm_get_profile synchronises, sums the
+ * elapsed milliseconds and the number of timed sections per category since the last call, and resets.
+ * Categories: 0 fused GCL edge kernel, 1 fused coordinate-head edge kernel, 2 node GEMMs, 3 radius graph,
+ * 4 remaining node kernels. */
+int dndm_set_profile(DndmEngine* e, int32_t on);
+int dndm_get_profile(DndmEngine* e, double* ms_per_category, int32_t* launches_per_category, int32_t n_cat);
 
 /* Trace hook for parity tests: when set (DEVICE, [n_layers, max_trace_nodes, 256] fp32 and
  * [n_layers, max_trace_nodes, 3] fp32, either may be NULL), every forward stores h and x after each block. */
