@@ -310,6 +310,8 @@ class B200EGNNDynamics(torch.nn.Module):
             flags = self.engine.read_flags()
             if flags & FLAG_EDGE_OVERFLOW:
                 raise RuntimeError('diffndm_b200: edge capacity exceeded (raise max_edges)')
-            if flags & FLAG_NAN and not self.training:
-                raise ValueError("NaN detected in EGNN output")
+            if flags & FLAG_NAN:
+                if not self.training:
+                    raise ValueError("NaN detected in EGNN output")
+                out_l[:, :3] = torch.nan_to_num(out_l[:, :3], nan=0.0)           # vel[isnan] = 0, dynamics.py:156-157
         return out_l, out_p

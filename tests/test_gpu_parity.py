@@ -37,7 +37,8 @@ def dev():
 def dyn(golden_weights, dev):
     from diffndm_b200.engine import B200EGNNDynamics
     from diffndm_b200.weights import DynamicsConfig
-    return B200EGNNDynamics(DynamicsConfig(), golden_weights, max_nodes=8192, max_edges=400000, max_samples=64)
+    d = B200EGNNDynamics(DynamicsConfig(), golden_weights, max_nodes=8192, max_edges=400000, max_samples=64)
+    return d.eval()          # sampling runs in eval mode (NaN -> ValueError, dynamics.py:155-159)
 
 
 def _t(a, dev):
@@ -191,8 +192,15 @@ def test_nan_raises_value_error(dyn, dev):
     c = FWD_CASES['synth60_b3']
     xl = c['xh_lig'].copy()
     xl[0, 0] = np.nan
-    with pytest.raises(ValueError, match='NaN detected in EGNN output'):        # dynamics.py:155-159
-        dyn(_t(xl, dev), _t(c['xh_pocket'], dev), _t(c['t'], dev), _t(c['lig_mask'], dev), _t(c['pocket_mask'], dev))
+    args = (_t(xl, dev), _t(c['xh_pocket'], dev), _t(c['t'], dev), _t(c['lig_mask'], dev), _t(c['pocket_mask'], dev))
+    with pytest.raises(ValueError, match='NaN detected in EGNN output'):        # eval mode, dynamics.py:155-159
+        dyn(*args)
+    dyn.train()                                                                 # training mode zeroes them, :156-157
+    try:
+        out, _ = dyn(*args)
+        assert not torch.isnan(out[:, :3]).any()
+    finally:
+        dyn.eval()
 
 
 # ---------------------------------------------------------------------------------------------------------------
