@@ -20,8 +20,9 @@
 // i+1 run under the epilogues of tiles i-1 / i.
 //
 // Determinism: edges are receiver-sorted (CSR).  Each (receiver, column) sum is accumulated by ONE thread in row
-// order; a receiver that continues from the previous tile gets its leading partial written to tile_head[tile] and
-// added later, in tile order, by agg_finalize_kernel.  No atomics anywhere.
+// order (a per-tile segment table gives every receiver's row range); a receiver that continues from the previous
+// tile gets its leading partial written to tile_head[tile] and added later, in tile order, by agg_finalize_kernel.
+// No atomics anywhere.  P and Q are stored in bf16 (half the gather bytes; the sum and the distance terms are fp32).
 #pragma once
 #include "common.cuh"
 
@@ -34,7 +35,7 @@ constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
 constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
 constexpr int EK_STAGE_BYTES = 2 * EK_TILE * 32 * 4;    //  32768  (one [128 rows][32 cols] fp32 buffer per epilogue group)
 constexpr int EK_MISC_BYTES = 2048;
-constexpr int EK_SMEM_BYTES = 1024 + EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES + EK_MISC_BYTES;
+constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES + EK_MISC_BYTES;
 static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
 
 struct EdgeConsts {         // lives in the kernel-parameter constant bank: warp-uniform reads
@@ -43,8 +44,8 @@ struct EdgeConsts {         // lives in the kernel-parameter constant bank: warp
 };
 
 struct EdgeProblem {
-    const float* P;          // [N, ldpq] : W1a h + b1 (row / receiver part)
-    const float* Q;          // [N, ldpq] : W1b h      (col / sender part)
+    const __nv_bfloat16* P;  // [N, ldpq] : W1a h + b1 (row / receiver part), bf16
+    const __nv_bfloat16* Q;  // [N, ldpq] : W1b h      (col / sender part), bf16
     const float* w1e;        // [2][256]  : first-layer weights of (radial_now, radial_input)
     float* head_out;         // HEAD: [E] scalar per edge
     float bout;              // GCL: attention bias
@@ -77,23 +78,19 @@ DNDM_DEVICE float silu_fast(float x) {
 }
 DNDM_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
-// number of leading rows of a 32-row quarter that continue the previous row's receiver
-DNDM_DEVICE int lead_rows(unsigned start_mask) { return start_mask ? (__ffs(start_mask) - 1) : 32; }
-
 template <bool kGCL>
 __global__ void __launch_bounds__(EK_THREADS, 1)
 edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
                 const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,
                 EdgeGraph g, EdgeProblem p0, EdgeProblem p1) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    // keep the pointer derived from the __shared__ array (LDS/STS, not generic LD/ST); 1024-B alignment for SW128
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    extern __shared__ __align__(1024) uint8_t smem[];            // SW128 operand tiles need 1024-B alignment
     uint8_t* sW = smem;
     uint8_t* sA = smem + EK_W2_BYTES;
-    float* sStage = reinterpret_cast<float*>(smem + EK_W2_BYTES + EK_A_BYTES);      // [2 groups][128][32] swizzled
+    uint8_t* sStage = smem + EK_W2_BYTES + EK_A_BYTES;           // [2 groups][128 rows][128 B], 16-B units XOR-swizzled
     uint8_t* misc = smem + EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES;
     int* sRow = reinterpret_cast<int*>(misc);                    // [2][128] receiver per tile row (-1 = padding)
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc + 1024);
+    uint8_t* sSeg = misc + 1024;                                 // [2][132] first row of every receiver segment (+ sentinel)
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc + 1024 + 272);
     uint64_t* mma_done = w_bar + 1;                              // [2]
     uint64_t* tmem_empty = mma_done + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
@@ -109,6 +106,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     const int num_tiles = (E + EK_TILE - 1) / EK_TILE;
 
     if (tid == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
         tma_prefetch_desc(tmap_w);
         mbar_init(w_bar, 1);
         mbar_init(&mma_done[0], 1);
@@ -131,23 +129,24 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
         }
-        // lane owns k = 4*lane..+3 and 128+4*lane..+3 of the first-layer pre-activation
+        // lane owns k = 8*lane .. 8*lane+7 of the first-layer pre-activation (one 16-byte bf16 unit)
         float wr[8], w0[8];
         {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(pr.w1e + 4 * lane));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(pr.w1e + 128 + 4 * lane));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 4 * lane));
-            const float4 d = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 128 + 4 * lane));
+            const float4 a = __ldg(reinterpret_cast<const float4*>(pr.w1e + 8 * lane));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(pr.w1e + 8 * lane + 4));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 8 * lane));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 8 * lane + 4));
             wr[0] = a.x; wr[1] = a.y; wr[2] = a.z; wr[3] = a.w; wr[4] = b.x; wr[5] = b.y; wr[6] = b.z; wr[7] = b.w;
             w0[0] = c.x; w0[1] = c.y; w0[2] = c.z; w0[3] = c.w; w0[4] = d.x; w0[5] = d.y; w0[6] = d.z; w0[7] = d.w;
         }
         constexpr uint32_t idesc = make_idesc_bf16_f32(EK_TILE, EK_H);
-        const uint32_t kc = lane >> 4, u = (lane & 15) >> 1, half = lane & 1;
+        const uint32_t kc = lane >> 3, u = lane & 7;
+        const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
+        const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
+        const size_t ld4 = (size_t)g.ldpq / 8;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            if (it >= 1) mbar_wait(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);     // A smem free again
-            if (it >= 2) mbar_wait(&tmem_empty[buf], ((it - 2) >> 1) & 1);       // D[buf] and sRow[buf] consumed
             const int e = tile * EK_TILE + pw * 32 + lane;
             int my_row = -1, my_col = 0;
             float my_rad = 0.f, my_r0 = 0.f;
@@ -160,37 +159,41 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 const float dz = g.x[3 * my_row + 2] - g.x[3 * my_col + 2];
                 my_rad = dx * dx + dy * dy + dz * dz;
             }
+            const int ld_row = my_row < 0 ? 0 : my_row;                          // padding rows load node 0 (discarded)
+            if (it >= 1) mbar_wait(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);     // A smem free again
+            if (it >= 2) mbar_wait(&tmem_empty[buf], ((it - 2) >> 1) & 1);       // D[buf] and sRow[buf] consumed
             sRow[buf * 128 + pw * 32 + lane] = my_row;
             if (pw == 0 && lane == 0) sCont[buf] = (tile > 0) ? (g.erow[tile * EK_TILE - 1] == my_row) : 0;
-#pragma unroll 4
-            for (int j = 0; j < 32; ++j) {
-                const int rj = __shfl_sync(0xffffffffu, my_row, j);
-                const int cj = __shfl_sync(0xffffffffu, my_col, j);
-                const float rad = __shfl_sync(0xffffffffu, my_rad, j);
-                const float r0v = __shfl_sync(0xffffffffu, my_r0, j);
-                float v[8];
-                if (rj >= 0) {
-                    const float* pp = pr.P + (size_t)rj * g.ldpq + 4 * lane;
-                    const float* qq = pr.Q + (size_t)cj * g.ldpq + 4 * lane;
-                    const float4 pa = __ldg(reinterpret_cast<const float4*>(pp));
-                    const float4 pb = __ldg(reinterpret_cast<const float4*>(pp + 128));
-                    const float4 qa = __ldg(reinterpret_cast<const float4*>(qq));
-                    const float4 qb = __ldg(reinterpret_cast<const float4*>(qq + 128));
-                    v[0] = pa.x + qa.x; v[1] = pa.y + qa.y; v[2] = pa.z + qa.z; v[3] = pa.w + qa.w;
-                    v[4] = pb.x + qb.x; v[5] = pb.y + qb.y; v[6] = pb.z + qb.z; v[7] = pb.w + qb.w;
+#pragma unroll 1
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                uint4 pv[8], qv[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {                                 // 16 independent 16-byte gathers in flight
+                    const int rj = __shfl_sync(0xffffffffu, ld_row, j0 + jj);
+                    const int cj = __shfl_sync(0xffffffffu, my_col, j0 + jj);
+                    pv[jj] = __ldg(Pb + (size_t)rj * ld4);
+                    qv[jj] = __ldg(Qb + (size_t)cj * ld4);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float rad = __shfl_sync(0xffffffffu, my_rad, j0 + jj);
+                    const float r0v = __shfl_sync(0xffffffffu, my_r0, j0 + jj);
+                    const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
+                    const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[2 * i] = __uint_as_float(pw_[i] << 16) + __uint_as_float(qw_[i] << 16);
+                        v[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u) + __uint_as_float(qw_[i] & 0xffff0000u);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = silu_fast(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                    uint4 o;
+                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                    const uint32_t r = pw * 32 + j0 + jj;
+                    *reinterpret_cast<uint4*>(sA + kc * 16384 + sw128_offset(r, u)) = o;
                 }
-                const uint32_t r = pw * 32 + j;
-                uint2 lo, hi;
-                lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]);
-                hi.x = pack_bf16x2(v[4], v[5]); hi.y = pack_bf16x2(v[6], v[7]);
-                const uint32_t off = sw128_offset(r, u) + half * 8;
-                *reinterpret_cast<uint2*>(sA + kc * 16384 + off) = lo;
-                *reinterpret_cast<uint2*>(sA + (kc + 2) * 16384 + off) = hi;
             }
             fence_proxy_async_smem();
             tc_fence_before_sync();
@@ -216,8 +219,11 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         const int grp = warp >> 2;         // handles tiles with (it & 1) == grp
         const int q = warp & 3;            // TMEM lane quarter of this warp
         const int trow = q * 32 + lane;    // tile row owned in passes 1/2
-        float* st = sStage + grp * (EK_TILE * 32);
+        uint8_t* st = sStage + grp * (EK_TILE * 128);
         const int* rows = sRow + grp * 128;
+        uint8_t* seg = sSeg + grp * 132;
+        // read offset of column `lane` inside a staged row r: ((lane>>2) ^ (r&7))*16 + (lane&3)*4
+        const uint32_t lane_u = lane >> 2, lane_w = (lane & 3) * 4;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             if ((it & 1) != grp) continue;
@@ -225,9 +231,37 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)grp * EK_H + ((uint32_t)(q * 32) << 16);
             const int my_node = rows[trow];
+            int n_seg = 0;
+            bool head0 = false;
+            if (kGCL) {
+                // receiver segments of the tile: row r starts one if its receiver differs from row r-1's
+                // (row 0 always starts segment 0; head0 marks it as the continuation of the previous tile's receiver)
+                const int prev = trow > 0 ? rows[trow - 1] : -2;
+                const bool start = (trow == 0) || (my_node != prev);
+                unsigned sm[4];
+                const unsigned mine = __ballot_sync(0xffffffffu, start);
+                // exchange the four quarter masks through the segment table area (tiny)
+                int before = 0;
+                {
+                    unsigned* xm = reinterpret_cast<unsigned*>(st);      // stage buffer is idle here
+                    if (lane == 0) xm[q] = mine;
+                    named_bar_sync(2 + grp, 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sm[k] = xm[k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < q) before += __popc(sm[k]);
+                        n_seg += __popc(sm[k]);
+                    }
+                }
+                if (start) seg[before + __popc(mine & ((1u << lane) - 1u))] = (uint8_t)trow;
+                if (trow == 0) seg[n_seg] = 128;
+                head0 = sCont[grp] != 0;
+                named_bar_sync(2 + grp, 128);       // table visible; xm reads done before the stage is reused
+            }
             float dot = 0.f;
             // ---- pass 1: m = SiLU(D + b2), dot with wout; GCL keeps m in TMEM for pass 2 ----
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int col0 = c * 32;
                 uint32_t v[32];
@@ -246,26 +280,6 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             } else {
                 tmem_st_wait();
                 const float att = sigmoid_fast(dot + pr.bout) * pr.out_scale;
-                // segment structure of the tile (warp-uniform): bit i of sm[k] = row 32k+i starts a new receiver
-                unsigned sm[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int r = 32 * k + lane;
-                    const int cur = rows[r];
-                    const int prev = (r > 0) ? rows[r - 1] : (sCont[grp] ? cur : -2);
-                    sm[k] = __ballot_sync(0xffffffffu, cur != prev);
-                }
-                const unsigned my_sm = sm[q];
-                // rows of this quarter before i_start continue a receiver owned by an earlier quarter
-                const int i_start = (q == 0) ? 0 : lead_rows(my_sm);
-                // rows after this quarter that continue its last receiver
-                int ext = 0;
-                for (int k = q + 1; k < 4; ++k) {
-                    const int l = lead_rows(sm[k]);
-                    ext += l;
-                    if (l < 32) break;
-                }
-                const bool tile_head0 = (q == 0) && !(my_sm & 1u);     // leading rows continue the previous TILE
 #pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
                     const int col0 = c * 32;
@@ -273,36 +287,24 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                     tmem_ld32(d_tmem + col0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) st[trow * 32 + ((j + trow) & 31)] = __uint_as_float(v[j]) * att;
+                    for (int uu = 0; uu < 8; ++uu) {
+                        float4 o;
+                        o.x = __uint_as_float(v[4 * uu]) * att;     o.y = __uint_as_float(v[4 * uu + 1]) * att;
+                        o.z = __uint_as_float(v[4 * uu + 2]) * att; o.w = __uint_as_float(v[4 * uu + 3]) * att;
+                        *reinterpret_cast<float4*>(st + trow * 128 + ((uu ^ (trow & 7)) << 4)) = o;
+                    }
                     named_bar_sync(2 + grp, 128);
-                    // ---- column `lane` over the rows of quarter q (+ continuation rows), in row order ----
-                    if (i_start < 32) {
-                        float val[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int rr = q * 32 + i;
-                            val[i] = st[rr * 32 + ((lane + rr) & 31)];
-                        }
+                    // ---- per-receiver column sums in row order: warp q takes segments q, q+4, ...; lane = column ----
+                    for (int s = q; s < n_seg; s += 4) {
+                        const int a = seg[s], b = seg[s + 1];
+                        const int node = rows[a];
+                        if (node < 0) continue;
                         float acc = 0.f;
-                        bool head = tile_head0;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (i > 0 && ((my_sm >> i) & 1u) && i > i_start) {
-                                const int node = rows[q * 32 + i - 1];
-                                if (head) g.tile_head[(size_t)tile * EK_H + col0 + lane] = acc;
-                                else if (node >= 0) g.agg[(size_t)node * EK_H + col0 + lane] = acc;
-                                head = false;
-                                acc = 0.f;
-                            }
-                            if (i >= i_start) acc += val[i];
-                        }
-                        for (int k = 0; k < ext; ++k) {
-                            const int rr = q * 32 + 32 + k;
-                            acc += st[rr * 32 + ((lane + rr) & 31)];
-                        }
-                        const int node = rows[q * 32 + 31 + ext];
-                        if (head) g.tile_head[(size_t)tile * EK_H + col0 + lane] = acc;
-                        else if (node >= 0) g.agg[(size_t)node * EK_H + col0 + lane] = acc;
+#pragma unroll 4
+                        for (int r = a; r < b; ++r)
+                            acc += *reinterpret_cast<const float*>(st + r * 128 + ((lane_u ^ (r & 7)) << 4) + lane_w);
+                        if (s == 0 && head0) g.tile_head[(size_t)tile * EK_H + col0 + lane] = acc;
+                        else g.agg[(size_t)node * EK_H + col0 + lane] = acc;
                     }
                     named_bar_sync(2 + grp, 128);      // stage buffer free for the next chunk
                 }

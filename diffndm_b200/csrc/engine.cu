@@ -85,7 +85,8 @@ struct DndmEngine {
     int num_sms = 148;
     bool weights_loaded = false;
     // workspace
-    float *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *pq = nullptr, *agg = nullptr, *tile_head = nullptr;
+    float *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *agg = nullptr, *tile_head = nullptr;
+    __nv_bfloat16* pq = nullptr;   // [N,1536] bf16 node projections: edge P|Q, coord P, cross P, coord Q, cross Q
     float *r0 = nullptr, *phi = nullptr, *psi = nullptr, *pocket_sum = nullptr;
     __nv_bfloat16 *hcat = nullptr, *hid = nullptr;
     int *node_sample = nullptr, *lig_ptr = nullptr, *pok_ptr = nullptr, *deg = nullptr, *row_ptr = nullptr;
@@ -455,7 +456,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
 
     auto proj_e = [&](int l) -> int {
         ProfScope ps(e, PROF_GEMM, st);
-        GemmEpilogue ep{e->layers[l].bias_e, 0, nullptr, 0, e->pq, 1536, nullptr, 0};
+        GemmEpilogue ep{e->layers[l].bias_e, 0, nullptr, 0, nullptr, 0, e->pq, 1536};
         return launch_gemm(st, e->tm_hcat, e->layers[l].tm_proj_e, N, 512, 256, 0, ep);
     };
     RET_IF(proj_e(0));
@@ -485,7 +486,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         // ---- node projections for this block's coordinate heads and the next block's edge model ----
         {
             ProfScope ps(e, PROF_GEMM, st);
-            GemmEpilogue ep{L.bias_c, 0, nullptr, 0, e->pq + 512, 1536, nullptr, 0};
+            GemmEpilogue ep{L.bias_c, 0, nullptr, 0, nullptr, 0, e->pq + 512, 1536};
             RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, N, 1024, 256, 0, ep));
         }
         if (l + 1 < e->cfg.n_layers) RET_IF(proj_e(l + 1));
