@@ -34,7 +34,7 @@ constexpr int EK_THREADS = 384;
 constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
 constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
 constexpr int EK_STAGE_BYTES = 2 * EK_TILE * 32 * 4;    //  32768  (one [128 rows][32 cols] fp32 buffer per epilogue group)
-constexpr int EK_MISC_BYTES = 2048;
+constexpr int EK_MISC_BYTES = 2048 + 512;
 constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES + EK_MISC_BYTES;
 static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
 
@@ -61,8 +61,16 @@ struct EdgeGraph {
     int ldpq;
     float* agg;              // GCL: [N,256]
     float* tile_head;        // GCL: [tiles,256]
+    int debug;               // measurement scaffolding: bit0 skip pass 2, bit1 skip producer math, bit2 skip pass 1
+    unsigned long long* timeline;   // measurement scaffolding: [tiles_of_cta0][8] globaltimer stamps (or null)
 };
 
+DNDM_DEVICE unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %clock64;" : "=l"(t));   // SM cycles (all stamps of one CTA share the SM clock)
+    return t;
+}
+#define TL(slot) do { if (g.timeline && (!(g.debug & 256) || warp < 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && it < 64) g.timeline[it * 8 + (slot)] = gtimer(); } while (0)
 DNDM_DEVICE void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -88,13 +96,13 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     uint8_t* sA = smem + EK_W2_BYTES;
     uint8_t* sStage = smem + EK_W2_BYTES + EK_A_BYTES;           // [2 groups][128 rows][128 B], 16-B units XOR-swizzled
     uint8_t* misc = smem + EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES;
-    int* sRow = reinterpret_cast<int*>(misc);                    // [2][128] receiver per tile row (-1 = padding)
-    uint8_t* sSeg = misc + 1024;                                 // [2][132] first row of every receiver segment (+ sentinel)
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc + 1024 + 272);
+    int* sRow = reinterpret_cast<int*>(misc);                    // [4][128] receiver per tile row (-1 = padding), slot it&3
+    uint8_t* sSeg = misc + 2048;                                 // [2][132] first row of every receiver segment (+ sentinel)
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc + 2048 + 272);
     uint64_t* mma_done = w_bar + 1;                              // [2]
     uint64_t* tmem_empty = mma_done + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    int* sCont = reinterpret_cast<int*>(tmem_slot + 1);          // [2] tile continues the previous tile's receiver
+    int* sCont = reinterpret_cast<int*>(tmem_slot + 1);          // [4] tile continues the previous tile's receiver
 
     const bool second = (blockIdx.y != 0);
     const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
@@ -147,6 +155,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
+            if (pw == 0) TL(0);
             const int e = tile * EK_TILE + pw * 32 + lane;
             int my_row = -1, my_col = 0;
             float my_rad = 0.f, my_r0 = 0.f;
@@ -161,11 +170,13 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             }
             const int ld_row = my_row < 0 ? 0 : my_row;                          // padding rows load node 0 (discarded)
             if (it >= 1) mbar_wait(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);     // A smem free again
-            if (it >= 2) mbar_wait(&tmem_empty[buf], ((it - 2) >> 1) & 1);       // D[buf] and sRow[buf] consumed
-            sRow[buf * 128 + pw * 32 + lane] = my_row;
-            if (pw == 0 && lane == 0) sCont[buf] = (tile > 0) ? (g.erow[tile * EK_TILE - 1] == my_row) : 0;
+            if (pw == ((g.debug & 128) ? 1 : 0)) TL(1);
+            // row ids live in slot it&3: the epilogue of tile it-4 finished long ago (its TMEM buffer was
+            // re-acquired for tile it-2), so production never waits for an epilogue
+            sRow[(it & 3) * 128 + pw * 32 + lane] = my_row;
+            if (pw == 0 && lane == 0) sCont[it & 3] = (tile > 0) ? (g.erow[tile * EK_TILE - 1] == my_row) : 0;
 #pragma unroll 1
-            for (int j0 = 0; j0 < 32; j0 += 8) {
+            for (int j0 = 0; j0 < ((g.debug & 2) ? 0 : 32); j0 += 8) {
                 uint4 pv[8], qv[8];
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {                                 // 16 independent 16-byte gathers in flight
@@ -194,11 +205,14 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                     const uint32_t r = pw * 32 + j0 + jj;
                     *reinterpret_cast<uint4*>(sA + kc * 16384 + sw128_offset(r, u)) = o;
                 }
+                if (pw == ((g.debug & 128) ? 1 : 0) && (g.debug & 16)) TL(2 + (j0 >> 3));
             }
+            if (pw == 0 && !(g.debug & 16)) TL(2);
             fence_proxy_async_smem();
             tc_fence_before_sync();
             named_bar_sync(1, 128);                   // all four producer warps have written A / sRow
             if (tid == 8 * 32) {
+                if (it >= 2) mbar_wait(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained by its epilogue group
                 tc_fence_after_sync();
                 if (it == 0) mbar_wait(w_bar, 0);
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H;
@@ -212,7 +226,9 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                     }
                 }
                 umma_commit(&mma_done[buf]);
+                if (!(g.debug & 16)) TL(3);
             }
+            if (!(g.debug & 64)) __syncwarp();
         }
     } else {
         // =========================== epilogue groups ===========================
@@ -220,14 +236,15 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         const int q = warp & 3;            // TMEM lane quarter of this warp
         const int trow = q * 32 + lane;    // tile row owned in passes 1/2
         uint8_t* st = sStage + grp * (EK_TILE * 128);
-        const int* rows = sRow + grp * 128;
         uint8_t* seg = sSeg + grp * 132;
         // read offset of column `lane` inside a staged row r: ((lane>>2) ^ (r&7))*16 + (lane&3)*4
         const uint32_t lane_u = lane >> 2, lane_w = (lane & 3) * 4;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             if ((it & 1) != grp) continue;
+            const int* rows = sRow + (it & 3) * 128;
             mbar_wait(&mma_done[grp], (it >> 1) & 1);
+            if (q == 0 && !(g.debug & (16 | 256))) TL(4);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)grp * EK_H + ((uint32_t)(q * 32) << 16);
             const int my_node = rows[trow];
@@ -256,13 +273,14 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 }
                 if (start) seg[before + __popc(mine & ((1u << lane) - 1u))] = (uint8_t)trow;
                 if (trow == 0) seg[n_seg] = 128;
-                head0 = sCont[grp] != 0;
+                head0 = sCont[it & 3] != 0;
                 named_bar_sync(2 + grp, 128);       // table visible; xm reads done before the stage is reused
             }
             float dot = 0.f;
             // ---- pass 1: m = SiLU(D + b2), dot with wout; GCL keeps m in TMEM for pass 2 ----
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
+                if (g.debug & 4) break;
                 const int col0 = c * 32;
                 uint32_t v[32];
                 tmem_ld32(d_tmem + col0, v);
@@ -275,17 +293,21 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 }
                 if (kGCL) tmem_st32(d_tmem + col0, v);
             }
+            if (q == 0 && !(g.debug & (16 | 256))) TL(5);
             if (!kGCL) {
                 if (my_node >= 0) pr.head_out[tile * EK_TILE + trow] = pr.out_scale * tanhf(dot);
             } else {
                 tmem_st_wait();
                 const float att = sigmoid_fast(dot + pr.bout) * pr.out_scale;
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < ((g.debug & 1) ? 0 : 8); ++c) {
                     const int col0 = c * 32;
                     uint32_t v[32];
+                    const bool tl2 = (g.debug & 256) && q == 1 && c == 0;
+                    if (tl2) TL(0);
                     tmem_ld32(d_tmem + col0, v);
                     tmem_ld_wait();
+                    if (tl2) TL(1);
 #pragma unroll
                     for (int uu = 0; uu < 8; ++uu) {
                         float4 o;
@@ -293,24 +315,42 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                         o.z = __uint_as_float(v[4 * uu + 2]) * att; o.w = __uint_as_float(v[4 * uu + 3]) * att;
                         *reinterpret_cast<float4*>(st + trow * 128 + ((uu ^ (trow & 7)) << 4)) = o;
                     }
+                    if (tl2) TL(2);
                     named_bar_sync(2 + grp, 128);
+                    if (tl2) TL(3);
                     // ---- per-receiver column sums in row order: warp q takes segments q, q+4, ...; lane = column ----
                     for (int s = q; s < n_seg; s += 4) {
                         const int a = seg[s], b = seg[s + 1];
                         const int node = rows[a];
                         if (node < 0) continue;
-                        float acc = 0.f;
-#pragma unroll 4
-                        for (int r = a; r < b; ++r)
-                            acc += *reinterpret_cast<const float*>(st + r * 128 + ((lane_u ^ (r & 7)) << 4) + lane_w);
+                        // four interleaved partial sums (rows mod 4), combined in a fixed order: short dependency
+                        // chains, all loads of an 8-row group in flight together
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        for (int r = a; r < b; r += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int rr = r + i;
+                                v[i] = (rr < b) ? *reinterpret_cast<const float*>(st + rr * 128 + ((lane_u ^ (rr & 7)) << 4) + lane_w)
+                                                : 0.f;
+                            }
+                            a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
+                            a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
+                        }
+                        const float acc = (a0 + a1) + (a2 + a3);
+                        if ((g.debug & 32) && acc != 12345.678f) continue;
                         if (s == 0 && head0) g.tile_head[(size_t)tile * EK_H + col0 + lane] = acc;
                         else g.agg[(size_t)node * EK_H + col0 + lane] = acc;
                     }
+                    if (tl2) TL(4);
                     named_bar_sync(2 + grp, 128);      // stage buffer free for the next chunk
+                    if (tl2) TL(5);
+                    if ((g.debug & 256) && q == 1 && c == 7) TL(6);
                 }
             }
             tc_fence_before_sync();
             mbar_arrive(&tmem_empty[grp]);
+            if (q == 0 && !(g.debug & 256)) TL(6);
         }
     }
     tc_fence_before_sync();

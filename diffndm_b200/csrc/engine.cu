@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <map>
@@ -101,6 +102,7 @@ struct DndmEngine {
     // last call
     int last_n_lig = 0, last_n_nodes = 0;
     float* x_final = nullptr;
+    unsigned long long* timeline = nullptr;   // measurement scaffolding
     // trace
     float *h_trace = nullptr, *x_trace = nullptr;
     int max_trace_nodes = 0;
@@ -173,6 +175,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(dev_alloc(&e->deg, N)); RET_IF(dev_alloc(&e->row_ptr, N + 1));
     RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 4));
     RET_IF(dev_alloc(&e->flags, 1));
+    if (getenv("DNDM_TIMELINE")) { RET_IF(dev_alloc(&e->timeline, 64 * 8)); CU_CHECK(cudaMemset(e->timeline, 0, 64 * 8 * 8)); }
     CU_CHECK(cudaMemset(e->flags, 0, 4));
     CU_CHECK(cudaMemset(e->hcat, 0, N * 512 * 2));
     CU_CHECK(cudaMemset(e->hid, 0, N * 256 * 2));
@@ -463,7 +466,8 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     for (int l = 0; l < e->cfg.n_layers; ++l) {
         LayerWeights& L = e->layers[l];
         // ---- GCL edge model + attention + deterministic aggregation ----
-        EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->agg, e->tile_head};
+        static const int edge_debug = getenv("DNDM_EDGE_DEBUG") ? atoi(getenv("DNDM_EDGE_DEBUG")) : 0;
+        EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->agg, e->tile_head, edge_debug, (l == 2 ? e->timeline : nullptr)};
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
@@ -492,7 +496,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         if (l + 1 < e->cfg.n_layers) RET_IF(proj_e(l + 1));
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
         {
-            EdgeGraph gh{e->erow, e->ecol, e->r0, x_cur, e->scalars + 1, 1536, nullptr, nullptr};
+            EdgeGraph gh{e->erow, e->ecol, e->r0, x_cur, e->scalars + 1, 1536, nullptr, nullptr, edge_debug, nullptr};
             EdgeProblem pc{e->pq + 512, e->pq + 1024, L.w1e_c, e->phi, 0.f, e->cfg.coords_range};
             EdgeProblem px{e->pq + 768, e->pq + 1280, L.w1e_x, e->psi, 0.f, e->cfg.coords_range};
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
@@ -612,6 +616,7 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
             break;
         }
         case 4: src = e->scalars; bytes = 8; break;
+        case 5: src = e->timeline; bytes = e->timeline ? 64 * 8 * 8 : 0; break;
         default: return set_err(DNDM_EINVAL, "unknown buffer id %d", what);
     }
     if (bytes > dst_bytes) bytes = dst_bytes;
