@@ -33,20 +33,20 @@ constexpr int EK_H = 256;         // hidden size (UMMA N and K)
 constexpr int EK_THREADS = 384;
 constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
 constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
-constexpr int EK_STAGE_BYTES = 2 * EK_TILE * 32 * 4;    //  32768  (one [128 rows][32 cols] fp32 buffer per epilogue group)
-constexpr int EK_MISC_BYTES = 2048 + 512;
+constexpr int EK_STAGE_BYTES = 2 * EK_TILE * 33 * 4;    //  33792  (one padded [128 rows][33] fp32 buffer per epilogue group)
+constexpr int EK_MISC_BYTES = 2048;
 constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES + EK_MISC_BYTES;
 static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
 
 struct EdgeConsts {         // lives in the kernel-parameter constant bank: warp-uniform reads
-    float b2[EK_H];
+    float b2[EK_H];        // HALF of the second-layer bias (the SiLU argument is evaluated as x/2)
     float wout[EK_H];
 };
 
 struct EdgeProblem {
-    const __nv_bfloat16* P;  // [N, ldpq] : W1a h + b1 (row / receiver part), bf16
-    const __nv_bfloat16* Q;  // [N, ldpq] : W1b h      (col / sender part), bf16
-    const float* w1e;        // [2][256]  : first-layer weights of (radial_now, radial_input)
+    const __nv_bfloat16* P;  // [N, ldpq] : (W1a h + b1)/2 (row / receiver part), bf16
+    const __nv_bfloat16* Q;  // [N, ldpq] : (W1b h)/2      (col / sender part), bf16
+    const float* w1e;        // [2][256]  : HALF the first-layer weights of (radial_now, radial_input)
     float* head_out;         // HEAD: [E] scalar per edge
     float bout;              // GCL: attention bias
     float out_scale;         // GCL: 1/normalization_factor ; HEAD: coords_range
@@ -61,16 +61,8 @@ struct EdgeGraph {
     int ldpq;
     float* agg;              // GCL: [N,256]
     float* tile_head;        // GCL: [tiles,256]
-    int debug;               // measurement scaffolding: bit0 skip pass 2, bit1 skip producer math, bit2 skip pass 1
-    unsigned long long* timeline;   // measurement scaffolding: [tiles_of_cta0][8] globaltimer stamps (or null)
 };
 
-DNDM_DEVICE unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %clock64;" : "=l"(t));   // SM cycles (all stamps of one CTA share the SM clock)
-    return t;
-}
-#define TL(slot) do { if (g.timeline && (!(g.debug & 256) || warp < 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && it < 64) g.timeline[it * 8 + (slot)] = gtimer(); } while (0)
 DNDM_DEVICE void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -79,12 +71,47 @@ DNDM_DEVICE float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// SiLU / sigmoid through one MUFU.TANH:  x*sigmoid(x) = h + h*tanh(h), h = x/2   (|rel err| ~ 2^-11)
-DNDM_DEVICE float silu_fast(float x) {
-    const float h = 0.5f * x;
-    return fmaf(h, tanh_approx(h), h);
-}
+// SiLU through one MUFU.TANH on the HALVED argument h = x/2:  x*sigmoid(x) = h + h*tanh(h)   (|rel err| ~ 2^-11).
+// The 1/2 is folded into the producing linear map on the host (exact: power of two), so callers pass h directly.
+DNDM_DEVICE float silu_half(float h) { return fmaf(h, tanh_approx(h), h); }
 DNDM_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+
+// mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of burning issue slots
+DNDM_DEVICE void mbar_wait_park(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
+        "@P bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(200000u)
+        : "memory");
+}
+
+// pass 1 of the epilogue for one row: m = SiLU(D + b2) (b2 pre-halved), dot with wout; GCL writes m back to TMEM.
+// `cc` must be one of the __grid_constant__ kernel parameters so that b2/wout become constant-bank operands.
+template <bool kGCL>
+DNDM_DEVICE float epilogue_pass1(const EdgeConsts& cc, uint32_t d_tmem) {
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int col0 = c * 32;
+        uint32_t v[32];
+        tmem_ld32(d_tmem + col0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float m = silu_half(fmaf(__uint_as_float(v[j]), 0.5f, cc.b2[col0 + j]));
+            dot = fmaf(m, cc.wout[col0 + j], dot);
+            v[j] = __float_as_uint(m);
+        }
+        if (kGCL) tmem_st32(d_tmem + col0, v);
+    }
+    return dot;
+}
+
+constexpr int EK_ST_LD = 33;      // padded row stride (floats) of the staging buffer: conflict-free row writes / column reads
 
 template <bool kGCL>
 __global__ void __launch_bounds__(EK_THREADS, 1)
@@ -94,19 +121,19 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     extern __shared__ __align__(1024) uint8_t smem[];            // SW128 operand tiles need 1024-B alignment
     uint8_t* sW = smem;
     uint8_t* sA = smem + EK_W2_BYTES;
-    uint8_t* sStage = smem + EK_W2_BYTES + EK_A_BYTES;           // [2 groups][128 rows][128 B], 16-B units XOR-swizzled
+    float* sStage = reinterpret_cast<float*>(smem + EK_W2_BYTES + EK_A_BYTES);   // [2 groups][128 rows][33]
     uint8_t* misc = smem + EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES;
-    int* sRow = reinterpret_cast<int*>(misc);                    // [4][128] receiver per tile row (-1 = padding), slot it&3
-    uint8_t* sSeg = misc + 2048;                                 // [2][132] first row of every receiver segment (+ sentinel)
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc + 2048 + 272);
+    int* sRow = reinterpret_cast<int*>(misc);                    // [3][128] receiver per tile row (-1 = padding), slot it%3
+    uint8_t* sSeg = misc + 1536;                                 // [2][132] first row of every receiver segment (+ sentinel)
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc + 1536 + 272);
     uint64_t* mma_done = w_bar + 1;                              // [2]
     uint64_t* tmem_empty = mma_done + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    int* sCont = reinterpret_cast<int*>(tmem_slot + 1);          // [4] tile continues the previous tile's receiver
+    int* sCont = reinterpret_cast<int*>(tmem_slot + 1);          // [3] tile continues the previous tile's receiver
+    unsigned* sMask = reinterpret_cast<unsigned*>(sCont + 3);    // [2][4] per-quarter segment-start masks
 
     const bool second = (blockIdx.y != 0);
     const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
-    const EdgeConsts& cc = second ? c1 : c0;
     const EdgeProblem& pr = second ? p1 : p0;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -137,7 +164,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
         }
-        // lane owns k = 8*lane .. 8*lane+7 of the first-layer pre-activation (one 16-byte bf16 unit)
+        // lane owns k = 8*lane .. 8*lane+7 of the (halved) first-layer pre-activation: one 16-byte bf16 unit
         float wr[8], w0[8];
         {
             const float4 a = __ldg(reinterpret_cast<const float4*>(pr.w1e + 8 * lane));
@@ -148,14 +175,15 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             w0[0] = c.x; w0[1] = c.y; w0[2] = c.z; w0[3] = c.w; w0[4] = d.x; w0[5] = d.y; w0[6] = d.z; w0[7] = d.w;
         }
         constexpr uint32_t idesc = make_idesc_bf16_f32(EK_TILE, EK_H);
-        const uint32_t kc = lane >> 3, u = lane & 7;
         const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
         const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
-        const size_t ld4 = (size_t)g.ldpq / 8;
+        const uint32_t ld4 = (uint32_t)g.ldpq / 8;
+        // byte offset of this lane's 16-byte unit inside A row r: kc*16384 + r*128 + ((u ^ (r&7)) << 4)
+        uint8_t* sA_lane = sA + (lane >> 3) * 16384;
+        const uint32_t u = lane & 7;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            if (pw == 0) TL(0);
             const int e = tile * EK_TILE + pw * 32 + lane;
             int my_row = -1, my_col = 0;
             float my_rad = 0.f, my_r0 = 0.f;
@@ -169,50 +197,63 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 my_rad = dx * dx + dy * dy + dz * dz;
             }
             const int ld_row = my_row < 0 ? 0 : my_row;                          // padding rows load node 0 (discarded)
-            if (it >= 1) mbar_wait(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);     // A smem free again
-            if (pw == ((g.debug & 128) ? 1 : 0)) TL(1);
-            // row ids live in slot it&3: the epilogue of tile it-4 finished long ago (its TMEM buffer was
-            // re-acquired for tile it-2), so production never waits for an epilogue
-            sRow[(it & 3) * 128 + pw * 32 + lane] = my_row;
-            if (pw == 0 && lane == 0) sCont[it & 3] = (tile > 0) ? (g.erow[tile * EK_TILE - 1] == my_row) : 0;
-#pragma unroll 1
-            for (int j0 = 0; j0 < ((g.debug & 2) ? 0 : 32); j0 += 8) {
-                uint4 pv[8], qv[8];
+            if (it >= 1) mbar_wait_park(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);   // A smem free again
+            // row ids live in slot it%3: the epilogue of tile it-3 has finished (its TMEM buffer was re-acquired
+            // for tile it-1, whose MMA completion was awaited above), so production never waits for an epilogue
+            const int slot = it % 3;
+            sRow[slot * 128 + pw * 32 + lane] = my_row;
+            if (pw == 0 && lane == 0) sCont[slot] = (tile > 0) ? (g.erow[tile * EK_TILE - 1] == my_row) : 0;
+            float pf[8];                              // P row of the current receiver, unpacked once per receiver
+            int cur_r = -1;
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {                                 // 16 independent 16-byte gathers in flight
-                    const int rj = __shfl_sync(0xffffffffu, ld_row, j0 + jj);
+            for (int i = 0; i < 8; ++i) pf[i] = 0.f;
+#pragma unroll 1
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                uint4 pv[8], qv[8];
+                int rj[8];
+                // gathers of the batch, all in flight together; P only when the receiver changes (rows are sorted)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    rj[jj] = __shfl_sync(0xffffffffu, ld_row, j0 + jj);
                     const int cj = __shfl_sync(0xffffffffu, my_col, j0 + jj);
-                    pv[jj] = __ldg(Pb + (size_t)rj * ld4);
+                    const int prev_r = (jj == 0) ? cur_r : rj[jj - 1];
+                    if (rj[jj] != prev_r) pv[jj] = __ldg(Pb + (size_t)rj[jj] * ld4);
                     qv[jj] = __ldg(Qb + (size_t)cj * ld4);
                 }
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
                     const float rad = __shfl_sync(0xffffffffu, my_rad, j0 + jj);
                     const float r0v = __shfl_sync(0xffffffffu, my_r0, j0 + jj);
-                    const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
+                    if (rj[jj] != cur_r) {                                   // warp-uniform
+                        cur_r = rj[jj];
+                        const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            pf[2 * i] = __uint_as_float(pw_[i] << 16);
+                            pf[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u);
+                        }
+                    }
                     const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
                     float v[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        v[2 * i] = __uint_as_float(pw_[i] << 16) + __uint_as_float(qw_[i] << 16);
-                        v[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u) + __uint_as_float(qw_[i] & 0xffff0000u);
+                        v[2 * i] = pf[2 * i] + __uint_as_float(qw_[i] << 16);
+                        v[2 * i + 1] = pf[2 * i + 1] + __uint_as_float(qw_[i] & 0xffff0000u);
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = silu_fast(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
+                    for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
                     uint4 o;
                     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
                     o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
                     const uint32_t r = pw * 32 + j0 + jj;
-                    *reinterpret_cast<uint4*>(sA + kc * 16384 + sw128_offset(r, u)) = o;
+                    *reinterpret_cast<uint4*>(sA_lane + r * 128 + ((u ^ (r & 7)) << 4)) = o;
                 }
-                if (pw == ((g.debug & 128) ? 1 : 0) && (g.debug & 16)) TL(2 + (j0 >> 3));
             }
-            if (pw == 0 && !(g.debug & 16)) TL(2);
             fence_proxy_async_smem();
             tc_fence_before_sync();
             named_bar_sync(1, 128);                   // all four producer warps have written A / sRow
             if (tid == 8 * 32) {
-                if (it >= 2) mbar_wait(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained by its epilogue group
+                if (it >= 2) mbar_wait_park(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained by its epilogue group
                 tc_fence_after_sync();
                 if (it == 0) mbar_wait(w_bar, 0);
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H;
@@ -226,25 +267,23 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                     }
                 }
                 umma_commit(&mma_done[buf]);
-                if (!(g.debug & 16)) TL(3);
             }
-            if (!(g.debug & 64)) __syncwarp();
+            __syncwarp();   // re-converge the issuing lane: without it the warp stays split for the whole next tile
         }
     } else {
         // =========================== epilogue groups ===========================
         const int grp = warp >> 2;         // handles tiles with (it & 1) == grp
         const int q = warp & 3;            // TMEM lane quarter of this warp
         const int trow = q * 32 + lane;    // tile row owned in passes 1/2
-        uint8_t* st = sStage + grp * (EK_TILE * 128);
+        float* st = sStage + grp * (EK_TILE * EK_ST_LD);
         uint8_t* seg = sSeg + grp * 132;
-        // read offset of column `lane` inside a staged row r: ((lane>>2) ^ (r&7))*16 + (lane&3)*4
-        const uint32_t lane_u = lane >> 2, lane_w = (lane & 3) * 4;
+        unsigned* xm = sMask + grp * 4;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             if ((it & 1) != grp) continue;
-            const int* rows = sRow + (it & 3) * 128;
-            mbar_wait(&mma_done[grp], (it >> 1) & 1);
-            if (q == 0 && !(g.debug & (16 | 256))) TL(4);
+            const int slot = it % 3;
+            const int* rows = sRow + slot * 128;
+            mbar_wait_park(&mma_done[grp], (it >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)grp * EK_H + ((uint32_t)(q * 32) << 16);
             const int my_node = rows[trow];
@@ -255,102 +294,62 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 // (row 0 always starts segment 0; head0 marks it as the continuation of the previous tile's receiver)
                 const int prev = trow > 0 ? rows[trow - 1] : -2;
                 const bool start = (trow == 0) || (my_node != prev);
-                unsigned sm[4];
                 const unsigned mine = __ballot_sync(0xffffffffu, start);
-                // exchange the four quarter masks through the segment table area (tiny)
+                if (lane == 0) xm[q] = mine;
+                named_bar_sync(2 + grp, 128);
                 int before = 0;
-                {
-                    unsigned* xm = reinterpret_cast<unsigned*>(st);      // stage buffer is idle here
-                    if (lane == 0) xm[q] = mine;
-                    named_bar_sync(2 + grp, 128);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) sm[k] = xm[k];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (k < q) before += __popc(sm[k]);
-                        n_seg += __popc(sm[k]);
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    const int pc = __popc(xm[k]);
+                    if (k < q) before += pc;
+                    n_seg += pc;
                 }
                 if (start) seg[before + __popc(mine & ((1u << lane) - 1u))] = (uint8_t)trow;
                 if (trow == 0) seg[n_seg] = 128;
-                head0 = sCont[it & 3] != 0;
-                named_bar_sync(2 + grp, 128);       // table visible; xm reads done before the stage is reused
+                head0 = sCont[slot] != 0;
+                named_bar_sync(2 + grp, 128);       // segment table visible
             }
-            float dot = 0.f;
-            // ---- pass 1: m = SiLU(D + b2), dot with wout; GCL keeps m in TMEM for pass 2 ----
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (g.debug & 4) break;
-                const int col0 = c * 32;
-                uint32_t v[32];
-                tmem_ld32(d_tmem + col0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float m = silu_fast(__uint_as_float(v[j]) + cc.b2[col0 + j]);
-                    dot = fmaf(m, cc.wout[col0 + j], dot);
-                    v[j] = __float_as_uint(m);
-                }
-                if (kGCL) tmem_st32(d_tmem + col0, v);
-            }
-            if (q == 0 && !(g.debug & (16 | 256))) TL(5);
+            // ---- pass 1 ----
+            const float dot = second ? epilogue_pass1<kGCL>(c1, d_tmem) : epilogue_pass1<kGCL>(c0, d_tmem);
             if (!kGCL) {
                 if (my_node >= 0) pr.head_out[tile * EK_TILE + trow] = pr.out_scale * tanhf(dot);
             } else {
                 tmem_st_wait();
                 const float att = sigmoid_fast(dot + pr.bout) * pr.out_scale;
+                float* my_st = st + trow * EK_ST_LD;
 #pragma unroll 1
-                for (int c = 0; c < ((g.debug & 1) ? 0 : 8); ++c) {
+                for (int c = 0; c < 8; ++c) {
                     const int col0 = c * 32;
                     uint32_t v[32];
-                    const bool tl2 = (g.debug & 256) && q == 1 && c == 0;
-                    if (tl2) TL(0);
                     tmem_ld32(d_tmem + col0, v);
                     tmem_ld_wait();
-                    if (tl2) TL(1);
 #pragma unroll
-                    for (int uu = 0; uu < 8; ++uu) {
-                        float4 o;
-                        o.x = __uint_as_float(v[4 * uu]) * att;     o.y = __uint_as_float(v[4 * uu + 1]) * att;
-                        o.z = __uint_as_float(v[4 * uu + 2]) * att; o.w = __uint_as_float(v[4 * uu + 3]) * att;
-                        *reinterpret_cast<float4*>(st + trow * 128 + ((uu ^ (trow & 7)) << 4)) = o;
-                    }
-                    if (tl2) TL(2);
+                    for (int j = 0; j < 32; ++j) my_st[j] = __uint_as_float(v[j]) * att;
                     named_bar_sync(2 + grp, 128);
-                    if (tl2) TL(3);
-                    // ---- per-receiver column sums in row order: warp q takes segments q, q+4, ...; lane = column ----
+                    // ---- per-receiver column sums: warp q takes segments q, q+4, ...; lane = column.  Two interleaved
+                    //      partial sums (even / odd rows) combined at the end: fixed order, short dependency chains ----
                     for (int s = q; s < n_seg; s += 4) {
                         const int a = seg[s], b = seg[s + 1];
                         const int node = rows[a];
                         if (node < 0) continue;
-                        // four interleaved partial sums (rows mod 4), combined in a fixed order: short dependency
-                        // chains, all loads of an 8-row group in flight together
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                        for (int r = a; r < b; r += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int rr = r + i;
-                                v[i] = (rr < b) ? *reinterpret_cast<const float*>(st + rr * 128 + ((lane_u ^ (rr & 7)) << 4) + lane_w)
-                                                : 0.f;
-                            }
-                            a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
-                            a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
+                        const float* p = st + a * EK_ST_LD + lane;
+                        float a0 = 0.f, a1 = 0.f;
+                        int r = a;
+                        for (; r + 8 <= b; r += 8, p += 8 * EK_ST_LD) {
+                            const float v0 = p[0], v1 = p[EK_ST_LD], v2 = p[2 * EK_ST_LD], v3 = p[3 * EK_ST_LD];
+                            const float v4 = p[4 * EK_ST_LD], v5 = p[5 * EK_ST_LD], v6 = p[6 * EK_ST_LD], v7 = p[7 * EK_ST_LD];
+                            a0 += v0; a1 += v1; a0 += v2; a1 += v3; a0 += v4; a1 += v5; a0 += v6; a1 += v7;
                         }
-                        const float acc = (a0 + a1) + (a2 + a3);
-                        if ((g.debug & 32) && acc != 12345.678f) continue;
+                        for (; r < b; ++r, p += EK_ST_LD) a0 += p[0];
+                        const float acc = a0 + a1;
                         if (s == 0 && head0) g.tile_head[(size_t)tile * EK_H + col0 + lane] = acc;
                         else g.agg[(size_t)node * EK_H + col0 + lane] = acc;
                     }
-                    if (tl2) TL(4);
                     named_bar_sync(2 + grp, 128);      // stage buffer free for the next chunk
-                    if (tl2) TL(5);
-                    if ((g.debug & 256) && q == 1 && c == 7) TL(6);
                 }
             }
             tc_fence_before_sync();
             mbar_arrive(&tmem_empty[grp]);
-            if (q == 0 && !(g.debug & 256)) TL(6);
         }
     }
     tc_fence_before_sync();

@@ -102,7 +102,6 @@ struct DndmEngine {
     // last call
     int last_n_lig = 0, last_n_nodes = 0;
     float* x_final = nullptr;
-    unsigned long long* timeline = nullptr;   // measurement scaffolding
     // trace
     float *h_trace = nullptr, *x_trace = nullptr;
     int max_trace_nodes = 0;
@@ -175,7 +174,6 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(dev_alloc(&e->deg, N)); RET_IF(dev_alloc(&e->row_ptr, N + 1));
     RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 4));
     RET_IF(dev_alloc(&e->flags, 1));
-    if (getenv("DNDM_TIMELINE")) { RET_IF(dev_alloc(&e->timeline, 64 * 8)); CU_CHECK(cudaMemset(e->timeline, 0, 64 * 8 * 8)); }
     CU_CHECK(cudaMemset(e->flags, 0, 4));
     CU_CHECK(cudaMemset(e->hcat, 0, N * 512 * 2));
     CU_CHECK(cudaMemset(e->hid, 0, N * 256 * 2));
@@ -326,15 +324,16 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         auto split_first = [&](const float* w, std::vector<__nv_bfloat16>& dst, size_t row_off_a, size_t row_off_b) {
             for (int o = 0; o < H; ++o)
                 for (int k = 0; k < H; ++k) {
-                    dst[(row_off_a + o) * H + k] = f2bf(w[(size_t)o * KIN + k]);
-                    dst[(row_off_b + o) * H + k] = f2bf(w[(size_t)o * KIN + H + k]);
+                    // halved (exact): the edge kernel evaluates SiLU(x) = h + h tanh(h) on h = x/2
+                    dst[(row_off_a + o) * H + k] = f2bf(0.5f * w[(size_t)o * KIN + k]);
+                    dst[(row_off_b + o) * H + k] = f2bf(0.5f * w[(size_t)o * KIN + H + k]);
                 }
         };
         auto edge_cols = [&](const float* w) {
             std::vector<float> v(2 * H);
             for (int o = 0; o < H; ++o) {
-                v[o] = w[(size_t)o * KIN + 2 * H];          // coefficient of the current radial
-                v[H + o] = w[(size_t)o * KIN + 2 * H + 1];  // coefficient of the input radial
+                v[o] = 0.5f * w[(size_t)o * KIN + 2 * H];          // (half) coefficient of the current radial
+                v[H + o] = 0.5f * w[(size_t)o * KIN + 2 * H + 1];  // (half) coefficient of the input radial
             }
             return v;
         };
@@ -348,7 +347,7 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         split_first(c0w, pc, 0, 2 * H);
         split_first(x0w, pc, H, 3 * H);
         std::vector<float> be(2 * H, 0.f), bcv(4 * H, 0.f);
-        for (int o = 0; o < H; ++o) { be[o] = e0b[o]; bcv[o] = c0b[o]; bcv[H + o] = x0b[o]; }
+        for (int o = 0; o < H; ++o) { be[o] = 0.5f * e0b[o]; bcv[o] = 0.5f * c0b[o]; bcv[H + o] = 0.5f * x0b[o]; }
         RET_IF(upload(e, pe, &L.wproj_e)); RET_IF(upload(e, pc, &L.wproj_c));
         RET_IF(upload(e, be, &L.bias_e)); RET_IF(upload(e, bcv, &L.bias_c));
         RET_IF(upload(e, edge_cols(e0w), &L.w1e_e)); RET_IF(upload(e, edge_cols(c0w), &L.w1e_c));
@@ -358,9 +357,9 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         RET_IF(upload(e, to_bf(n0w, (size_t)H * 2 * H), &L.w3)); RET_IF(upload(e, to_bf(n2w, (size_t)H * H), &L.w4));
         RET_IF(upload(e, std::vector<float>(n0b, n0b + H), &L.b3)); RET_IF(upload(e, std::vector<float>(n2b, n2b + H), &L.b4));
         for (int o = 0; o < H; ++o) {
-            L.c_e.b2[o] = e2b[o]; L.c_e.wout[o] = aw[o];
-            L.c_c.b2[o] = c2b[o]; L.c_c.wout[o] = c4w[o];
-            L.c_x.b2[o] = x2b[o]; L.c_x.wout[o] = x4w[o];
+            L.c_e.b2[o] = 0.5f * e2b[o]; L.c_e.wout[o] = aw[o];
+            L.c_c.b2[o] = 0.5f * c2b[o]; L.c_c.wout[o] = c4w[o];
+            L.c_x.b2[o] = 0.5f * x2b[o]; L.c_x.wout[o] = x4w[o];
         }
         L.att_bias = ab[0];
         RET_IF(make_tmap_bf16(&L.tm_proj_e, L.wproj_e, 2 * H, H, H, GEMM_BN));
@@ -466,8 +465,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     for (int l = 0; l < e->cfg.n_layers; ++l) {
         LayerWeights& L = e->layers[l];
         // ---- GCL edge model + attention + deterministic aggregation ----
-        static const int edge_debug = getenv("DNDM_EDGE_DEBUG") ? atoi(getenv("DNDM_EDGE_DEBUG")) : 0;
-        EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->agg, e->tile_head, edge_debug, (l == 2 ? e->timeline : nullptr)};
+        EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->agg, e->tile_head};
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
@@ -496,7 +494,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         if (l + 1 < e->cfg.n_layers) RET_IF(proj_e(l + 1));
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
         {
-            EdgeGraph gh{e->erow, e->ecol, e->r0, x_cur, e->scalars + 1, 1536, nullptr, nullptr, edge_debug, nullptr};
+            EdgeGraph gh{e->erow, e->ecol, e->r0, x_cur, e->scalars + 1, 1536, nullptr, nullptr};
             EdgeProblem pc{e->pq + 512, e->pq + 1024, L.w1e_c, e->phi, 0.f, e->cfg.coords_range};
             EdgeProblem px{e->pq + 768, e->pq + 1280, L.w1e_x, e->psi, 0.f, e->cfg.coords_range};
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
@@ -616,7 +614,6 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
             break;
         }
         case 4: src = e->scalars; bytes = 8; break;
-        case 5: src = e->timeline; bytes = e->timeline ? 64 * 8 * 8 : 0; break;
         default: return set_err(DNDM_EINVAL, "unknown buffer id %d", what);
     }
     if (bytes > dst_bytes) bytes = dst_bytes;
