@@ -1,0 +1,40 @@
+"""CPU, world_size 2 over gloo: pocket sharding and the distributed ATP selection (the only exchange on the path)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from diffndm_b200.parallel import atp_select_distributed, shard_pockets
+    g = torch.Generator().manual_seed(0)
+    # 5 candidates in total, ragged: rank 0 owns 3, rank 1 owns 2
+    sizes_all = torch.tensor([4, 7, 5, 6, 3])
+    scores_all = torch.tensor([0.3, 0.9, 0.9, 0.1, 0.5])
+    z_all = torch.randn(int(sizes_all.sum()), 13, generator=g)
+    own = [0, 1, 2] if rank == 0 else [3, 4]
+    starts = torch.cumsum(sizes_all, 0) - sizes_all
+    z_own = torch.cat([z_all[int(starts[c]):int(starts[c] + sizes_all[c])] for c in own])
+    z, m, s = atp_select_distributed(scores_all[own], z_own, sizes_all[own], top_k=3)
+    # expected winners: candidates 1, 2 (tie broken by index), then 4
+    exp = torch.cat([z_all[int(starts[c]):int(starts[c] + sizes_all[c])] for c in (1, 2, 4)])
+    ok = torch.equal(z, exp) and s.tolist() == [7, 5, 3] and m.tolist() == [0] * 7 + [1] * 5 + [2] * 3
+    ok = ok and shard_pockets(7, rank, world) == list(range(rank, 7, world))
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_atp_selection_world2_gloo():
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)
