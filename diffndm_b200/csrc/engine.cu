@@ -162,6 +162,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     DndmEngine* e = new DndmEngine();
     e->cfg = *cfg;
     e->num_sms = prop.multiProcessorCount;
+    g_num_sms = e->num_sms;
     const size_t N = (size_t)((cfg->max_nodes + 127) / 128) * 128, E = cfg->max_edges, B = cfg->max_samples;
     const size_t tiles = (E + EK_TILE - 1) / EK_TILE + 1;
     RET_IF(dev_alloc(&e->x0, N * 3)); RET_IF(dev_alloc(&e->xa, N * 3)); RET_IF(dev_alloc(&e->xb, N * 3));
@@ -377,11 +378,14 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
+static int g_num_sms = 148;
 static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, int M, int Nout, int K, int a_col0,
-                       const GemmEpilogue& ep) {
+                       const GemmEpilogue& ep, int n_col0 = 0) {
     if (M <= 0) return DNDM_OK;
-    dim3 grid((M + GEMM_BM - 1) / GEMM_BM, Nout / GEMM_BN);
-    gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tw, M, K, a_col0, ep);
+    const int n_tiles = Nout / GEMM_BN;
+    const int total = ((M + GEMM_BM - 1) / GEMM_BM) * n_tiles;
+    const int grid = total < g_num_sms ? total : g_num_sms;
+    gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tw, M, K, a_col0, n_col0 / GEMM_BN, n_tiles, ep);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
@@ -442,8 +446,11 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
 
     {
         ProfScope ps(e, PROF_NODE, st);
-        encode_embed_kernel<<<node_blocks, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len, e->node_sample,
-                                                         e->enc_l, e->enc_p, e->x0, e->xa, e->xb, e->h, e->hcat);
+        const int lig_ctas = (n_lig + ENC_NODES_PER_CTA - 1) / ENC_NODES_PER_CTA;
+        const int pok_ctas = (n_pocket + ENC_NODES_PER_CTA - 1) / ENC_NODES_PER_CTA;
+        encode_embed_kernel<<<lig_ctas + pok_ctas, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len,
+                                                                 e->node_sample, e->enc_l, e->enc_p, lig_ctas, e->x0, e->xa,
+                                                                 e->xb, e->h, e->hcat);
         pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, st>>>(e->x0, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
         COUNT_LAUNCH(2);
     }
@@ -488,8 +495,10 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         // ---- node projections for this block's coordinate heads and the next block's edge model ----
         {
             ProfScope ps(e, PROF_GEMM, st);
+            // receiver parts (coord P | cross P) are only read for ligand rows; sender parts (Q) for every node
             GemmEpilogue ep{L.bias_c, 0, nullptr, 0, nullptr, 0, e->pq + 512, 1536};
-            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, N, 1024, 256, 0, ep));
+            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, n_lig, 512, 256, 0, ep, 0));
+            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, N, 512, 256, 0, ep, 512));
         }
         if (l + 1 < e->cfg.n_layers) RET_IF(proj_e(l + 1));
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
@@ -661,6 +670,11 @@ extern "C" int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const floa
     RET_IF(make_tmap_bf16(&ta, a_bf16, M, K, K, GEMM_BM));
     RET_IF(make_tmap_bf16(&tw, w_bf16, N, K, K, GEMM_BN));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+            g_num_sms = sms;
+    }
     GemmEpilogue ep{bias, act, nullptr, 0, out, N, nullptr, 0};
     return launch_gemm(st, ta, tw, M, N, K, 0, ep);
 }

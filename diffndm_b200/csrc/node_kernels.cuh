@@ -20,52 +20,58 @@ struct EncoderWeights {
     int nf, hid;
 };
 
+// One CTA = 256 threads = the 256 output channels; thread k keeps its row of Wc2 (<= 32 floats), w_t and bc in
+// registers and walks ENC_NODES_PER_CTA nodes, 8 at a time (hidden activations of the 8 nodes staged in smem).
+// CTAs [0, lig_ctas) take ligand atoms, the rest pocket atoms (different encoder weights).
+constexpr int ENC_NODES_PER_CTA = 64;
+constexpr int ENC_MAX_HID = 32;
+
 __global__ void __launch_bounds__(256)
 encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ xh_pok, int n_lig, int n_nodes,
                     int ld_lig, int ld_pok, const float* __restrict__ t, int t_len, const int* __restrict__ node_sample,
-                    EncoderWeights wl, EncoderWeights wp, float* __restrict__ x0, float* __restrict__ xa,
+                    EncoderWeights wl, EncoderWeights wp, int lig_ctas, float* __restrict__ x0, float* __restrict__ xa,
                     float* __restrict__ xb, float* __restrict__ h, __nv_bfloat16* __restrict__ hcat) {
-    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (node >= n_nodes) return;
-    const bool is_lig = node < n_lig;
-    const float* src = is_lig ? xh_lig + (size_t)node * ld_lig : xh_pok + (size_t)(node - n_lig) * ld_pok;
+    __shared__ float s_hid[8][ENC_MAX_HID];
+    __shared__ float s_t[8];
+    const bool is_lig = (int)blockIdx.x < lig_ctas;
     const EncoderWeights& w = is_lig ? wl : wp;
-    if (lane < 3) {
-        const float c = src[lane];
-        x0[3 * node + lane] = c;
-        xa[3 * node + lane] = c;
-        xb[3 * node + lane] = c;
-    }
-    // hidden layer: lane j < hid computes s_j
-    float s = 0.f;
-    if (lane < w.hid) {
-        float a = w.b1[lane];
-        for (int k = 0; k < w.nf; ++k) a = fmaf(w.w1[lane * w.nf + k], src[3 + k], a);
-        s = silu_f(a);
-    }
-    const float tv = t[t_len == 1 ? 0 : node_sample[node]];
-    float o[8];
+    const int first = is_lig ? blockIdx.x * ENC_NODES_PER_CTA : n_lig + (blockIdx.x - lig_ctas) * ENC_NODES_PER_CTA;
+    const int last = min(first + ENC_NODES_PER_CTA, is_lig ? n_lig : n_nodes);
+    const int k = threadIdx.x;
+    const int hid = w.hid, nf = w.nf;
+    float wrow[ENC_MAX_HID];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = 64 * i + 2 * lane;
-        o[2 * i] = fmaf(w.wt[k], tv, w.bc[k]);
-        o[2 * i + 1] = fmaf(w.wt[k + 1], tv, w.bc[k + 1]);
-    }
-    for (int j = 0; j < w.hid; ++j) {
-        const float sj = __shfl_sync(0xffffffffu, s, j);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = 64 * i + 2 * lane;
-            o[2 * i] = fmaf(w.wc2[k * w.hid + j], sj, o[2 * i]);
-            o[2 * i + 1] = fmaf(w.wc2[(k + 1) * w.hid + j], sj, o[2 * i + 1]);
+    for (int j = 0; j < ENC_MAX_HID; ++j) wrow[j] = (j < hid) ? w.wc2[k * hid + j] : 0.f;
+    const float wt = w.wt[k], bc = w.bc[k];
+    for (int n0 = first; n0 < last; n0 += 8) {
+        const int nn = min(8, last - n0);
+        // hidden layer of the encoder: thread (i, j) -> node n0+i, unit j
+        {
+            const int i = threadIdx.x / ENC_MAX_HID, j = threadIdx.x % ENC_MAX_HID;
+            if (i < nn && j < hid) {
+                const int node = n0 + i;
+                const float* src = is_lig ? xh_lig + (size_t)node * ld_lig : xh_pok + (size_t)(node - n_lig) * ld_pok;
+                float a = w.b1[j];
+                for (int q = 0; q < nf; ++q) a = fmaf(w.w1[j * nf + q], src[3 + q], a);
+                s_hid[i][j] = silu_f(a);
+                if (j < 3) {
+                    const float c = src[j];
+                    x0[3 * node + j] = c; xa[3 * node + j] = c; xb[3 * node + j] = c;
+                }
+                if (j == 3) s_t[i] = t[t_len == 1 ? 0 : node_sample[node]];
+            }
         }
-    }
+        __syncthreads();
+        for (int i = 0; i < nn; ++i) {
+            float o = fmaf(wt, s_t[i], bc);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = 64 * i + 2 * lane;
-        *reinterpret_cast<float2*>(h + (size_t)node * 256 + k) = make_float2(o[2 * i], o[2 * i + 1]);
-        *reinterpret_cast<uint32_t*>(hcat + (size_t)node * 512 + k) = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+            for (int j = 0; j < ENC_MAX_HID; ++j)
+                if (j < hid) o = fmaf(wrow[j], s_hid[i][j], o);
+            const int node = n0 + i;
+            h[(size_t)node * 256 + k] = o;
+            hcat[(size_t)node * 512 + k] = __float2bfloat16_rn(o);
+        }
+        __syncthreads();
     }
 }
 
