@@ -52,9 +52,13 @@ def parse():
     return ap.parse_args()
 
 
+POCKET_ATOMS = 330     # mean of the CrossDocked-shaped pocket-size distribution; same size on every rank so
+                       # that the weak-scaling runs compare equal per-GPU work (geometry / ligand sizes differ per rank)
+
+
 def make_inputs(rank, batch):
     from diffndm_b200 import synthetic
-    px, pt = synthetic.synthetic_pocket(rank)
+    px, pt = synthetic.synthetic_pocket(rank, POCKET_ATOMS)
     sizes = synthetic.synthetic_ligand_sizes(rank, batch)
     return px, pt, sizes, synthetic.make_batch(px, pt, sizes, rank)
 
@@ -63,6 +67,11 @@ def make_inputs(rank, batch):
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_step_seconds(batch, n_steps, warmup, rank=0):
+    try:   # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     from oracle import egnn_oracle as O
     from diffndm_b200.weights import DynamicsConfig, random_init
     W = random_init(DynamicsConfig(), 0, 0.3)
@@ -110,7 +119,7 @@ def run_reference(args):
 
 def workload_config(batch):
     return {'workload': f'crossdocked_fullatom_cond conditional sampling, synthetic CrossDocked-shaped pockets x {batch} '
-                        f'ligands, {T_STEPS} steps (BASELINE configs[1]); one pocket per GPU, random-init weights',
+                        f'ligands, {T_STEPS} steps (BASELINE configs[1]); one {POCKET_ATOMS}-atom pocket per GPU, random-init weights',
             'ligands_per_pocket': batch, 'timesteps': T_STEPS,
             'l2': 'per-step working set (node projections + activations) exceeds the 126 MB L2; no explicit flush'}
 

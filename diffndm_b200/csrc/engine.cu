@@ -22,6 +22,7 @@ using namespace dndm;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+static int g_num_sms = 148;
 static long long g_launches = 0;   // kernels of this library launched (or captured) so far
 #define COUNT_LAUNCH(n) (g_launches += (n))
 static int set_err(int code, const char* fmt, ...) {
@@ -378,7 +379,6 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static int g_num_sms = 148;
 static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, int M, int Nout, int K, int a_col0,
                        const GemmEpilogue& ep, int n_col0 = 0) {
     if (M <= 0) return DNDM_OK;
