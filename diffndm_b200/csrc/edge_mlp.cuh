@@ -10,19 +10,19 @@
 // remains.
 //
 // Persistent, warp-specialised CTA (384 threads, 1 CTA / SM):
-//   warps 8-11  producers : gather + first-layer epilogue -> bf16 A tile in SWIZZLE_128B K-major smem; one elected
-//                           lane issues the 16 tcgen05.mma (M128 N256 K16) of the tile into TMEM buffer (it & 1)
-//   warps 0-3   epilogue group 0 (even tiles of this CTA), warps 4-7 epilogue group 1 (odd tiles):
-//                           pass 1 (TMEM -> regs): m, attention dot, m written back to TMEM
-//                           pass 2: gated messages staged through smem, column-owner threads form the per-receiver
-//                           sums in row order and store them
-// W2 (128 KiB bf16) is TMA-loaded once per CTA and stays resident.  The MMA of tile i and the production of tile
-// i+1 run under the epilogues of tiles i-1 / i.
+//   warps 4-11  producers : gather + first-layer epilogue -> bf16 A tile in SWIZZLE_128B K-major smem (16 edges per
+//                           warp, 8 edges' gathers in flight); one elected lane issues the 16 tcgen05.mma
+//                           (M128 N256 K16) of the tile into TMEM accumulator (it & 1)
+//   warps 0-3   epilogue  : one thread per edge: tcgen05.ld -> m = SiLU(D + b2) -> dot with the attention / head
+//                           weights; GCL writes m (bf16) to the message buffer and att[e]; HEAD writes the scalar
+// W2 (128 KiB bf16) is TMA-loaded once per CTA and stays resident; the MMA of tile i and the production of tile i+1
+// run under the epilogue of tile i-1 (two TMEM accumulators).
 //
-// Determinism: edges are receiver-sorted (CSR).  Each (receiver, column) sum is accumulated by ONE thread in row
-// order (a per-tile segment table gives every receiver's row range); a receiver that continues from the previous
-// tile gets its leading partial written to tile_head[tile] and added later, in tile order, by agg_finalize_kernel.
-// No atomics anywhere.  P and Q are stored in bf16 (half the gather bytes; the sum and the distance terms are fp32).
+// The per-receiver sum is a separate streaming kernel (segment_reduce_kernel): edges are receiver-sorted, so the
+// messages of a node are one contiguous block that a warp adds up in edge order -- deterministic, no atomics, and it
+// emits the bf16 operand of the node MLP directly.  (An in-kernel segmented reduction through shared memory was
+// measured first: its staging + barriers made the epilogue 3x longer than the producer.)
+// P and Q are stored in bf16 (half the gather bytes); their sum and the distance terms are fp32.
 #pragma once
 #include "common.cuh"
 
@@ -33,9 +33,8 @@ constexpr int EK_H = 256;         // hidden size (UMMA N and K)
 constexpr int EK_THREADS = 384;
 constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
 constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
-constexpr int EK_STAGE_BYTES = 2 * EK_TILE * 33 * 4;    //  33792  (one padded [128 rows][33] fp32 buffer per epilogue group)
-constexpr int EK_MISC_BYTES = 2048;
-constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES + EK_MISC_BYTES;
+constexpr int EK_MISC_BYTES = 256 + 8 * 2 * 16 * 16;
+constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_MISC_BYTES;
 static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
 
 struct EdgeConsts {         // lives in the kernel-parameter constant bank: warp-uniform reads
@@ -59,8 +58,8 @@ struct EdgeGraph {
     const float* x;          // [N,3] current coordinates
     const int* n_edges;      // device scalar: number of edges this launch covers
     int ldpq;
-    float* agg;              // GCL: [N,256]
-    float* tile_head;        // GCL: [tiles,256]
+    __nv_bfloat16* msg;      // GCL: [E,256] ungated messages m_ij (bf16)
+    float* att;              // GCL: [E] attention gate / normalization_factor
 };
 
 DNDM_DEVICE void named_bar_sync(int id, int nthreads) {
@@ -89,10 +88,11 @@ DNDM_DEVICE void mbar_wait_park(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// pass 1 of the epilogue for one row: m = SiLU(D + b2) (b2 pre-halved), dot with wout; GCL writes m back to TMEM.
+// Epilogue of one tile row (one thread = one edge): m = SiLU(D + b2) (b2 pre-halved), dot with wout.
+// GCL additionally writes m as bf16 to the message buffer (64 contiguous bytes per 32-column chunk).
 // `cc` must be one of the __grid_constant__ kernel parameters so that b2/wout become constant-bank operands.
 template <bool kGCL>
-DNDM_DEVICE float epilogue_pass1(const EdgeConsts& cc, uint32_t d_tmem) {
+DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, __nv_bfloat16* msg_row, bool valid) {
     float dot = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -100,18 +100,28 @@ DNDM_DEVICE float epilogue_pass1(const EdgeConsts& cc, uint32_t d_tmem) {
         uint32_t v[32];
         tmem_ld32(d_tmem + col0, v);
         tmem_ld_wait();
+        float m[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const float m = silu_half(fmaf(__uint_as_float(v[j]), 0.5f, cc.b2[col0 + j]));
-            dot = fmaf(m, cc.wout[col0 + j], dot);
-            v[j] = __float_as_uint(m);
+            m[j] = silu_half(fmaf(__uint_as_float(v[j]), 0.5f, cc.b2[col0 + j]));
+            dot = fmaf(m[j], cc.wout[col0 + j], dot);
         }
-        if (kGCL) tmem_st32(d_tmem + col0, v);
+        if (kGCL && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_bf16x2(m[j], m[j + 1]);     o.y = pack_bf16x2(m[j + 2], m[j + 3]);
+                o.z = pack_bf16x2(m[j + 4], m[j + 5]); o.w = pack_bf16x2(m[j + 6], m[j + 7]);
+                *reinterpret_cast<uint4*>(msg_row + col0 + j) = o;
+            }
+        }
     }
     return dot;
 }
 
-constexpr int EK_ST_LD = 33;      // padded row stride (floats) of the staging buffer: conflict-free row writes / column reads
+constexpr int EK_EPI_WARPS = 4;                     // warps 0-3: epilogue (one TMEM lane quarter each)
+constexpr int EK_PROD_WARPS = 8;                    // warps 4-11: producers, 16 edges of every tile each
+constexpr int EK_PROD_THREADS = EK_PROD_WARPS * 32;
 
 template <bool kGCL>
 __global__ void __launch_bounds__(EK_THREADS, 1)
@@ -121,16 +131,12 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     extern __shared__ __align__(1024) uint8_t smem[];            // SW128 operand tiles need 1024-B alignment
     uint8_t* sW = smem;
     uint8_t* sA = smem + EK_W2_BYTES;
-    float* sStage = reinterpret_cast<float*>(smem + EK_W2_BYTES + EK_A_BYTES);   // [2 groups][128 rows][33]
-    uint8_t* misc = smem + EK_W2_BYTES + EK_A_BYTES + EK_STAGE_BYTES;
-    int* sRow = reinterpret_cast<int*>(misc);                    // [3][128] receiver per tile row (-1 = padding), slot it%3
-    uint8_t* sSeg = misc + 1536;                                 // [2][132] first row of every receiver segment (+ sentinel)
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc + 1536 + 272);
+    uint8_t* misc = smem + EK_W2_BYTES + EK_A_BYTES;
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc);
     uint64_t* mma_done = w_bar + 1;                              // [2]
     uint64_t* tmem_empty = mma_done + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    int* sCont = reinterpret_cast<int*>(tmem_slot + 1);          // [3] tile continues the previous tile's receiver
-    unsigned* sMask = reinterpret_cast<unsigned*>(sCont + 3);    // [2][4] per-quarter segment-start masks
+    int4* sMeta = reinterpret_cast<int4*>(misc + 256);           // [8 producer warps][2 slots][16 edges]
 
     const bool second = (blockIdx.y != 0);
     const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
@@ -146,8 +152,8 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         mbar_init(w_bar, 1);
         mbar_init(&mma_done[0], 1);
         mbar_init(&mma_done[1], 1);
-        mbar_init(&tmem_empty[0], 128);
-        mbar_init(&tmem_empty[1], 128);
+        mbar_init(&tmem_empty[0], EK_EPI_WARPS * 32);
+        mbar_init(&tmem_empty[1], EK_EPI_WARPS * 32);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -156,10 +162,11 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 8) {
+    if (warp >= EK_EPI_WARPS) {
         // =========================== producers (+ MMA issue) ===========================
-        const int pw = warp - 8;
-        if (tid == 8 * 32 && (int)blockIdx.x < num_tiles) {
+        const int pw = warp - EK_EPI_WARPS;
+        const bool issuer = (tid == EK_EPI_WARPS * 32);
+        if (issuer && (int)blockIdx.x < num_tiles) {
             mbar_arrive_expect_tx(w_bar, EK_W2_BYTES);
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
@@ -178,82 +185,80 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
         const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
         const uint32_t ld4 = (uint32_t)g.ldpq / 8;
-        // byte offset of this lane's 16-byte unit inside A row r: kc*16384 + r*128 + ((u ^ (r&7)) << 4)
-        uint8_t* sA_lane = sA + (lane >> 3) * 16384;
+        uint8_t* sA_lane = sA + (lane >> 3) * 16384;   // this lane's 16-byte unit of A row r: + r*128 + ((u ^ (r&7)) << 4)
         const uint32_t u = lane & 7;
+        // warp-private metadata slots: [2 tiles][16 edges] x (row, col, radial_now, radial_input)
+        int4* meta = sMeta + pw * 32;
+        const int l16 = lane & 15;
+
+        // ---- software pipeline over tiles: metadata two levels ahead, Q gathers one half-tile (8 edges) ahead ----
+        struct Meta { int row, col; float r0; };
+        auto meta_l1 = [&](int tile) {                       // level 1: edge -> (row, col, r0); padding edges use node 0
+            Meta m{0, 0, 0.f};
+            const int e = tile * EK_TILE + pw * 16 + l16;
+            if (tile < num_tiles && e < E) { m.row = g.erow[e]; m.col = g.ecol[e]; m.r0 = g.r0[e]; }
+            return m;
+        };
+        auto meta_l2 = [&](const Meta& m, int slot) {        // level 2: current squared distance; publish to the warp
+            const float dx = g.x[3 * m.row] - g.x[3 * m.col];
+            const float dy = g.x[3 * m.row + 1] - g.x[3 * m.col + 1];
+            const float dz = g.x[3 * m.row + 2] - g.x[3 * m.col + 2];
+            const float rad = dx * dx + dy * dy + dz * dz;
+            if (lane < 16) meta[slot * 16 + l16] = make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
+            __syncwarp();
+        };
+        auto issue_q = [&](uint4 (&qv)[8], int slot, int half) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) qv[jj] = __ldg(Qb + (uint32_t)meta[slot * 16 + half * 8 + jj].y * ld4);
+        };
+        auto compute_half = [&](const uint4 (&qv)[8], int slot, int half) {
+            uint4 pv[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) pv[jj] = __ldg(Pb + (uint32_t)meta[slot * 16 + half * 8 + jj].x * ld4);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int4 md = meta[slot * 16 + half * 8 + jj];
+                const float rad = __int_as_float(md.z), r0v = __int_as_float(md.w);
+                const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
+                const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[2 * i] = __uint_as_float(pw_[i] << 16) + __uint_as_float(qw_[i] << 16);
+                    v[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u) + __uint_as_float(qw_[i] & 0xffff0000u);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                const uint32_t r = pw * 16 + half * 8 + jj;
+                *reinterpret_cast<uint4*>(sA_lane + r * 128 + ((u ^ (r & 7)) << 4)) = o;
+            }
+        };
+
+        uint4 q0[8], q1[8];
+        {
+            const Meta m0 = meta_l1(blockIdx.x);
+            meta_l2(m0, 0);
+        }
+        Meta m_next = meta_l1(blockIdx.x + gridDim.x);
+        if ((int)blockIdx.x < num_tiles) issue_q(q0, 0, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const int e = tile * EK_TILE + pw * 32 + lane;
-            int my_row = -1, my_col = 0;
-            float my_rad = 0.f, my_r0 = 0.f;
-            if (e < E) {
-                my_row = g.erow[e];
-                my_col = g.ecol[e];
-                my_r0 = g.r0[e];
-                const float dx = g.x[3 * my_row] - g.x[3 * my_col];
-                const float dy = g.x[3 * my_row + 1] - g.x[3 * my_col + 1];
-                const float dz = g.x[3 * my_row + 2] - g.x[3 * my_col + 2];
-                my_rad = dx * dx + dy * dy + dz * dz;
-            }
-            const int ld_row = my_row < 0 ? 0 : my_row;                          // padding rows load node 0 (discarded)
+            const int buf = it & 1, slot = it & 1;
+            issue_q(q1, slot, 1);                                                // second half's senders
+            meta_l2(m_next, slot ^ 1);                                           // next tile's metadata -> other slot
+            m_next = meta_l1(tile + 2 * gridDim.x);                              // level-1 loads two tiles ahead
             if (it >= 1) mbar_wait_park(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);   // A smem free again
-            // row ids live in slot it%3: the epilogue of tile it-3 has finished (its TMEM buffer was re-acquired
-            // for tile it-1, whose MMA completion was awaited above), so production never waits for an epilogue
-            const int slot = it % 3;
-            sRow[slot * 128 + pw * 32 + lane] = my_row;
-            if (pw == 0 && lane == 0) sCont[slot] = (tile > 0) ? (g.erow[tile * EK_TILE - 1] == my_row) : 0;
-            float pf[8];                              // P row of the current receiver, unpacked once per receiver
-            int cur_r = -1;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pf[i] = 0.f;
-#pragma unroll 1
-            for (int j0 = 0; j0 < 32; j0 += 8) {
-                uint4 pv[8], qv[8];
-                int rj[8];
-                // gathers of the batch, all in flight together; P only when the receiver changes (rows are sorted)
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    rj[jj] = __shfl_sync(0xffffffffu, ld_row, j0 + jj);
-                    const int cj = __shfl_sync(0xffffffffu, my_col, j0 + jj);
-                    const int prev_r = (jj == 0) ? cur_r : rj[jj - 1];
-                    if (rj[jj] != prev_r) pv[jj] = __ldg(Pb + (size_t)rj[jj] * ld4);
-                    qv[jj] = __ldg(Qb + (size_t)cj * ld4);
-                }
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const float rad = __shfl_sync(0xffffffffu, my_rad, j0 + jj);
-                    const float r0v = __shfl_sync(0xffffffffu, my_r0, j0 + jj);
-                    if (rj[jj] != cur_r) {                                   // warp-uniform
-                        cur_r = rj[jj];
-                        const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            pf[2 * i] = __uint_as_float(pw_[i] << 16);
-                            pf[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u);
-                        }
-                    }
-                    const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[2 * i] = pf[2 * i] + __uint_as_float(qw_[i] << 16);
-                        v[2 * i + 1] = pf[2 * i + 1] + __uint_as_float(qw_[i] & 0xffff0000u);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
-                    uint4 o;
-                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                    const uint32_t r = pw * 32 + j0 + jj;
-                    *reinterpret_cast<uint4*>(sA_lane + r * 128 + ((u ^ (r & 7)) << 4)) = o;
-                }
-            }
+            compute_half(q0, slot, 0);
+            if (tile + (int)gridDim.x < num_tiles) issue_q(q0, slot ^ 1, 0);     // first half of the NEXT tile
+            compute_half(q1, slot, 1);
             fence_proxy_async_smem();
             tc_fence_before_sync();
-            named_bar_sync(1, 128);                   // all four producer warps have written A / sRow
-            if (tid == 8 * 32) {
-                if (it >= 2) mbar_wait_park(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained by its epilogue group
+            named_bar_sync(1, EK_PROD_THREADS);       // all producer warps have written their rows of A
+            if (issuer) {
+                if (it >= 2) mbar_wait_park(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained by the epilogue
                 tc_fence_after_sync();
                 if (it == 0) mbar_wait(w_bar, 0);
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H;
@@ -271,90 +276,79 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             __syncwarp();   // re-converge the issuing lane: without it the warp stays split for the whole next tile
         }
     } else {
-        // =========================== epilogue groups ===========================
-        const int grp = warp >> 2;         // handles tiles with (it & 1) == grp
-        const int q = warp & 3;            // TMEM lane quarter of this warp
-        const int trow = q * 32 + lane;    // tile row owned in passes 1/2
-        float* st = sStage + grp * (EK_TILE * EK_ST_LD);
-        uint8_t* seg = sSeg + grp * 132;
-        unsigned* xm = sMask + grp * 4;
+        // =========================== epilogue (warps 0-3, one thread per edge of the tile) ===========================
+        const int q = warp;                // TMEM lane quarter
+        const int trow = q * 32 + lane;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            if ((it & 1) != grp) continue;
-            const int slot = it % 3;
-            const int* rows = sRow + slot * 128;
-            mbar_wait_park(&mma_done[grp], (it >> 1) & 1);
+            const int buf = it & 1;
+            const int e = tile * EK_TILE + trow;
+            const bool valid = e < E;
+            mbar_wait_park(&mma_done[buf], (it >> 1) & 1);
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + (uint32_t)grp * EK_H + ((uint32_t)(q * 32) << 16);
-            const int my_node = rows[trow];
-            int n_seg = 0;
-            bool head0 = false;
-            if (kGCL) {
-                // receiver segments of the tile: row r starts one if its receiver differs from row r-1's
-                // (row 0 always starts segment 0; head0 marks it as the continuation of the previous tile's receiver)
-                const int prev = trow > 0 ? rows[trow - 1] : -2;
-                const bool start = (trow == 0) || (my_node != prev);
-                const unsigned mine = __ballot_sync(0xffffffffu, start);
-                if (lane == 0) xm[q] = mine;
-                named_bar_sync(2 + grp, 128);
-                int before = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int pc = __popc(xm[k]);
-                    if (k < q) before += pc;
-                    n_seg += pc;
-                }
-                if (start) seg[before + __popc(mine & ((1u << lane) - 1u))] = (uint8_t)trow;
-                if (trow == 0) seg[n_seg] = 128;
-                head0 = sCont[slot] != 0;
-                named_bar_sync(2 + grp, 128);       // segment table visible
-            }
-            // ---- pass 1 ----
-            const float dot = second ? epilogue_pass1<kGCL>(c1, d_tmem) : epilogue_pass1<kGCL>(c0, d_tmem);
-            if (!kGCL) {
-                if (my_node >= 0) pr.head_out[tile * EK_TILE + trow] = pr.out_scale * tanhf(dot);
-            } else {
-                tmem_st_wait();
-                const float att = sigmoid_fast(dot + pr.bout) * pr.out_scale;
-                float* my_st = st + trow * EK_ST_LD;
-#pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    const int col0 = c * 32;
-                    uint32_t v[32];
-                    tmem_ld32(d_tmem + col0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) my_st[j] = __uint_as_float(v[j]) * att;
-                    named_bar_sync(2 + grp, 128);
-                    // ---- per-receiver column sums: warp q takes segments q, q+4, ...; lane = column.  Two interleaved
-                    //      partial sums (even / odd rows) combined at the end: fixed order, short dependency chains ----
-                    for (int s = q; s < n_seg; s += 4) {
-                        const int a = seg[s], b = seg[s + 1];
-                        const int node = rows[a];
-                        if (node < 0) continue;
-                        const float* p = st + a * EK_ST_LD + lane;
-                        float a0 = 0.f, a1 = 0.f;
-                        int r = a;
-                        for (; r + 8 <= b; r += 8, p += 8 * EK_ST_LD) {
-                            const float v0 = p[0], v1 = p[EK_ST_LD], v2 = p[2 * EK_ST_LD], v3 = p[3 * EK_ST_LD];
-                            const float v4 = p[4 * EK_ST_LD], v5 = p[5 * EK_ST_LD], v6 = p[6 * EK_ST_LD], v7 = p[7 * EK_ST_LD];
-                            a0 += v0; a1 += v1; a0 += v2; a1 += v3; a0 += v4; a1 += v5; a0 += v6; a1 += v7;
-                        }
-                        for (; r < b; ++r, p += EK_ST_LD) a0 += p[0];
-                        const float acc = a0 + a1;
-                        if (s == 0 && head0) g.tile_head[(size_t)tile * EK_H + col0 + lane] = acc;
-                        else g.agg[(size_t)node * EK_H + col0 + lane] = acc;
-                    }
-                    named_bar_sync(2 + grp, 128);      // stage buffer free for the next chunk
-                }
-            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H + ((uint32_t)(q * 32) << 16);
+            __nv_bfloat16* msg_row = kGCL ? g.msg + (size_t)e * EK_H : nullptr;
+            const float dot = second ? epilogue_row<kGCL>(c1, d_tmem, msg_row, valid) : epilogue_row<kGCL>(c0, d_tmem, msg_row, valid);
             tc_fence_before_sync();
-            mbar_arrive(&tmem_empty[grp]);
+            mbar_arrive(&tmem_empty[buf]);             // accumulator drained: the MMA of tile it+2 may overwrite it
+            if (valid) {
+                if (kGCL) g.att[e] = sigmoid_fast(dot + pr.bout) * pr.out_scale;
+                else pr.head_out[e] = pr.out_scale * tanhf(dot);
+            }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// Deterministic per-receiver reduction of the gated messages (replaces unsorted_segment_sum, egnn_new.py:319-335, and
+// feeds the node MLP):  agg[n] = sum_{e in row n} att[e] * msg[e]  in CSR (= edge) order, written as the bf16 operand
+// half hcat[n][256:512].  One warp per node, lane = 8 columns; the messages of a node are one contiguous block.
+__global__ void __launch_bounds__(256)
+segment_reduce_kernel(const __nv_bfloat16* __restrict__ msg, const float* __restrict__ att, const int* __restrict__ row_ptr,
+                      int n_nodes, __nv_bfloat16* __restrict__ hcat) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (node >= n_nodes) return;
+    const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const uint4* mp = reinterpret_cast<const uint4*>(msg) + lane;            // row stride 32 uint4
+    int e = e0;
+    for (; e + 4 <= e1; e += 4) {
+        uint4 v[4];
+        float a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = __ldg(mp + (size_t)(e + k) * 32);
+            a[k] = __ldg(att + e + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[2 * i] = fmaf(a[k], __uint_as_float(w[i] << 16), acc[2 * i]);
+                acc[2 * i + 1] = fmaf(a[k], __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
+            }
+        }
+    }
+    for (; e < e1; ++e) {
+        const uint4 v = __ldg(mp + (size_t)e * 32);
+        const float a = __ldg(att + e);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc[2 * i] = fmaf(a, __uint_as_float(w[i] << 16), acc[2 * i]);
+            acc[2 * i + 1] = fmaf(a, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
+        }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(hcat + (size_t)node * 512 + 256 + 8 * lane) = o;
 }
 
 }  // namespace dndm

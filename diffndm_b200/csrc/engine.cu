@@ -87,7 +87,8 @@ struct DndmEngine {
     int num_sms = 148;
     bool weights_loaded = false;
     // workspace
-    float *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *agg = nullptr, *tile_head = nullptr;
+    float *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *att = nullptr;
+    __nv_bfloat16* msg = nullptr;  // [E,256] bf16 edge messages of the current block
     __nv_bfloat16* pq = nullptr;   // [N,1536] bf16 node projections: edge P|Q, coord P, cross P, coord Q, cross Q
     float *r0 = nullptr, *phi = nullptr, *psi = nullptr, *pocket_sum = nullptr;
     __nv_bfloat16 *hcat = nullptr, *hid = nullptr;
@@ -165,10 +166,9 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     e->num_sms = prop.multiProcessorCount;
     g_num_sms = e->num_sms;
     const size_t N = (size_t)((cfg->max_nodes + 127) / 128) * 128, E = cfg->max_edges, B = cfg->max_samples;
-    const size_t tiles = (E + EK_TILE - 1) / EK_TILE + 1;
     RET_IF(dev_alloc(&e->x0, N * 3)); RET_IF(dev_alloc(&e->xa, N * 3)); RET_IF(dev_alloc(&e->xb, N * 3));
-    RET_IF(dev_alloc(&e->h, N * 256)); RET_IF(dev_alloc(&e->pq, N * 1536)); RET_IF(dev_alloc(&e->agg, N * 256));
-    RET_IF(dev_alloc(&e->tile_head, tiles * 256));
+    RET_IF(dev_alloc(&e->h, N * 256)); RET_IF(dev_alloc(&e->pq, N * 1536));
+    RET_IF(dev_alloc(&e->msg, (E + 128) * 256)); RET_IF(dev_alloc(&e->att, E + 128));
     RET_IF(dev_alloc(&e->r0, E)); RET_IF(dev_alloc(&e->phi, E)); RET_IF(dev_alloc(&e->psi, E));
     RET_IF(dev_alloc(&e->pocket_sum, B * 3));
     RET_IF(dev_alloc(&e->hcat, N * 512)); RET_IF(dev_alloc(&e->hid, N * 256));
@@ -199,7 +199,7 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     if (!e) return;
     free_weights(e);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
-    void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->agg, e->tile_head, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
+    void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->msg, e->att, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
                     e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->flags};
     for (void* p : bufs) cudaFree(p);
     delete e;
@@ -472,7 +472,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     for (int l = 0; l < e->cfg.n_layers; ++l) {
         LayerWeights& L = e->layers[l];
         // ---- GCL edge model + attention + deterministic aggregation ----
-        EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->agg, e->tile_head};
+        EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->msg, e->att};
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
@@ -481,7 +481,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         }
         {
             ProfScope ps(e, PROF_NODE, st);
-            agg_finalize_kernel<<<node_blocks, 256, 0, st>>>(e->agg, e->tile_head, e->row_ptr, N, e->hcat);
+            segment_reduce_kernel<<<node_blocks, 256, 0, st>>>(e->msg, e->att, e->row_ptr, N, e->hcat);
         }
         COUNT_LAUNCH(2);
         // ---- node MLP with residual ----

@@ -76,37 +76,6 @@ encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// (a8) finish the deterministic segment sum: add, in tile order, the leading partials of receivers whose
-// edge range crosses 128-edge tile boundaries, and emit the bf16 operand [h | agg] of the node MLP.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-agg_finalize_kernel(const float* __restrict__ agg, const float* __restrict__ tile_head, const int* __restrict__ row_ptr,
-                    int n_nodes, __nv_bfloat16* __restrict__ hcat) {
-    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (node >= n_nodes) return;
-    const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (e1 > e0) {
-        const float* ap = agg + (size_t)node * 256 + 8 * lane;
-        a = *reinterpret_cast<const float4*>(ap);
-        b = *reinterpret_cast<const float4*>(ap + 4);
-        const int t0 = e0 >> 7, t1 = (e1 - 1) >> 7;
-        for (int t = t0 + 1; t <= t1; ++t) {
-            const float* hp = tile_head + (size_t)t * 256 + 8 * lane;
-            const float4 c = *reinterpret_cast<const float4*>(hp);
-            const float4 d = *reinterpret_cast<const float4*>(hp + 4);
-            a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
-            b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
-        }
-    }
-    uint4 o;
-    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
-    *reinterpret_cast<uint4*>(hcat + (size_t)node * 512 + 256 + 8 * lane) = o;
-}
-
-// ------------------------------------------------------------------------------------------------
 // (a5,a7) coordinate update of the ligand atoms (pocket atoms are frozen: update_coords_mask, dynamics.py:130-132)
 //   x_i += sum_j ( n_ij phi_ij + c_ij psi_ij ) / norm       egnn_new.py:96-123, coord2diff :296-302, coord2cross :305-316
 // One warp per ligand atom; lanes stride the CSR row, fixed-order shuffle reduction (deterministic).
