@@ -9,9 +9,9 @@
 //   HEAD: out[e] = range * tanh(w5 . m)                                       (coord / cross scalar heads)
 // remains.
 //
-// Persistent, warp-specialised CTA (384 threads, 1 CTA / SM):
-//   warps 4-11  producers : gather + first-layer epilogue -> bf16 A tile in SWIZZLE_128B K-major smem (16 edges per
-//                           warp, 8 edges' gathers in flight); one elected lane issues the 16 tcgen05.mma
+// Persistent, warp-specialised CTA (640 threads, 1 CTA / SM, <= 96 registers per thread):
+//   warps 4-19  producers : gather + first-layer epilogue -> bf16 A tile in SWIZZLE_128B K-major smem (8 edges per
+//                           warp and tile, metadata prefetched a tile ahead); one elected lane issues the 16 tcgen05.mma
 //                           (M128 N256 K16) of the tile into TMEM accumulator (it & 1)
 //   warps 0-3   epilogue  : one thread per edge: tcgen05.ld -> m = SiLU(D + b2) -> dot with the attention / head
 //                           weights; GCL writes m (bf16) to the message buffer and att[e]; HEAD writes the scalar
@@ -30,10 +30,10 @@ namespace dndm {
 
 constexpr int EK_TILE = 128;      // edges per tile (UMMA M)
 constexpr int EK_H = 256;         // hidden size (UMMA N and K)
-constexpr int EK_THREADS = 384;
+constexpr int EK_THREADS = 640;    // 4 epilogue + 16 producer warps, <= 96 registers each: latency hidden by warps
 constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
 constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
-constexpr int EK_MISC_BYTES = 256 + 8 * 2 * 16 * 16;
+constexpr int EK_MISC_BYTES = 256 + 16 * 2 * 8 * 16;
 constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_MISC_BYTES;
 static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
 
@@ -95,20 +95,20 @@ template <bool kGCL>
 DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, __nv_bfloat16* msg_row, bool valid) {
     float dot = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int col0 = c * 32;
-        uint32_t v[32];
-        tmem_ld32(d_tmem + col0, v);
+    for (int c = 0; c < 16; ++c) {
+        const int col0 = c * 16;
+        uint32_t v[16];
+        tmem_ld16(d_tmem + col0, v);
         tmem_ld_wait();
-        float m[32];
+        float m[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
             m[j] = silu_half(fmaf(__uint_as_float(v[j]), 0.5f, cc.b2[col0 + j]));
             dot = fmaf(m[j], cc.wout[col0 + j], dot);
         }
         if (kGCL && valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < 16; j += 8) {
                 uint4 o;
                 o.x = pack_bf16x2(m[j], m[j + 1]);     o.y = pack_bf16x2(m[j + 2], m[j + 3]);
                 o.z = pack_bf16x2(m[j + 4], m[j + 5]); o.w = pack_bf16x2(m[j + 6], m[j + 7]);
@@ -120,7 +120,7 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, __nv_bfloa
 }
 
 constexpr int EK_EPI_WARPS = 4;                     // warps 0-3: epilogue (one TMEM lane quarter each)
-constexpr int EK_PROD_WARPS = 8;                    // warps 4-11: producers, 16 edges of every tile each
+constexpr int EK_PROD_WARPS = 16;                   // warps 4-19: producers, 8 edges of every tile each
 constexpr int EK_PROD_THREADS = EK_PROD_WARPS * 32;
 
 template <bool kGCL>
@@ -136,7 +136,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     uint64_t* mma_done = w_bar + 1;                              // [2]
     uint64_t* tmem_empty = mma_done + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    int4* sMeta = reinterpret_cast<int4*>(misc + 256);           // [8 producer warps][2 slots][16 edges]
+    int4* sMeta = reinterpret_cast<int4*>(misc + 256);           // [16 producer warps][2 slots][8 edges]
 
     const bool second = (blockIdx.y != 0);
     const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
@@ -187,15 +187,16 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         const uint32_t ld4 = (uint32_t)g.ldpq / 8;
         uint8_t* sA_lane = sA + (lane >> 3) * 16384;   // this lane's 16-byte unit of A row r: + r*128 + ((u ^ (r&7)) << 4)
         const uint32_t u = lane & 7;
-        // warp-private metadata slots: [2 tiles][16 edges] x (row, col, radial_now, radial_input)
-        int4* meta = sMeta + pw * 32;
-        const int l16 = lane & 15;
+        // warp-private metadata slots: [2 tiles][8 edges] x (row, col, radial_now, radial_input)
+        int4* meta = sMeta + pw * 16;
+        const int l8 = lane & 7;
 
-        // ---- software pipeline over tiles: metadata two levels ahead, Q gathers one half-tile (8 edges) ahead ----
+        // metadata is fetched one tile ahead (two dependent global loads); gathers are issued 4 edges at a time and
+        // their latency is hidden by the other producer warps of the SM sub-partition
         struct Meta { int row, col; float r0; };
         auto meta_l1 = [&](int tile) {                       // level 1: edge -> (row, col, r0); padding edges use node 0
             Meta m{0, 0, 0.f};
-            const int e = tile * EK_TILE + pw * 16 + l16;
+            const int e = tile * EK_TILE + pw * 8 + l8;
             if (tile < num_tiles && e < E) { m.row = g.erow[e]; m.col = g.ecol[e]; m.r0 = g.r0[e]; }
             return m;
         };
@@ -204,21 +205,21 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             const float dy = g.x[3 * m.row + 1] - g.x[3 * m.col + 1];
             const float dz = g.x[3 * m.row + 2] - g.x[3 * m.col + 2];
             const float rad = dx * dx + dy * dy + dz * dz;
-            if (lane < 16) meta[slot * 16 + l16] = make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
+            if (lane < 8) meta[slot * 8 + l8] = make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
             __syncwarp();
         };
-        auto issue_q = [&](uint4 (&qv)[8], int slot, int half) {
+        auto compute4 = [&](int slot, int half) {
+            uint4 pv[4], qv[4];
+            int4 md[4];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) qv[jj] = __ldg(Qb + (uint32_t)meta[slot * 16 + half * 8 + jj].y * ld4);
-        };
-        auto compute_half = [&](const uint4 (&qv)[8], int slot, int half) {
-            uint4 pv[8];
+            for (int jj = 0; jj < 4; ++jj) {
+                md[jj] = meta[slot * 8 + half * 4 + jj];
+                pv[jj] = __ldg(Pb + (uint32_t)md[jj].x * ld4);
+                qv[jj] = __ldg(Qb + (uint32_t)md[jj].y * ld4);
+            }
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) pv[jj] = __ldg(Pb + (uint32_t)meta[slot * 16 + half * 8 + jj].x * ld4);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const int4 md = meta[slot * 16 + half * 8 + jj];
-                const float rad = __int_as_float(md.z), r0v = __int_as_float(md.w);
+            for (int jj = 0; jj < 4; ++jj) {
+                const float rad = __int_as_float(md[jj].z), r0v = __int_as_float(md[jj].w);
                 const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
                 const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
                 float v[8];
@@ -232,28 +233,24 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 uint4 o;
                 o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
                 o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                const uint32_t r = pw * 16 + half * 8 + jj;
+                const uint32_t r = pw * 8 + half * 4 + jj;
                 *reinterpret_cast<uint4*>(sA_lane + r * 128 + ((u ^ (r & 7)) << 4)) = o;
             }
         };
 
-        uint4 q0[8], q1[8];
         {
             const Meta m0 = meta_l1(blockIdx.x);
             meta_l2(m0, 0);
         }
         Meta m_next = meta_l1(blockIdx.x + gridDim.x);
-        if ((int)blockIdx.x < num_tiles) issue_q(q0, 0, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1, slot = it & 1;
-            issue_q(q1, slot, 1);                                                // second half's senders
             meta_l2(m_next, slot ^ 1);                                           // next tile's metadata -> other slot
             m_next = meta_l1(tile + 2 * gridDim.x);                              // level-1 loads two tiles ahead
             if (it >= 1) mbar_wait_park(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);   // A smem free again
-            compute_half(q0, slot, 0);
-            if (tile + (int)gridDim.x < num_tiles) issue_q(q0, slot ^ 1, 0);     // first half of the NEXT tile
-            compute_half(q1, slot, 1);
+            compute4(slot, 0);
+            compute4(slot, 1);
             fence_proxy_async_smem();
             tc_fence_before_sync();
             named_bar_sync(1, EK_PROD_THREADS);       // all producer warps have written their rows of A
