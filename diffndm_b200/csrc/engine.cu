@@ -56,6 +56,19 @@ static PFN_encodeTiled get_encode_fn() {
     }
     return fn;
 }
+static int make_tmap_f32_out(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled (f32 out) failed with %d", (int)r);
+    return DNDM_OK;
+}
 // bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128-byte swizzle.
 static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     PFN_encodeTiled fn = get_encode_fn();
@@ -96,6 +109,7 @@ struct DndmEngine {
     int *ecol = nullptr, *erow = nullptr, *scalars = nullptr;
     unsigned* flags = nullptr;
     CUtensorMap tm_hcat, tm_hid;
+    CUtensorMap to_pq, to_hid, to_hcat, to_h;   // TMA-store destinations of the node GEMMs (32-row boxes)
     // weights
     std::vector<LayerWeights> layers;
     std::vector<void*> weight_allocs;
@@ -181,6 +195,10 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaMemset(e->hid, 0, N * 256 * 2));
     RET_IF(make_tmap_bf16(&e->tm_hcat, e->hcat, N, 512, 512, GEMM_BM));
     RET_IF(make_tmap_bf16(&e->tm_hid, e->hid, N, 256, 256, GEMM_BM));
+    RET_IF(make_tmap_bf16(&e->to_pq, e->pq, N, 1536, 1536, 32));
+    RET_IF(make_tmap_bf16(&e->to_hid, e->hid, N, 256, 256, 32));
+    RET_IF(make_tmap_bf16(&e->to_hcat, e->hcat, N, 512, 512, 32));
+    RET_IF(make_tmap_f32_out(&e->to_h, e->h, N, 256, 256));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
@@ -379,13 +397,13 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, int M, int Nout, int K, int a_col0,
-                       const GemmEpilogue& ep, int n_col0 = 0) {
+static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to16,
+                       const CUtensorMap& to32, int M, int Nout, int K, int a_col0, const GemmEpilogue& ep, int n_col0 = 0) {
     if (M <= 0) return DNDM_OK;
     const int n_tiles = Nout / GEMM_BN;
     const int total = ((M + GEMM_BM - 1) / GEMM_BM) * n_tiles;
     const int grid = total < g_num_sms ? total : g_num_sms;
-    gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tw, M, K, a_col0, n_col0 / GEMM_BN, n_tiles, ep);
+    gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tw, to16, to32, M, K, a_col0, n_col0 / GEMM_BN, n_tiles, ep);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
@@ -465,8 +483,8 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
 
     auto proj_e = [&](int l) -> int {
         ProfScope ps(e, PROF_GEMM, st);
-        GemmEpilogue ep{e->layers[l].bias_e, 0, nullptr, 0, nullptr, 0, e->pq, 1536};
-        return launch_gemm(st, e->tm_hcat, e->layers[l].tm_proj_e, N, 512, 256, 0, ep);
+        GemmEpilogue ep{e->layers[l].bias_e, 0, nullptr, 0, 0, 0, 1, 0};
+        return launch_gemm(st, e->tm_hcat, e->layers[l].tm_proj_e, e->to_pq, e->to_h, N, 512, 256, 0, ep);
     };
     RET_IF(proj_e(0));
     for (int l = 0; l < e->cfg.n_layers; ++l) {
@@ -487,18 +505,18 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         // ---- node MLP with residual ----
         {
             ProfScope ps(e, PROF_GEMM, st);
-            GemmEpilogue ep1{L.b3, 1, nullptr, 0, nullptr, 0, e->hid, 256};
-            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_w3, N, 256, 512, 0, ep1));
-            GemmEpilogue ep2{L.b4, 0, e->h, 256, e->h, 256, e->hcat, 512};
-            RET_IF(launch_gemm(st, e->tm_hid, L.tm_w4, N, 256, 256, 0, ep2));
+            GemmEpilogue ep1{L.b3, 1, nullptr, 0, 0, 0, 1, 0};
+            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_w3, e->to_hid, e->to_h, N, 256, 512, 0, ep1));
+            GemmEpilogue ep2{L.b4, 0, e->h, 256, 1, 0, 1, 0};          // h += ...; bf16 copy -> hcat[:, :256]
+            RET_IF(launch_gemm(st, e->tm_hid, L.tm_w4, e->to_hcat, e->to_h, N, 256, 256, 0, ep2));
         }
         // ---- node projections for this block's coordinate heads and the next block's edge model ----
         {
             ProfScope ps(e, PROF_GEMM, st);
             // receiver parts (coord P | cross P) are only read for ligand rows; sender parts (Q) for every node
-            GemmEpilogue ep{L.bias_c, 0, nullptr, 0, nullptr, 0, e->pq + 512, 1536};
-            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, n_lig, 512, 256, 0, ep, 0));
-            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, N, 512, 256, 0, ep, 512));
+            GemmEpilogue ep{L.bias_c, 0, nullptr, 0, 0, 0, 1, 512};      // pq columns 512.. hold the coordinate-head projections
+            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, e->to_pq, e->to_h, n_lig, 512, 256, 0, ep, 0));
+            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, e->to_pq, e->to_h, N, 512, 256, 0, ep, 512));
         }
         if (l + 1 < e->cfg.n_layers) RET_IF(proj_e(l + 1));
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
@@ -666,15 +684,16 @@ extern "C" int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const floa
     if (!a_bf16 || !w_bf16 || !out) return set_err(DNDM_EINVAL, "null argument");
     if (K % GEMM_BK != 0 || N % GEMM_BN != 0 || M < 1) return set_err(DNDM_EINVAL, "need K %% 64 == 0 and N %% 128 == 0");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CUtensorMap ta, tw;
+    CUtensorMap ta, tw, to;
     RET_IF(make_tmap_bf16(&ta, a_bf16, M, K, K, GEMM_BM));
     RET_IF(make_tmap_bf16(&tw, w_bf16, N, K, K, GEMM_BN));
+    RET_IF(make_tmap_f32_out(&to, out, M, N, N));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
             g_num_sms = sms;
     }
-    GemmEpilogue ep{bias, act, nullptr, 0, out, N, nullptr, 0};
-    return launch_gemm(st, ta, tw, M, N, K, 0, ep);
+    GemmEpilogue ep{bias, act, nullptr, 0, 1, 0, 0, 0};
+    return launch_gemm(st, ta, tw, to, to, M, N, K, 0, ep);
 }

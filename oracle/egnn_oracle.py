@@ -415,6 +415,26 @@ def spsa_update(z_lig, xh_pocket, perturbations, f_plus, f_minus, lig_mask, pock
 
 
 # ----------------------------------------------------------------------------
+# (a14) ATP selection -- conditional_model.py:1203-1232
+# ----------------------------------------------------------------------------
+def atp_select(r0, r, s, big_z, big_pocket, big_lig_mask, big_pocket_mask, top_k):
+    """mixed = r0*(s/250) + r*(250 - s/250)  [sic, :1203]; global top-k over all candidates (:1205); winners re-batched
+    in rank order (:1212-1232).  Ties are broken by the lower candidate index (torch.topk on CPU keeps that order for
+    the fixtures used here).  Returns (z_lig, xh_pocket, lig_mask) of the selected candidates."""
+    r0 = np.asarray(r0, np.float32)
+    r = np.asarray(r, np.float32)
+    mixed = r0 * np.float32(s / 250) + r * np.float32(250 - s / 250)
+    order = np.argsort(-mixed, kind='stable')[:top_k]
+    zs, ps, ms = [], [], []
+    for rank, idx in enumerate(order):
+        nm = big_lig_mask == idx
+        zs.append(big_z[nm])
+        ps.append(big_pocket[big_pocket_mask == idx])
+        ms.append(np.full(int(nm.sum()), rank, np.int64))
+    return np.concatenate(zs), np.concatenate(ps), np.concatenate(ms), order
+
+
+# ----------------------------------------------------------------------------
 # algorithmic work model (SURVEY.md §8d)
 # ----------------------------------------------------------------------------
 def reference_flops(n_nodes, n_edges, cfg: OracleConfig = OracleConfig()):

@@ -318,6 +318,73 @@ def test_spsa_update_vs_oracle(dyn, dev):
     assert np.abs(xp.cpu().numpy() - xpr).max() < 1e-4 * max(1.0, np.abs(xpr).max())
 
 
+def test_x0_lookahead_vs_oracle(dyn, dev, golden_weights):
+    """my_to_x0 (conditional_model.py:457-468): z0 = (z_t - sigma_t eps)/alpha_t, then the p(x,h|z0) head."""
+    from diffndm_b200.sampler import ConditionalSampler
+    c = FWD_CASES['synth60_b3']
+    B = 3
+    smp = ConditionalSampler(dyn, timesteps=500)
+    lm, pm = c['lig_mask'], c['pocket_mask']
+    t = np.full((B, 1), 30 / 500, np.float32)
+    rng = np.random.default_rng(5)
+    noise = rng.standard_normal(c['xh_lig'].shape).astype(np.float32)
+    x_l, h_l, x_p, h_p = smp.my_to_x0(torch.from_numpy(t), _t(c['xh_lig'], dev), _t(c['xh_pocket'], dev), _t(lm, dev), _t(pm, dev),
+                                      B, noise=_t(noise, dev))
+    g = O.gamma_table()
+    eps_t, _ = O.dynamics_forward(golden_weights, c['xh_lig'], c['xh_pocket'], t, lm, pm, CFG)
+    z0 = O.x0_lookahead_z0(c['xh_lig'], eps_t, np.full(B, g[30]), lm)
+    eps0, _ = O.dynamics_forward(golden_weights, z0, c['xh_pocket'], np.zeros((B, 1), np.float32), lm, pm, CFG)
+    xr, types, xpr, hpr = O.sample_p_xh_given_z0(z0, c['xh_pocket'], eps0, noise, np.full(B, g[0]), lm, pm, CFG)
+    assert np.abs(x_l.cpu().numpy() - xr).max() < 2e-3 * max(1.0, np.abs(xr).max())
+    assert np.abs(x_p.cpu().numpy() - xpr).max() < 2e-3 * max(1.0, np.abs(xpr).max())
+    assert np.array_equal(h_l.argmax(1).cpu().numpy(), types)
+    assert np.abs(h_p.cpu().numpy() - hpr).max() < 1e-5
+
+
+def test_atp_event_vs_oracle(dyn, dev):
+    """ATP ("SVDD") event (conditional_model.py:1085-1241) with the candidate groups batched along the sample axis:
+    the selection (mixed reward [sic], global top-k, re-batching) must equal the oracle's on the engine's own candidates."""
+    from diffndm_b200 import synthetic
+    from diffndm_b200.sampler import ConditionalSampler
+    px, pt = synthetic.synthetic_pocket(8, 50)
+    sizes = np.array([6, 9, 5, 7])
+    b = synthetic.make_batch(px, pt, sizes, 8)
+    B, G, s = 4, 3, 20
+    smp = ConditionalSampler(dyn, timesteps=500)
+    rec = []
+
+    def reward(x, types, mask):
+        x = x.cpu().numpy().astype(np.float64)
+        m = mask.cpu().numpy()
+        r = np.array([np.sqrt(((x[m == i] - x[m == i].mean(0)) ** 2).sum(1).mean()) + 0.01 * i for i in range(m.max() + 1)])
+        rec.append((x.copy(), m.copy(), r.copy()))
+        return r.tolist()
+
+    torch.manual_seed(0)
+    s_arr = torch.full((B, 1), s / 500)
+    t_arr = torch.full((B, 1), (s + 1) / 500)
+    z, xp, lm = smp._atp_event(s, s_arr, t_arr, _t(b['xh_lig'], dev), _t(b['xh_pocket'], dev), _t(b['lig_mask'], dev),
+                               _t(b['pocket_mask'], dev), B, reward, G)
+    (x0, m0, r0), (xc, mc, rc) = rec           # look-ahead molecules, then current-state molecules
+    assert m0.max() + 1 == G * B and np.array_equal(m0, mc)
+    # rebuild the candidate batch the event scored: group 0 is the incoming state, coordinates of the current-state call
+    n_l, n_p = len(b['lig_mask']), len(b['pocket_mask'])
+    assert np.abs(xc[:n_l] - b['xh_lig'][:, :3]).max() < 1e-6
+    big_pm = np.concatenate([b['pocket_mask'] + g * B for g in range(G)])
+    # selection on the recorded rewards (the candidates themselves are engine outputs)
+    order = np.argsort(-(r0.astype(np.float32) * np.float32(s / 250) + rc.astype(np.float32) * np.float32(250 - s / 250)),
+                       kind='stable')[:B]
+    lm_np = lm.cpu().numpy()
+    assert np.array_equal(np.bincount(lm_np), np.bincount(mc, minlength=G * B)[order])
+    zc = z.cpu().numpy()
+    start = 0
+    for rank, idx in enumerate(order):
+        n = int((mc == idx).sum())
+        assert np.abs(zc[start:start + n, :3] - xc[mc == idx]).max() < 1e-6
+        start += n
+    assert xp.shape[0] == n_p and z.shape[0] == len(lm_np)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full benchmark size: properties that do not need the oracle to finish
 # ---------------------------------------------------------------------------------------------------------------
