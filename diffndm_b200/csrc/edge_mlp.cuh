@@ -14,7 +14,8 @@
 //                           warp and tile, metadata prefetched a tile ahead); one elected lane issues the 16 tcgen05.mma
 //                           (M128 N256 K16) of the tile into TMEM accumulator (it & 1)
 //   warps 0-3   epilogue  : one thread per edge: tcgen05.ld -> m = SiLU(D + b2) -> dot with the attention / head
-//                           weights; GCL writes m (bf16) to the message buffer and att[e]; HEAD writes the scalar
+//                           weights; GCL stages m (bf16) in a swizzled smem slab per warp and TMA-stores it to the
+//                           message buffer, plus att[e]; HEAD writes the scalar
 // W2 (128 KiB bf16) is TMA-loaded once per CTA and stays resident; the MMA of tile i and the production of tile i+1
 // run under the epilogue of tile i-1 (two TMEM accumulators).
 //
@@ -33,7 +34,7 @@ constexpr int EK_H = 256;         // hidden size (UMMA N and K)
 constexpr int EK_THREADS = 640;    // 4 epilogue + 16 producer warps, <= 96 registers each: latency hidden by warps
 constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
 constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
-constexpr int EK_MISC_BYTES = 256 + 16 * 2 * 8 * 16;
+constexpr int EK_MISC_BYTES = 256 + 16 * 2 * 8 * 16 + 3840 + 4 * 4096;   // barriers, metadata, pad to 1 KiB, message slabs
 constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_MISC_BYTES;
 static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
 
@@ -91,9 +92,15 @@ DNDM_DEVICE void mbar_wait_park(uint64_t* bar, uint32_t parity) {
 // Epilogue of one tile row (one thread = one edge): m = SiLU(D + b2) (b2 pre-halved), dot with wout.
 // GCL additionally writes m as bf16 to the message buffer (64 contiguous bytes per 32-column chunk).
 // `cc` must be one of the __grid_constant__ kernel parameters so that b2/wout become constant-bank operands.
+// GCL additionally stages m as bf16 in this warp's shared-memory slab ([32 rows][64 columns], SWIZZLE_128B) and hands
+// every finished 64-column quarter to a TMA store into the message buffer.
+// `cc` must be one of the __grid_constant__ kernel parameters so that b2/wout become constant-bank operands.
 template <bool kGCL>
-DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, __nv_bfloat16* msg_row, bool valid) {
+DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* slab, const CUtensorMap* tmap_msg, int row0,
+                               int lane) {
     float dot = 0.f;
+    uint8_t* rowp = slab + lane * 128;
+    const uint32_t sw = lane & 7;
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
         const int col0 = c * 16;
@@ -106,13 +113,26 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, __nv_bfloa
             m[j] = silu_half(fmaf(__uint_as_float(v[j]), 0.5f, cc.b2[col0 + j]));
             dot = fmaf(m[j], cc.wout[col0 + j], dot);
         }
-        if (kGCL && valid) {
+        if (kGCL) {
+            if ((c & 3) == 0) {                        // slab reuse: the previous quarter's TMA store has read it
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+            }
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {
                 uint4 o;
                 o.x = pack_bf16x2(m[j], m[j + 1]);     o.y = pack_bf16x2(m[j + 2], m[j + 3]);
                 o.z = pack_bf16x2(m[j + 4], m[j + 5]); o.w = pack_bf16x2(m[j + 6], m[j + 7]);
-                *reinterpret_cast<uint4*>(msg_row + col0 + j) = o;
+                const uint32_t unit = (c & 3) * 2 + (j >> 3);
+                *reinterpret_cast<uint4*>(rowp + ((unit ^ sw) << 4)) = o;
+            }
+            if ((c & 3) == 3) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(tmap_msg, slab, (c >> 2) * 64, row0);
+                    tma_store_commit();
+                }
             }
         }
     }
@@ -126,7 +146,7 @@ constexpr int EK_PROD_THREADS = EK_PROD_WARPS * 32;
 template <bool kGCL>
 __global__ void __launch_bounds__(EK_THREADS, 1)
 edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
-                const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,
+                const __grid_constant__ CUtensorMap tmap_msg, const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,
                 EdgeGraph g, EdgeProblem p0, EdgeProblem p1) {
     extern __shared__ __align__(1024) uint8_t smem[];            // SW128 operand tiles need 1024-B alignment
     uint8_t* sW = smem;
@@ -137,6 +157,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     uint64_t* tmem_empty = mma_done + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     int4* sMeta = reinterpret_cast<int4*>(misc + 256);           // [16 producer warps][2 slots][8 edges]
+    uint8_t* sSlab = misc + 8192;                          // [4 epilogue warps][32 rows][128 B] message staging
 
     const bool second = (blockIdx.y != 0);
     const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
@@ -284,8 +305,10 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             mbar_wait_park(&mma_done[buf], (it >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H + ((uint32_t)(q * 32) << 16);
-            __nv_bfloat16* msg_row = kGCL ? g.msg + (size_t)e * EK_H : nullptr;
-            const float dot = second ? epilogue_row<kGCL>(c1, d_tmem, msg_row, valid) : epilogue_row<kGCL>(c0, d_tmem, msg_row, valid);
+            uint8_t* slab = sSlab + q * 4096;
+            const int row0 = tile * EK_TILE + q * 32;
+            const float dot = second ? epilogue_row<kGCL>(c1, d_tmem, slab, &tmap_msg, row0, lane)
+                                     : epilogue_row<kGCL>(c0, d_tmem, slab, &tmap_msg, row0, lane);
             tc_fence_before_sync();
             mbar_arrive(&tmem_empty[buf]);             // accumulator drained: the MMA of tile it+2 may overwrite it
             if (valid) {
@@ -294,6 +317,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             }
         }
     }
+    if (kGCL && warp < EK_EPI_WARPS && lane == 0) tma_store_wait_all();   // message writes complete before exit
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);

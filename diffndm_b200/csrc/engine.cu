@@ -109,7 +109,8 @@ struct DndmEngine {
     int *ecol = nullptr, *erow = nullptr, *scalars = nullptr;
     unsigned* flags = nullptr;
     CUtensorMap tm_hcat, tm_hid;
-    CUtensorMap to_pq, to_hid, to_hcat, to_h;   // TMA-store destinations of the node GEMMs (32-row boxes)
+    CUtensorMap to_pq, to_hid, to_hcat, to_h;
+    CUtensorMap to_msg;                          // TMA-store destination of the edge messages (box 32 rows x 64 cols)   // TMA-store destinations of the node GEMMs (32-row boxes)
     // weights
     std::vector<LayerWeights> layers;
     std::vector<void*> weight_allocs;
@@ -199,6 +200,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(make_tmap_bf16(&e->to_hid, e->hid, N, 256, 256, 32));
     RET_IF(make_tmap_bf16(&e->to_hcat, e->hcat, N, 512, 512, 32));
     RET_IF(make_tmap_f32_out(&e->to_h, e->h, N, 256, 256));
+    RET_IF(make_tmap_bf16(&e->to_msg, e->msg, E + 128, 256, 256, 32));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
@@ -494,7 +496,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
-            edge_mlp_kernel<true><<<dim3(e->num_sms, 1), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_e, L.tm_w2_e, L.c_e, L.c_e,
+            edge_mlp_kernel<true><<<dim3(e->num_sms, 1), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e, L.c_e,
                                                                                           g, pe, pe);
         }
         {
@@ -527,7 +529,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
             {
                 ProfScope ps(e, PROF_HEAD, st);
-                edge_mlp_kernel<false><<<dim3(gx, 2), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_c, L.tm_w2_x, L.c_c, L.c_x, gh,
+                edge_mlp_kernel<false><<<dim3(gx, 2), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_c, L.tm_w2_x, e->to_msg, L.c_c, L.c_x, gh,
                                                                                        pc, px);
             }
             ProfScope ps2(e, PROF_NODE, st);
