@@ -337,35 +337,45 @@ segment_reduce_kernel(const __nv_bfloat16* __restrict__ msg, const float* __rest
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     const uint4* mp = reinterpret_cast<const uint4*>(msg) + lane;            // row stride 32 uint4
-    int e = e0;
-    for (; e + 4 <= e1; e += 4) {
-        uint4 v[4];
-        float a[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[k] = __ldg(mp + (size_t)(e + k) * 32);
-            a[k] = __ldg(att + e + k);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                acc[2 * i] = fmaf(a[k], __uint_as_float(w[i] << 16), acc[2 * i]);
-                acc[2 * i + 1] = fmaf(a[k], __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
-            }
-        }
-    }
-    for (; e < e1; ++e) {
-        const uint4 v = __ldg(mp + (size_t)e * 32);
-        const float a = __ldg(att + e);
+    auto ld_stream = [](const uint4* p) {                                     // read-once data: do not pollute L1
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        return v;
+    };
+    auto fma_row = [&](const uint4& v, float a) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             acc[2 * i] = fmaf(a, __uint_as_float(w[i] << 16), acc[2 * i]);
             acc[2 * i + 1] = fmaf(a, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
         }
+    };
+    int e = e0;
+    for (; e + 8 <= e1; e += 8) {
+        uint4 v[8];
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = ld_stream(mp + (size_t)(e + k) * 32);
+            a[k] = __ldg(att + e + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fma_row(v[k], a[k]);
     }
+    if (e + 4 <= e1) {
+        uint4 v[4];
+        float a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = ld_stream(mp + (size_t)(e + k) * 32);
+            a[k] = __ldg(att + e + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fma_row(v[k], a[k]);
+        e += 4;
+    }
+    for (; e < e1; ++e) fma_row(ld_stream(mp + (size_t)e * 32), __ldg(att + e));
     uint4 o;
     o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
     o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
