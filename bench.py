@@ -311,8 +311,12 @@ def run_b200(args):
             peak, peak_src = 1590.0, 'fallback (B200_PROFILING.md)'
         t_launch = g_ms / max(g_n, 1) * 1e-3
         achieved = E_edges * EXEC_FLOP_PER_EDGE_GCL / t_launch / 1e12
+        # DRAM traffic of the kernel from the committed `ncu --set full` capture of this exact workload
+        # (profiles/r1_edge_kernel_ncu_raw.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch); other batch sizes: null
+        traffic = 47.57e6 + 284.61e6 if (B == 100 and POCKET_ATOMS == 330) else None
         roof = {'bound': 'tensor', 'kernel': 'edge_mlp_kernel<GCL>', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': 'profiles/r1_edge_kernel_ncu_raw.txt',
+                'peak_source': peak_src,
                 'us_per_launch': t_launch * 1e6, 'edges_per_launch': E_edges,
                 'flop_per_edge_executed': EXEC_FLOP_PER_EDGE_GCL,
                 'achieved_reference_equivalent': E_edges * REF_FLOP_PER_EDGE_GCL / t_launch / 1e12,
