@@ -106,7 +106,7 @@ struct DndmEngine {
     float *r0 = nullptr, *phi = nullptr, *psi = nullptr, *pocket_sum = nullptr;
     __nv_bfloat16 *hcat = nullptr, *hid = nullptr;
     int *node_sample = nullptr, *lig_ptr = nullptr, *pok_ptr = nullptr, *deg = nullptr, *row_ptr = nullptr;
-    int *ecol = nullptr, *erow = nullptr, *scalars = nullptr;
+    int *ecol = nullptr, *erow = nullptr, *scalars = nullptr, *block_sums = nullptr;
     unsigned* flags = nullptr;
     CUtensorMap tm_hcat, tm_hid;
     CUtensorMap to_pq, to_hid, to_hcat, to_h;
@@ -189,7 +189,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(dev_alloc(&e->hcat, N * 512)); RET_IF(dev_alloc(&e->hid, N * 256));
     RET_IF(dev_alloc(&e->node_sample, N)); RET_IF(dev_alloc(&e->lig_ptr, B + 1)); RET_IF(dev_alloc(&e->pok_ptr, B + 1));
     RET_IF(dev_alloc(&e->deg, N)); RET_IF(dev_alloc(&e->row_ptr, N + 1));
-    RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 4));
+    RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 4)); RET_IF(dev_alloc(&e->block_sums, 1024));
     RET_IF(dev_alloc(&e->flags, 1));
     CU_CHECK(cudaMemset(e->flags, 0, 4));
     CU_CHECK(cudaMemset(e->hcat, 0, N * 512 * 2));
@@ -220,7 +220,7 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     free_weights(e);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->msg, e->att, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
-                    e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->flags};
+                    e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->flags};
     for (void* p : bufs) cudaFree(p);
     delete e;
 }
@@ -441,9 +441,17 @@ static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, cu
     gp.cut2_i = sq(e->cfg.edge_cutoff_interaction);
     const int blocks = (n_nodes * 32 + 255) / 256;
     graph_rows_kernel<false><<<blocks, 256, 0, st>>>(gp, e->deg, nullptr, nullptr, nullptr, nullptr, e->cfg.max_edges);
-    graph_scan_kernel<<<1, 1024, 0, st>>>(e->deg, e->row_ptr, n_nodes, n_lig, e->cfg.max_edges, e->scalars, e->flags);
+    {
+        const int nb = (n_nodes + SCAN_ELEMS - 1) / SCAN_ELEMS;
+        if (nb > 1024) return set_err(DNDM_ECAPACITY, "more than %d nodes per call are not supported by the scan", 1024 * SCAN_ELEMS);
+        scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(e->deg, n_nodes, e->block_sums);
+        scan_offsets_kernel<<<1, 1024, 0, st>>>(e->block_sums, nb, n_nodes, n_lig, e->cfg.max_edges, e->row_ptr, e->scalars,
+                                               e->flags);
+        scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(e->deg, e->block_sums, n_nodes, n_lig, e->cfg.max_edges, e->row_ptr,
+                                                       e->scalars);
+    }
     graph_rows_kernel<true><<<blocks, 256, 0, st>>>(gp, nullptr, e->row_ptr, e->ecol, e->erow, e->r0, e->cfg.max_edges);
-    COUNT_LAUNCH(3);
+    COUNT_LAUNCH(5);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
 }

@@ -72,53 +72,104 @@ graph_rows_kernel(GraphParams p, int* deg, const int* row_ptr, int* ecol, int* e
     if (!kFill && lane == 0) deg[i] = count;
 }
 
-// Exclusive scan of deg[0..n) -> row_ptr[0..n], single CTA (n is ~1e4..1e5).  Also publishes
-// scalars[0] = E, scalars[1] = E_lig = row_ptr[n_lig] and raises flag bit 2 when E exceeds capacity.
-__global__ void __launch_bounds__(1024)
-graph_scan_kernel(const int* deg, int* row_ptr, int n, int n_lig, int max_edges, int* scalars, unsigned* flags) {
-    __shared__ int warp_sums[32];
-    __shared__ int carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int beg = min(tid * per, n), end = min(beg + per, n);
+// Exclusive scan of deg[0..n) -> row_ptr[0..n] in three small launches (reduce / scan of block sums / rescan):
+//   blocks of SCAN_ELEMS elements with coalesced loads.  The middle kernel also publishes scalars[0] = E,
+//   scalars[1] = E_lig = row_ptr[n_lig] (set by the last kernel) and raises flag bit 2 when E exceeds capacity.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ELEMS = 2048;          // per block, 8 per thread
+
+DNDM_DEVICE int block_reduce_sum(int v, int* smem_warp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) smem_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) t += smem_warp[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_block_sums_kernel(const int* __restrict__ deg, int n, int* __restrict__ block_sums) {
+    __shared__ int sw[SCAN_THREADS / 32];
+    const int base = blockIdx.x * SCAN_ELEMS;
     int s = 0;
-    for (int i = beg; i < end; ++i) s += deg[i];
-    int incl = s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ELEMS / SCAN_THREADS; ++k) {
+        const int i = base + k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += deg[i];
+    }
+    const int tot = block_reduce_sum(s, sw);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_offsets_kernel(int* __restrict__ block_sums, int n_blocks, int n, int n_lig, int max_edges, int* __restrict__ row_ptr,
+                    int* __restrict__ scalars, unsigned* __restrict__ flags) {
+    // n_blocks <= 1024: one thread per block sum, warp-shuffle scan
+    __shared__ int warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v = tid < n_blocks ? block_sums[tid] : 0;
+    int incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31) warp_sums[warp] = incl;
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        int w = warp_sums[lane];
+        const int w = warp_tot[lane];
         int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= o) wi += t;
         }
-        warp_sums[lane] = wi - w;     // exclusive
-        if (lane == 31) carry = wi;
+        warp_tot[lane] = wi - w;
+        if (lane == 31) {
+            const int E = wi;
+            row_ptr[n] = E;
+            scalars[0] = min(E, max_edges);
+            if (n_lig >= n) scalars[1] = min(E, max_edges);          // no pocket rows: every edge has a ligand receiver
+            if (E > max_edges) atomicOr(flags, 4u);
+        }
     }
     __syncthreads();
-    int run = warp_sums[warp] + incl - s;
-    for (int i = beg; i < end; ++i) {
-        row_ptr[i] = run;
-        run += deg[i];
+    if (tid < n_blocks) block_sums[tid] = warp_tot[warp] + incl - v;     // exclusive offset of each block
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_kernel(const int* __restrict__ deg, const int* __restrict__ block_offs, int n, int n_lig, int max_edges,
+                  int* __restrict__ row_ptr, int* __restrict__ scalars) {
+    // thread t owns 8 consecutive elements; block-level exclusive scan of the per-thread sums
+    __shared__ int sw[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.x * SCAN_ELEMS + tid * 8;
+    int d[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        d[k] = (i0 + k < n) ? deg[i0 + k] : 0;
+        s += d[k];
     }
-    __syncthreads();
-    if (tid == 0) {
-        const int E = carry;
-        row_ptr[n] = E;
-        scalars[0] = min(E, max_edges);
-        if (E > max_edges) atomicOr(flags, 4u);
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
+    if (lane == 31) sw[warp] = incl;
     __syncthreads();
-    if (tid == 0) {
-        // E_lig = row_ptr[n_lig]; all row_ptr entries were written above by this CTA
-        scalars[1] = min(n_lig < n ? row_ptr[n_lig] : carry, max_edges);
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += sw[w];
+    int run = block_offs[blockIdx.x] + woff + incl - s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (i0 + k < n) {
+            row_ptr[i0 + k] = run;
+            if (i0 + k == n_lig) scalars[1] = min(run, max_edges);      // E_lig = row_ptr[n_lig]
+        }
+        run += d[k];
     }
 }
 
