@@ -31,6 +31,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version / debug lines on stdout by default; stdout is reserved for the one JSON line
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 T_STEPS = 500
 CALLS_PER_TRAJ = T_STEPS + 1
