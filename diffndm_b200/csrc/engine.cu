@@ -107,6 +107,8 @@ struct DndmEngine {
     __nv_bfloat16 *hcat = nullptr, *hid = nullptr;
     int *node_sample = nullptr, *lig_ptr = nullptr, *pok_ptr = nullptr, *deg = nullptr, *row_ptr = nullptr;
     int *ecol = nullptr, *erow = nullptr, *scalars = nullptr, *block_sums = nullptr;
+    int *deg_act = nullptr, *rp_act = nullptr, *erow_c = nullptr, *ecol_c = nullptr;   // last-block compacted graph
+    float* r0_c = nullptr;
     unsigned* flags = nullptr;
     CUtensorMap tm_hcat, tm_hid;
     CUtensorMap to_pq, to_hid, to_hcat, to_h;
@@ -190,6 +192,8 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(dev_alloc(&e->node_sample, N)); RET_IF(dev_alloc(&e->lig_ptr, B + 1)); RET_IF(dev_alloc(&e->pok_ptr, B + 1));
     RET_IF(dev_alloc(&e->deg, N)); RET_IF(dev_alloc(&e->row_ptr, N + 1));
     RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 4)); RET_IF(dev_alloc(&e->block_sums, 1024));
+    RET_IF(dev_alloc(&e->deg_act, N)); RET_IF(dev_alloc(&e->rp_act, N + 1)); RET_IF(dev_alloc(&e->erow_c, E + 1));
+    RET_IF(dev_alloc(&e->ecol_c, E)); RET_IF(dev_alloc(&e->r0_c, E));
     RET_IF(dev_alloc(&e->flags, 1));
     CU_CHECK(cudaMemset(e->flags, 0, 4));
     CU_CHECK(cudaMemset(e->hcat, 0, N * 512 * 2));
@@ -220,7 +224,8 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     free_weights(e);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->msg, e->att, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
-                    e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->flags};
+                    e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->deg_act, e->rp_act, e->erow_c,
+                    e->ecol_c, e->r0_c, e->flags};
     for (void* p : bufs) cudaFree(p);
     delete e;
 }
@@ -432,6 +437,33 @@ static int prepare_batch(DndmEngine* e, const int64_t* lig_mask, const int64_t* 
     return DNDM_OK;
 }
 
+// exclusive scan of deg[0..n) -> out[0..n]; total -> scalars[slot_total]; out[n_lig] -> scalars[slot_lig] (if >= 0)
+static int exclusive_scan(DndmEngine* e, const int* deg, int* out, int n, int n_lig, int slot_total, int slot_lig,
+                          cudaStream_t st) {
+    const int nb = (n + SCAN_ELEMS - 1) / SCAN_ELEMS;
+    if (nb > 1024) return set_err(DNDM_ECAPACITY, "more than %d nodes per call are not supported by the scan", 1024 * SCAN_ELEMS);
+    scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(deg, n, e->block_sums);
+    scan_offsets_kernel<<<1, 1024, 0, st>>>(e->block_sums, nb, n, n_lig, e->cfg.max_edges, out, e->scalars, e->flags, slot_total,
+                                           slot_lig);
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(deg, e->block_sums, n, n_lig, e->cfg.max_edges, out, e->scalars, slot_lig);
+    COUNT_LAUNCH(3);
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
+// compacted edge list of the receivers the LAST block still needs (ligand atoms + their pocket senders)
+static int build_last_block_edges(DndmEngine* e, int n_lig, int n_nodes, cudaStream_t st) {
+    mark_active_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol, e->deg, e->scalars, n_lig, n_nodes, e->deg_act, 0);
+    mark_active_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol, e->deg, e->scalars, n_lig, n_nodes, e->deg_act, 1);
+    COUNT_LAUNCH(2);
+    RET_IF(exclusive_scan(e, e->deg_act, e->rp_act, n_nodes, n_lig, 2, -1, st));
+    compact_edges_kernel<<<(n_nodes * 32 + 255) / 256, 256, 0, st>>>(e->row_ptr, e->rp_act, e->erow, e->ecol, e->r0, n_nodes,
+                                                                     e->erow_c, e->ecol_c, e->r0_c);
+    COUNT_LAUNCH(1);
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
 static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, cudaStream_t st) {
     GraphParams gp;
     gp.x = x; gp.lig_ptr = e->lig_ptr; gp.pok_ptr = e->pok_ptr; gp.node_sample = e->node_sample;
@@ -441,17 +473,9 @@ static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, cu
     gp.cut2_i = sq(e->cfg.edge_cutoff_interaction);
     const int blocks = (n_nodes * 32 + 255) / 256;
     graph_rows_kernel<false><<<blocks, 256, 0, st>>>(gp, e->deg, nullptr, nullptr, nullptr, nullptr, e->cfg.max_edges);
-    {
-        const int nb = (n_nodes + SCAN_ELEMS - 1) / SCAN_ELEMS;
-        if (nb > 1024) return set_err(DNDM_ECAPACITY, "more than %d nodes per call are not supported by the scan", 1024 * SCAN_ELEMS);
-        scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(e->deg, n_nodes, e->block_sums);
-        scan_offsets_kernel<<<1, 1024, 0, st>>>(e->block_sums, nb, n_nodes, n_lig, e->cfg.max_edges, e->row_ptr, e->scalars,
-                                               e->flags);
-        scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(e->deg, e->block_sums, n_nodes, n_lig, e->cfg.max_edges, e->row_ptr,
-                                                       e->scalars);
-    }
+    RET_IF(exclusive_scan(e, e->deg, e->row_ptr, n_nodes, n_lig, 0, 1, st));
     graph_rows_kernel<true><<<blocks, 256, 0, st>>>(gp, nullptr, e->row_ptr, e->ecol, e->erow, e->r0, e->cfg.max_edges);
-    COUNT_LAUNCH(5);
+    COUNT_LAUNCH(2);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
 }
@@ -496,11 +520,18 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         GemmEpilogue ep{e->layers[l].bias_e, 0, nullptr, 0, 0, 0, 1, 0};
         return launch_gemm(st, e->tm_hcat, e->layers[l].tm_proj_e, e->to_pq, e->to_h, N, 512, 256, 0, ep);
     };
+    const bool prune_last = (out_pocket == nullptr) && n_pocket > 0;
+    if (prune_last) {
+        ProfScope ps(e, PROF_GRAPH, st);
+        RET_IF(build_last_block_edges(e, n_lig, N, st));
+    }
     RET_IF(proj_e(0));
     for (int l = 0; l < e->cfg.n_layers; ++l) {
         LayerWeights& L = e->layers[l];
+        const bool pruned = prune_last && (l + 1 == e->cfg.n_layers);
         // ---- GCL edge model + attention + deterministic aggregation ----
-        EdgeGraph g{e->erow, e->ecol, e->r0, x_cur, e->scalars + 0, 1536, e->msg, e->att};
+        EdgeGraph g{pruned ? e->erow_c : e->erow, pruned ? e->ecol_c : e->ecol, pruned ? e->r0_c : e->r0, x_cur,
+                    e->scalars + (pruned ? 2 : 0), 1536, e->msg, e->att};
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
@@ -509,7 +540,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         }
         {
             ProfScope ps(e, PROF_NODE, st);
-            segment_reduce_kernel<<<node_blocks, 256, 0, st>>>(e->msg, e->att, e->row_ptr, N, e->hcat);
+            segment_reduce_kernel<<<node_blocks, 256, 0, st>>>(e->msg, e->att, pruned ? e->rp_act : e->row_ptr, N, e->hcat);
         }
         COUNT_LAUNCH(2);
         // ---- node MLP with residual ----
@@ -650,7 +681,7 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
             src = e->ecol; bytes = (int64_t)sc[0] * 4;
             break;
         }
-        case 4: src = e->scalars; bytes = 8; break;
+        case 4: src = e->scalars; bytes = 16; break;
         default: return set_err(DNDM_EINVAL, "unknown buffer id %d", what);
     }
     if (bytes > dst_bytes) bytes = dst_bytes;

@@ -105,7 +105,7 @@ scan_block_sums_kernel(const int* __restrict__ deg, int n, int* __restrict__ blo
 
 __global__ void __launch_bounds__(1024)
 scan_offsets_kernel(int* __restrict__ block_sums, int n_blocks, int n, int n_lig, int max_edges, int* __restrict__ row_ptr,
-                    int* __restrict__ scalars, unsigned* __restrict__ flags) {
+                    int* __restrict__ scalars, unsigned* __restrict__ flags, int slot_total, int slot_lig) {
     // n_blocks <= 1024: one thread per block sum, warp-shuffle scan
     __shared__ int warp_tot[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -130,8 +130,8 @@ scan_offsets_kernel(int* __restrict__ block_sums, int n_blocks, int n, int n_lig
         if (lane == 31) {
             const int E = wi;
             row_ptr[n] = E;
-            scalars[0] = min(E, max_edges);
-            if (n_lig >= n) scalars[1] = min(E, max_edges);          // no pocket rows: every edge has a ligand receiver
+            scalars[slot_total] = min(E, max_edges);
+            if (n_lig >= n && slot_lig >= 0) scalars[slot_lig] = min(E, max_edges);   // no pocket rows
             if (E > max_edges) atomicOr(flags, 4u);
         }
     }
@@ -141,7 +141,7 @@ scan_offsets_kernel(int* __restrict__ block_sums, int n_blocks, int n, int n_lig
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_apply_kernel(const int* __restrict__ deg, const int* __restrict__ block_offs, int n, int n_lig, int max_edges,
-                  int* __restrict__ row_ptr, int* __restrict__ scalars) {
+                  int* __restrict__ row_ptr, int* __restrict__ scalars, int slot_lig) {
     // thread t owns 8 consecutive elements; block-level exclusive scan of the per-thread sums
     __shared__ int sw[SCAN_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -167,9 +167,49 @@ scan_apply_kernel(const int* __restrict__ deg, const int* __restrict__ block_off
     for (int k = 0; k < 8; ++k) {
         if (i0 + k < n) {
             row_ptr[i0 + k] = run;
-            if (i0 + k == n_lig) scalars[1] = min(run, max_edges);      // E_lig = row_ptr[n_lig]
+            if (i0 + k == n_lig && slot_lig >= 0) scalars[slot_lig] = min(run, max_edges);      // E_lig = row_ptr[n_lig]
         }
         run += d[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact dead-work elimination for the LAST block when the caller discards the pocket output (every conditional
+// sampler call site does: `eps, _ = dynamics(...)`): after the last block only ligand rows of h are decoded, and the
+// last coordinate update reads h of the ligand atoms and of the pocket atoms that send to a ligand atom.  So the last
+// GCL only has to aggregate for receivers in  L u P1,  P1 = {pocket j : exists ligand-row edge (i, j)}.
+//   mark_active_kernel : deg_act[n] = deg[n] for n in L u P1, else 0
+//   (scan)             : rp_act = exclusive scan of deg_act; scalars[2] = number of kept edges
+//   compact_edges_kernel: copies the kept rows of (erow, ecol, r0) to the compacted arrays
+// ------------------------------------------------------------------------------------------------
+__global__ void mark_active_kernel(const int* __restrict__ ecol, const int* __restrict__ deg, const int* __restrict__ scalars,
+                                   int n_lig, int n_nodes, int* __restrict__ deg_act, int pass) {
+    const int stride = gridDim.x * blockDim.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pass == 0) {                      // ligand rows keep their degree, pocket rows start at 0
+        for (int n = t; n < n_nodes; n += stride) deg_act[n] = n < n_lig ? deg[n] : 0;
+    } else {                              // every pocket sender of a ligand row becomes active (idempotent writes)
+        const int e_lig = scalars[1];
+        for (int e = t; e < e_lig; e += stride) {
+            const int c = ecol[e];
+            if (c >= n_lig) deg_act[c] = deg[c];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+compact_edges_kernel(const int* __restrict__ row_ptr, const int* __restrict__ rp_act, const int* __restrict__ erow,
+                     const int* __restrict__ ecol, const float* __restrict__ r0, int n_nodes, int* __restrict__ erow_c,
+                     int* __restrict__ ecol_c, float* __restrict__ r0_c) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (node >= n_nodes) return;
+    const int a0 = rp_act[node], a1 = rp_act[node + 1];
+    const int s0 = row_ptr[node];
+    for (int k = lane; k < a1 - a0; k += 32) {
+        erow_c[a0 + k] = erow[s0 + k];
+        ecol_c[a0 + k] = ecol[s0 + k];
+        r0_c[a0 + k] = r0[s0 + k];
     }
 }
 

@@ -243,10 +243,15 @@ class Engine:
 
     def graph_stats(self):
         """(E, E_ligand_receiver) of the last forward / radius_graph call (synchronises)."""
-        t = torch.zeros(2, dtype=torch.int32, device=torch.device('cuda', self.device))
-        _check(self.lib, self.lib.dndm_debug_copy(self._h, 4, _ptr(t), 8, _stream()), 'dndm_debug_copy')
-        e, el = t.cpu().tolist()
-        return e, el
+        return self.graph_stats_full()[:2]
+
+    def graph_stats_full(self):
+        """(E, E_ligand_receiver, E_last_block): the third entry is the number of edges the last block aggregates when
+        the pocket output is not requested (ligand receivers + their pocket senders); stale otherwise."""
+        t = torch.zeros(4, dtype=torch.int32, device=torch.device('cuda', self.device))
+        _check(self.lib, self.lib.dndm_debug_copy(self._h, 4, _ptr(t), 16, _stream()), 'dndm_debug_copy')
+        e, el, ea, _ = t.cpu().tolist()
+        return e, el, ea
 
 
 def launch_count() -> int:

@@ -153,6 +153,22 @@ def test_forward_deterministic_bitwise(dyn, dev):
         assert torch.equal(a, b) and torch.equal(ap, bp)
 
 
+def test_last_block_pruning_is_exact(dyn, dev):
+    """When the pocket output is not requested (every conditional sampler call site discards it) the last block only
+    aggregates for ligand atoms and their pocket senders: the ligand output must be bit-identical."""
+    for name in ('3rfm_b2', 'synth60_b3_tmix'):
+        c = FWD_CASES[name]
+        args = (_t(c['xh_lig'], dev), _t(c['xh_pocket'], dev), _t(c['t'], dev), _t(c['lig_mask'], dev), _t(c['pocket_mask'], dev))
+        full, _ = dyn(*args)
+        dyn.compute_pocket_output = False
+        try:
+            pruned, none = dyn(*args)
+        finally:
+            dyn.compute_pocket_output = True
+        assert none is None
+        assert torch.equal(full, pruned)
+
+
 def test_forward_batch_composition_invariance(dyn, dev):
     """Samples never interact (dynamics.py:115): a sample's output is bit-identical alone or inside a batch,
     as long as its edges land at the same positions of the 128-edge tiles -- and within tolerance otherwise."""
