@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=100, help='ligands per pocket (BASELINE configs[1]: 100)')
     ap.add_argument('--cpu-batch', type=int, default=8, help='ligands in the bounded CPU sample')
+    ap.add_argument('--pocket-atoms', type=int, default=None, help='override the pocket size (default: 330, the distribution mean)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -404,7 +405,10 @@ def run_b200(args):
 
 
 def main():
+    global POCKET_ATOMS
     args = parse()
+    if args.pocket_atoms:
+        POCKET_ATOMS = args.pocket_atoms
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "gemm_tn.cuh"
+#include "gemm_wres.cuh"
 #include "edge_mlp.cuh"
 #include "graph.cuh"
 #include "node_kernels.cuh"
@@ -69,6 +70,19 @@ static int make_tmap_f32_out(CUtensorMap* m, const void* base, uint64_t rows, ui
     if (r != CUDA_SUCCESS) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled (f32 out) failed with %d", (int)r);
     return DNDM_OK;
 }
+static int make_tmap_bf16_box(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                              uint32_t box_rows, CUtensorMapSwizzle swz) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled (bf16 box) failed with %d", (int)r);
+    return DNDM_OK;
+}
 // bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128-byte swizzle.
 static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     PFN_encodeTiled fn = get_encode_fn();
@@ -89,6 +103,9 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // ------------------------------------------------------------------------------------------------
 struct LayerWeights {
     __nv_bfloat16 *wproj_e, *wproj_c, *w2_e, *w2_c, *w2_x, *w3, *w4;   // device bf16
+    __nv_bfloat16 *wm, *wp;                                             // merged sender/next-edge and receiver projections
+    float *bias_m, *bias_p;
+    CUtensorMap tm_wm, tm_wp, tm_we0, tm_w4r;                            // 256-row boxes for the weight-resident GEMM
     float *bias_e, *bias_c, *b3, *b4, *w1e_e, *w1e_c, *w1e_x;          // device fp32
     CUtensorMap tm_proj_e, tm_proj_c, tm_w2_e, tm_w2_c, tm_w2_x, tm_w3, tm_w4;
     EdgeConsts c_e, c_c, c_x;                                            // host copies (kernel parameters)
@@ -112,6 +129,7 @@ struct DndmEngine {
     unsigned* flags = nullptr;
     CUtensorMap tm_hcat, tm_hid;
     CUtensorMap to_pq, to_hid, to_hcat, to_h;
+    CUtensorMap to_pq32, to_hcat32;              // 32-column bf16 boxes (SWIZZLE_64B) for the weight-resident GEMM
     CUtensorMap to_msg;                          // TMA-store destination of the edge messages (box 32 rows x 64 cols)   // TMA-store destinations of the node GEMMs (32-row boxes)
     // weights
     std::vector<LayerWeights> layers;
@@ -205,6 +223,9 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(make_tmap_bf16(&e->to_hcat, e->hcat, N, 512, 512, 32));
     RET_IF(make_tmap_f32_out(&e->to_h, e->h, N, 256, 256));
     RET_IF(make_tmap_bf16(&e->to_msg, e->msg, E + 128, 256, 256, 32));
+    RET_IF(make_tmap_bf16_box(&e->to_pq32, e->pq, N, 1536, 1536, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    RET_IF(make_tmap_bf16_box(&e->to_hcat32, e->hcat, N, 512, 512, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
@@ -397,6 +418,43 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         RET_IF(make_tmap_bf16(&L.tm_w2_c, L.w2_c, H, H, H, 256));
         RET_IF(make_tmap_bf16(&L.tm_w2_x, L.w2_x, H, H, H, 256));
     }
+    // ---- merged projection weights for the weight-resident GEMM (pq columns: [0,512) edge P|Q of the NEXT block,
+    //      [512,1024) coord Q | cross Q, [1024,1536) coord P | cross P of THIS block); all pre-halved ----
+    for (int l = 0; l < e->cfg.n_layers; ++l) {
+        LayerWeights& L = e->layers[l];
+        const std::string p = "egnn.e_block_" + std::to_string(l) + ".";
+        const float *c0w, *c0b, *x0w, *x0b, *n0w = nullptr, *n0b = nullptr;
+        RET_IF(need(p + "gcl_equiv.coord_mlp.0.weight", H, KIN, &c0w)); RET_IF(need(p + "gcl_equiv.coord_mlp.0.bias", H, 1, &c0b));
+        RET_IF(need(p + "gcl_equiv.cross_product_mlp.0.weight", H, KIN, &x0w));
+        RET_IF(need(p + "gcl_equiv.cross_product_mlp.0.bias", H, 1, &x0b));
+        if (l + 1 < e->cfg.n_layers) {
+            const std::string pn = "egnn.e_block_" + std::to_string(l + 1) + ".";
+            RET_IF(need(pn + "gcl_0.edge_mlp.0.weight", H, KIN, &n0w)); RET_IF(need(pn + "gcl_0.edge_mlp.0.bias", H, 1, &n0b));
+        }
+        std::vector<__nv_bfloat16> wm((size_t)4 * H * H, f2bf(0.f)), wp((size_t)2 * H * H);
+        std::vector<float> bm(4 * H, 0.f), bp(2 * H, 0.f);
+        for (int o = 0; o < H; ++o)
+            for (int k = 0; k < H; ++k) {
+                if (n0w) {
+                    wm[((size_t)o) * H + k] = f2bf(0.5f * n0w[(size_t)o * KIN + k]);              // next edge, receiver part
+                    wm[((size_t)H + o) * H + k] = f2bf(0.5f * n0w[(size_t)o * KIN + H + k]);      // next edge, sender part
+                }
+                wm[((size_t)2 * H + o) * H + k] = f2bf(0.5f * c0w[(size_t)o * KIN + H + k]);      // coord, sender part
+                wm[((size_t)3 * H + o) * H + k] = f2bf(0.5f * x0w[(size_t)o * KIN + H + k]);      // cross, sender part
+                wp[((size_t)o) * H + k] = f2bf(0.5f * c0w[(size_t)o * KIN + k]);                  // coord, receiver part
+                wp[((size_t)H + o) * H + k] = f2bf(0.5f * x0w[(size_t)o * KIN + k]);              // cross, receiver part
+            }
+        for (int o = 0; o < H; ++o) {
+            if (n0b) bm[o] = 0.5f * n0b[o];
+            bp[o] = 0.5f * c0b[o];
+            bp[H + o] = 0.5f * x0b[o];
+        }
+        RET_IF(upload(e, wm, &L.wm)); RET_IF(upload(e, wp, &L.wp)); RET_IF(upload(e, bm, &L.bias_m)); RET_IF(upload(e, bp, &L.bias_p));
+        RET_IF(make_tmap_bf16(&L.tm_wm, L.wm, 4 * H, H, H, 256));
+        RET_IF(make_tmap_bf16(&L.tm_wp, L.wp, 2 * H, H, H, 256));
+        RET_IF(make_tmap_bf16(&L.tm_we0, L.wproj_e, 2 * H, H, H, 256));
+        RET_IF(make_tmap_bf16(&L.tm_w4r, L.w4, H, H, H, 256));
+    }
     e->weights_loaded = true;
     return DNDM_OK;
 }
@@ -411,6 +469,19 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
     const int total = ((M + GEMM_BM - 1) / GEMM_BM) * n_tiles;
     const int grid = total < g_num_sms ? total : g_num_sms;
     gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tw, to16, to32, M, K, a_col0, n_col0 / GEMM_BN, n_tiles, ep);
+    COUNT_LAUNCH(1);
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
+static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to16, int M,
+                       int n_groups, int g0, int a_col0, const WresEpilogue& ep) {
+    if (M <= 0) return DNDM_OK;
+    const int m_tiles = (M + WR_BM - 1) / WR_BM;
+    int gx = g_num_sms / n_groups;
+    if (gx < 1) gx = 1;
+    if (gx > m_tiles) gx = m_tiles;
+    gemm_wres_kernel<<<dim3(gx, n_groups), WR_THREADS, WR_SMEM_BYTES, st>>>(ta, tw, to16, M, a_col0, g0, ep);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
@@ -515,17 +586,17 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     float* x_next = e->xb;
     const float inv_norm = 1.0f / e->cfg.normalization_factor;
 
-    auto proj_e = [&](int l) -> int {
+    // first-layer projections of block 0's edge model (pq columns [0,512))
+    {
         ProfScope ps(e, PROF_GEMM, st);
-        GemmEpilogue ep{e->layers[l].bias_e, 0, nullptr, 0, 0, 0, 1, 0};
-        return launch_gemm(st, e->tm_hcat, e->layers[l].tm_proj_e, e->to_pq, e->to_h, N, 512, 256, 0, ep);
-    };
+        WresEpilogue ep{e->layers[0].bias_e, nullptr, 0, nullptr, 0, 0, 1, 0};
+        RET_IF(launch_wres(st, e->tm_hcat, e->layers[0].tm_we0, e->to_pq32, N, 2, 0, 0, ep));
+    }
     const bool prune_last = (out_pocket == nullptr) && n_pocket > 0;
     if (prune_last) {
         ProfScope ps(e, PROF_GRAPH, st);
         RET_IF(build_last_block_edges(e, n_lig, N, st));
     }
-    RET_IF(proj_e(0));
     for (int l = 0; l < e->cfg.n_layers; ++l) {
         LayerWeights& L = e->layers[l];
         const bool pruned = prune_last && (l + 1 == e->cfg.n_layers);
@@ -548,23 +619,24 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             ProfScope ps(e, PROF_GEMM, st);
             GemmEpilogue ep1{L.b3, 1, nullptr, 0, 0, 0, 1, 0};
             RET_IF(launch_gemm(st, e->tm_hcat, L.tm_w3, e->to_hid, e->to_h, N, 256, 512, 0, ep1));
-            GemmEpilogue ep2{L.b4, 0, e->h, 256, 1, 0, 1, 0};          // h += ...; bf16 copy -> hcat[:, :256]
-            RET_IF(launch_gemm(st, e->tm_hid, L.tm_w4, e->to_hcat, e->to_h, N, 256, 256, 0, ep2));
+            WresEpilogue ep2{L.b4, e->h, 256, e->h, 256, 0, 1, 0};       // h += W4 hid + b4 ; bf16 copy -> hcat[:, :256]
+            RET_IF(launch_wres(st, e->tm_hid, L.tm_w4r, e->to_hcat32, N, 1, 0, 0, ep2));
         }
-        // ---- node projections for this block's coordinate heads and the next block's edge model ----
+        // ---- node projections: this block's coordinate heads (sender parts for every node, receiver parts for the
+        //      ligand rows) and the next block's edge model, one weight-resident GEMM over the new h ----
         {
             ProfScope ps(e, PROF_GEMM, st);
-            // receiver parts (coord P | cross P) are only read for ligand rows; sender parts (Q) for every node
-            GemmEpilogue ep{L.bias_c, 0, nullptr, 0, 0, 0, 1, 512};      // pq columns 512.. hold the coordinate-head projections
-            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, e->to_pq, e->to_h, n_lig, 512, 256, 0, ep, 0));
-            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_proj_c, e->to_pq, e->to_h, N, 512, 256, 0, ep, 512));
+            const bool has_next = l + 1 < e->cfg.n_layers;
+            WresEpilogue epm{L.bias_m, nullptr, 0, nullptr, 0, 0, 1, 0};
+            RET_IF(launch_wres(st, e->tm_hcat, L.tm_wm, e->to_pq32, N, has_next ? 4 : 2, has_next ? 0 : 2, 0, epm));
+            WresEpilogue epp{L.bias_p, nullptr, 0, nullptr, 0, 0, 1, 1024};
+            RET_IF(launch_wres(st, e->tm_hcat, L.tm_wp, e->to_pq32, n_lig, 2, 0, 0, epp));
         }
-        if (l + 1 < e->cfg.n_layers) RET_IF(proj_e(l + 1));
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
         {
             EdgeGraph gh{e->erow, e->ecol, e->r0, x_cur, e->scalars + 1, 1536, nullptr, nullptr};
-            EdgeProblem pc{e->pq + 512, e->pq + 1024, L.w1e_c, e->phi, 0.f, e->cfg.coords_range};
-            EdgeProblem px{e->pq + 768, e->pq + 1280, L.w1e_x, e->psi, 0.f, e->cfg.coords_range};
+            EdgeProblem pc{e->pq + 1024, e->pq + 512, L.w1e_c, e->phi, 0.f, e->cfg.coords_range};
+            EdgeProblem px{e->pq + 1280, e->pq + 768, L.w1e_x, e->psi, 0.f, e->cfg.coords_range};
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
             {
                 ProfScope ps(e, PROF_HEAD, st);

@@ -1,0 +1,212 @@
+// Weight-resident node GEMM for K = 256:   C[M, 256*G] = epilogue( A[M,256] (bf16) x W[256*G, 256]^T (bf16) )
+//
+// A CTA owns one 256-column group of W -- 128 KiB, TMA-loaded once and resident for the CTA's lifetime, exactly like W2
+// in the edge kernel -- and streams the A row blocks assigned to it through a 4-stage ring (one full 128 x 256 row block
+// of prefetch).  The accumulator drain is a pure latency chain (tcgen05.ld -> bias/residual -> cvt -> st.shared -> fence
+// -> TMA store, ~1000 cycles per 32-column chunk for one warp; ncu: profiles/r1_wres_*), so it is spread over
+// 4 * WR_EPI_SPLIT epilogue warps: each TMEM lane quarter is served by WR_EPI_SPLIT warps that split the 256 columns.
+//
+// Persistent, warp-specialised (1 CTA / SM, grid = (ceil(#SMs / G), G)):
+//   warp 0     TMA producer : W group once; A tiles (128 x 64 bf16, SWIZZLE_128B) into the ring
+//   warp 1     MMA issuer   : 16 x tcgen05.mma M128 N256 K16 per row block into one of two TMEM accumulators (2 x 256)
+//   warps 2..  epilogue     : tcgen05.ld (32 columns at a time) -> bias / residual -> fp32 rows straight to global
+//                             (each thread owns one row: full 128-byte runs) and/or bf16 through a swizzled smem slab
+//                             and a TMA store; no block-level barrier
+#pragma once
+#include "common.cuh"
+
+namespace dndm {
+
+constexpr int WR_BM = 128;
+constexpr int WR_BN = 256;
+constexpr int WR_K = 256;
+constexpr int WR_STAGES = 4;
+constexpr int WR_EPI_SPLIT = 4;                               // epilogue warps per TMEM lane quarter (2 or 4)
+constexpr int WR_EPI_WARPS = 4 * WR_EPI_SPLIT;
+constexpr int WR_THREADS = 64 + 32 * WR_EPI_WARPS;
+constexpr int WR_CHUNKS = WR_BN / 32 / WR_EPI_SPLIT;          // 32-column chunks per epilogue warp and row block
+constexpr int WR_NSLAB = WR_EPI_SPLIT == 2 ? 2 : 1;           // bf16 slabs per warp (double-buffered when a warp has 4 chunks)
+constexpr int WR_W_BYTES = WR_BN * WR_K * 2;                 // 131072
+constexpr int WR_STAGE_BYTES = WR_BM * 64 * 2;               //  16384  (128 rows x 64 k)
+constexpr int WR_SLAB16_BYTES = 32 * 32 * 2;                 //   2048  [32 rows][32 bf16], SWIZZLE_64B
+constexpr int WR_OUT_BYTES = WR_EPI_WARPS * WR_NSLAB * WR_SLAB16_BYTES;
+constexpr int WR_SMEM_BYTES = WR_W_BYTES + WR_STAGES * WR_STAGE_BYTES + WR_OUT_BYTES + 256;
+static_assert(WR_SMEM_BYTES <= 232448, "gemm_wres shared memory");
+
+struct WresEpilogue {
+    const float* bias;        // [256*G] or nullptr
+    const float* residual;    // [M, ldr] fp32 or nullptr (may alias out_f32: every element is read by the thread that writes it)
+    int ldr;
+    float* out_f32;           // [M, ld_f32] fp32 destination or nullptr; column offset col0_f32
+    int ld_f32;
+    int col0_f32;
+    int has_bf16;             // store bf16 through tmap_o16 at column offset col0_bf16
+    int col0_bf16;
+};
+
+__global__ void __launch_bounds__(WR_THREADS, 1)
+gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_o16, int M, int a_col0, int g0, WresEpilogue ep) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sW = smem;                                           // [4 k-chunks][256 rows][128 B]
+    uint8_t* sA = smem + WR_W_BYTES;                              // ring of [128 rows][128 B]
+    uint8_t* sOut = sA + WR_STAGES * WR_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + WR_OUT_BYTES);
+    uint64_t* empty_bar = full_bar + WR_STAGES;
+    uint64_t* acc_full = empty_bar + WR_STAGES;      // [2]
+    uint64_t* acc_empty = acc_full + 2;              // [2]
+    uint64_t* w_bar = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = blockIdx.y + g0;                              // 256-column group of W / of the output
+    const int m_tiles = (M + WR_BM - 1) / WR_BM;
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < WR_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 32 * WR_EPI_WARPS);
+        }
+        mbar_init(w_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool has_work = (int)blockIdx.x < m_tiles;
+
+    if (warp == 0) {
+        if (elect_one() && has_work) {
+            mbar_arrive_expect_tx(w_bar, WR_W_BYTES);
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, &tmap_w, w_bar, kc * 64, grp * WR_BN);
+            int kq = 0;
+            for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x) {
+                for (int kb = 0; kb < 4; ++kb, ++kq) {
+                    const int s = kq % WR_STAGES;
+                    const uint32_t ph = (kq / WR_STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], WR_STAGE_BYTES);
+                    tma_load_2d(sA + s * WR_STAGE_BYTES, &tmap_a, &full_bar[s], a_col0 + kb * 64, m_blk * WR_BM);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one() && has_work) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(WR_BM, WR_BN);
+            mbar_wait(w_bar, 0);
+            int kq = 0, it = 0;
+            for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++it) {
+                const int buf = it & 1;
+                if (it >= 2) mbar_wait(&acc_empty[buf], ((it - 2) >> 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * WR_BN;
+                for (int kb = 0; kb < 4; ++kb, ++kq) {
+                    const int s = kq % WR_STAGES;
+                    const uint32_t ph = (kq / WR_STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t sa = smem_u32(sA + s * WR_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(sW + kb * 32768);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, make_kmajor_sw128_desc(sa + k * 32), make_kmajor_sw128_desc(sb + k * 32), idesc,
+                                  (kb | k) != 0);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int part = (warp - 2) >> 2;                         // which WR_CHUNKS-chunk column span of the 256
+        uint8_t* s16b = sOut + (warp - 2) * WR_NSLAB * WR_SLAB16_BYTES;
+        const uint32_t sw64 = (lane >> 1) & 3;
+        int it = 0;
+        for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after_sync();
+            const int row0 = m_blk * WR_BM + q * 32;
+            const long grow = (long)row0 + lane;
+            const bool row_ok = grow < M;
+#pragma unroll
+            for (int cc = 0; cc < WR_CHUNKS; ++cc) {
+                const int c = part * WR_CHUNKS + cc;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + buf * WR_BN + ((uint32_t)(q * 32) << 16) + c * 32, v);
+                const int col0 = grp * WR_BN + c * 32;
+                float f[32];
+                if (ep.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                        f[j] = b.x; f[j + 1] = b.y; f[j + 2] = b.z; f[j + 3] = b.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                }
+                if (ep.residual && row_ok) {
+                    const float* rp = ep.residual + grow * ep.ldr + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 r = *reinterpret_cast<const float4*>(rp + j);
+                        f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+                    }
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+                if (ep.out_f32 && row_ok) {
+                    float* op = ep.out_f32 + grow * ep.ld_f32 + ep.col0_f32 + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                }
+                if (ep.has_bf16) {
+                    uint8_t* s16 = s16b + (WR_NSLAB == 2 ? (cc & 1) : 0) * WR_SLAB16_BYTES;
+                    // the TMA store that last used this slab has finished reading it
+                    if (lane == 0) {
+                        if (WR_NSLAB == 2) tma_store_wait_read1(); else tma_store_wait_read();
+                    }
+                    __syncwarp();
+                    uint8_t* rowp = s16 + lane * 64;
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(f[8 * uu], f[8 * uu + 1]);     pk.y = pack_bf16x2(f[8 * uu + 2], f[8 * uu + 3]);
+                        pk.z = pack_bf16x2(f[8 * uu + 4], f[8 * uu + 5]); pk.w = pack_bf16x2(f[8 * uu + 6], f[8 * uu + 7]);
+                        *reinterpret_cast<uint4*>(rowp + ((uu ^ sw64) << 4)) = pk;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && row0 < M) {
+                        tma_store_2d(&tmap_o16, s16, ep.col0_bf16 + col0, row0);
+                        tma_store_commit();
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&acc_empty[buf]);
+        }
+        if (lane == 0) tma_store_wait_all();
+        __syncwarp();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace dndm
