@@ -92,6 +92,10 @@ DNDM_DEVICE void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_
 }
 DNDM_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DNDM_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// Bulk L2 prefetch of a contiguous global range (address and size multiples of 16 bytes).
+DNDM_DEVICE void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 DNDM_DEVICE void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 DNDM_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 

@@ -103,9 +103,9 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // ------------------------------------------------------------------------------------------------
 struct LayerWeights {
     __nv_bfloat16 *wproj_e, *wproj_c, *w2_e, *w2_c, *w2_x, *w3, *w4;   // device bf16
-    __nv_bfloat16 *wm, *wp;                                             // merged sender/next-edge and receiver projections
-    float *bias_m, *bias_p;
-    CUtensorMap tm_wm, tm_wp, tm_we0, tm_w4r;                            // 256-row boxes for the weight-resident GEMM
+    __nv_bfloat16* wm;                                                  // merged projections [next-edge P|Q ; coord Q ; cross Q ; coord P ; cross P]
+    float* bias_m;
+    CUtensorMap tm_wm, tm_we0, tm_w4r;                            // 256-row boxes for the weight-resident GEMM
     float *bias_e, *bias_c, *b3, *b4, *w1e_e, *w1e_c, *w1e_x;          // device fp32
     CUtensorMap tm_proj_e, tm_proj_c, tm_w2_e, tm_w2_c, tm_w2_x, tm_w3, tm_w4;
     EdgeConsts c_e, c_c, c_x;                                            // host copies (kernel parameters)
@@ -431,8 +431,8 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
             const std::string pn = "egnn.e_block_" + std::to_string(l + 1) + ".";
             RET_IF(need(pn + "gcl_0.edge_mlp.0.weight", H, KIN, &n0w)); RET_IF(need(pn + "gcl_0.edge_mlp.0.bias", H, 1, &n0b));
         }
-        std::vector<__nv_bfloat16> wm((size_t)4 * H * H, f2bf(0.f)), wp((size_t)2 * H * H);
-        std::vector<float> bm(4 * H, 0.f), bp(2 * H, 0.f);
+        std::vector<__nv_bfloat16> wm((size_t)6 * H * H, f2bf(0.f));     // rows [4H,6H): receiver parts (ligand rows only)
+        std::vector<float> bm(6 * H, 0.f);
         for (int o = 0; o < H; ++o)
             for (int k = 0; k < H; ++k) {
                 if (n0w) {
@@ -441,17 +441,16 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
                 }
                 wm[((size_t)2 * H + o) * H + k] = f2bf(0.5f * c0w[(size_t)o * KIN + H + k]);      // coord, sender part
                 wm[((size_t)3 * H + o) * H + k] = f2bf(0.5f * x0w[(size_t)o * KIN + H + k]);      // cross, sender part
-                wp[((size_t)o) * H + k] = f2bf(0.5f * c0w[(size_t)o * KIN + k]);                  // coord, receiver part
-                wp[((size_t)H + o) * H + k] = f2bf(0.5f * x0w[(size_t)o * KIN + k]);              // cross, receiver part
+                wm[((size_t)4 * H + o) * H + k] = f2bf(0.5f * c0w[(size_t)o * KIN + k]);          // coord, receiver part
+                wm[((size_t)5 * H + o) * H + k] = f2bf(0.5f * x0w[(size_t)o * KIN + k]);          // cross, receiver part
             }
         for (int o = 0; o < H; ++o) {
             if (n0b) bm[o] = 0.5f * n0b[o];
-            bp[o] = 0.5f * c0b[o];
-            bp[H + o] = 0.5f * x0b[o];
+            bm[4 * H + o] = 0.5f * c0b[o];
+            bm[5 * H + o] = 0.5f * x0b[o];
         }
-        RET_IF(upload(e, wm, &L.wm)); RET_IF(upload(e, wp, &L.wp)); RET_IF(upload(e, bm, &L.bias_m)); RET_IF(upload(e, bp, &L.bias_p));
-        RET_IF(make_tmap_bf16(&L.tm_wm, L.wm, 4 * H, H, H, 256));
-        RET_IF(make_tmap_bf16(&L.tm_wp, L.wp, 2 * H, H, H, 256));
+        RET_IF(upload(e, wm, &L.wm)); RET_IF(upload(e, bm, &L.bias_m));
+        RET_IF(make_tmap_bf16(&L.tm_wm, L.wm, 6 * H, H, H, 256));
         RET_IF(make_tmap_bf16(&L.tm_we0, L.wproj_e, 2 * H, H, H, 256));
         RET_IF(make_tmap_bf16(&L.tm_w4r, L.w4, H, H, H, 256));
     }
@@ -474,14 +473,25 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
     return DNDM_OK;
 }
 
+// n_full column groups over M rows followed by n_tail groups over the first M_tail rows (see gemm_wres_kernel)
 static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to16, int M,
-                       int n_groups, int g0, int a_col0, const WresEpilogue& ep) {
+                       int n_full, int g0, int a_col0, const WresEpilogue& ep, int n_tail = 0, int M_tail = 0) {
     if (M <= 0) return DNDM_OK;
-    const int m_tiles = (M + WR_BM - 1) / WR_BM;
-    int gx = g_num_sms / n_groups;
-    if (gx < 1) gx = 1;
-    if (gx > m_tiles) gx = m_tiles;
-    gemm_wres_kernel<<<dim3(gx, n_groups), WR_THREADS, WR_SMEM_BYTES, st>>>(ta, tw, to16, M, a_col0, g0, ep);
+    if (M_tail <= 0) n_tail = 0;
+    const int m_tiles = (M + WR_BM - 1) / WR_BM, t_tiles = (M_tail + WR_BM - 1) / WR_BM;
+    int ctas_tail = 0;
+    if (n_tail > 0) {                                   // share the SMs in proportion to the row blocks
+        const double per_cta = (double)(n_full * m_tiles + n_tail * t_tiles) / g_num_sms;
+        ctas_tail = (int)(t_tiles / per_cta + 0.999);
+        if (ctas_tail < 1) ctas_tail = 1;
+        if (ctas_tail > t_tiles) ctas_tail = t_tiles;
+    }
+    int ctas_full = (g_num_sms - n_tail * ctas_tail) / n_full;
+    if (ctas_full < 1) ctas_full = 1;
+    if (ctas_full > m_tiles) ctas_full = m_tiles;
+    const int grid = n_full * ctas_full + n_tail * ctas_tail;
+    gemm_wres_kernel<<<grid, WR_THREADS, WR_SMEM_BYTES, st>>>(ta, tw, to16, M, M_tail, a_col0, g0, n_full, ctas_full,
+                                                              ctas_tail > 0 ? ctas_tail : 1, ep);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
@@ -628,9 +638,8 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             ProfScope ps(e, PROF_GEMM, st);
             const bool has_next = l + 1 < e->cfg.n_layers;
             WresEpilogue epm{L.bias_m, nullptr, 0, nullptr, 0, 0, 1, 0};
-            RET_IF(launch_wres(st, e->tm_hcat, L.tm_wm, e->to_pq32, N, has_next ? 4 : 2, has_next ? 0 : 2, 0, epm));
-            WresEpilogue epp{L.bias_p, nullptr, 0, nullptr, 0, 0, 1, 1024};
-            RET_IF(launch_wres(st, e->tm_hcat, L.tm_wp, e->to_pq32, n_lig, 2, 0, 0, epp));
+            // column groups 0-3 over all nodes (0,1 only when a next block exists), groups 4,5 over the ligand rows only
+            RET_IF(launch_wres(st, e->tm_hcat, L.tm_wm, e->to_pq32, N, has_next ? 4 : 2, has_next ? 0 : 2, 0, epm, 2, n_lig));
         }
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
         {

@@ -46,7 +46,8 @@ struct WresEpilogue {
 
 __global__ void __launch_bounds__(WR_THREADS, 1)
 gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_o16, int M, int a_col0, int g0, WresEpilogue ep) {
+                 const __grid_constant__ CUtensorMap tmap_o16, int M, int M_tail, int a_col0, int g0, int n_full,
+                 int ctas_full, int ctas_tail, WresEpilogue ep) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sW = smem;                                           // [4 k-chunks][256 rows][128 B]
     uint8_t* sA = smem + WR_W_BYTES;                              // ring of [128 rows][128 B]
@@ -59,7 +60,20 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = blockIdx.y + g0;                              // 256-column group of W / of the output
+    // 1-D grid: the first n_full column groups cover all M rows with ctas_full CTAs each; the remaining ("tail") groups
+    // cover only the first M_tail rows (the ligand-row-only projections) with ctas_tail CTAs each.
+    int grp, cta_rank, cta_stride;
+    if ((int)blockIdx.x < n_full * ctas_full) {
+        grp = g0 + blockIdx.x / ctas_full;
+        cta_rank = blockIdx.x % ctas_full;
+        cta_stride = ctas_full;
+    } else {
+        const int b2 = blockIdx.x - n_full * ctas_full;
+        grp = g0 + n_full + b2 / ctas_tail;
+        cta_rank = b2 % ctas_tail;
+        cta_stride = ctas_tail;
+        M = M_tail;
+    }
     const int m_tiles = (M + WR_BM - 1) / WR_BM;
 
     if (threadIdx.x == 0) {
@@ -82,7 +96,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const bool has_work = (int)blockIdx.x < m_tiles;
+    const bool has_work = cta_rank < m_tiles;
 
     if (warp == 0) {
         if (elect_one() && has_work) {
@@ -90,7 +104,11 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, &tmap_w, w_bar, kc * 64, grp * WR_BN);
             int kq = 0;
-            for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x) {
+            for (int m_blk = cta_rank; m_blk < m_tiles; m_blk += cta_stride) {
+                if (ep.residual && ep.ldr == WR_BN) {             // the row block of the fp32 residual is one contiguous range
+                    const int rows = min(WR_BM, M - m_blk * WR_BM);
+                    bulk_prefetch_l2(ep.residual + (size_t)m_blk * WR_BM * WR_BN, (uint32_t)rows * WR_BN * 4);
+                }
                 for (int kb = 0; kb < 4; ++kb, ++kq) {
                     const int s = kq % WR_STAGES;
                     const uint32_t ph = (kq / WR_STAGES) & 1;
@@ -106,7 +124,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             constexpr uint32_t idesc = make_idesc_bf16_f32(WR_BM, WR_BN);
             mbar_wait(w_bar, 0);
             int kq = 0, it = 0;
-            for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++it) {
+            for (int m_blk = cta_rank; m_blk < m_tiles; m_blk += cta_stride, ++it) {
                 const int buf = it & 1;
                 if (it >= 2) mbar_wait(&acc_empty[buf], ((it - 2) >> 1) & 1);
                 tc_fence_after_sync();
@@ -134,20 +152,14 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* s16b = sOut + (warp - 2) * WR_NSLAB * WR_SLAB16_BYTES;
         const uint32_t sw64 = (lane >> 1) & 3;
         int it = 0;
-        for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++it) {
+        for (int m_blk = cta_rank; m_blk < m_tiles; m_blk += cta_stride, ++it) {
             const int buf = it & 1;
-            mbar_wait(&acc_full[buf], (it >> 1) & 1);
-            tc_fence_after_sync();
             const int row0 = m_blk * WR_BM + q * 32;
             const long grow = (long)row0 + lane;
             const bool row_ok = grow < M;
-#pragma unroll
-            for (int cc = 0; cc < WR_CHUNKS; ++cc) {
-                const int c = part * WR_CHUNKS + cc;
-                uint32_t v[32];
-                tmem_ld32(tmem_base + buf * WR_BN + ((uint32_t)(q * 32) << 16) + c * 32, v);
+            // bias + residual of a chunk: independent of the accumulator, so chunk 0's loads are issued before the wait
+            auto load_addend = [&](int c, float* f) {
                 const int col0 = grp * WR_BN + c * 32;
-                float f[32];
                 if (ep.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -166,6 +178,18 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
                     }
                 }
+            };
+            float f[32];
+            load_addend(part * WR_CHUNKS, f);
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after_sync();
+#pragma unroll
+            for (int cc = 0; cc < WR_CHUNKS; ++cc) {
+                const int c = part * WR_CHUNKS + cc;
+                const int col0 = grp * WR_BN + c * 32;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + buf * WR_BN + ((uint32_t)(q * 32) << 16) + c * 32, v);
+                if (cc > 0) load_addend(c, f);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);

@@ -20,58 +20,81 @@ struct EncoderWeights {
     int nf, hid;
 };
 
-// One CTA = 256 threads = the 256 output channels; thread k keeps its row of Wc2 (<= 32 floats), w_t and bc in
-// registers and walks ENC_NODES_PER_CTA nodes, 8 at a time (hidden activations of the 8 nodes staged in smem).
+// One CTA = 256 threads = the 256 output channels, ENC_NODES_PER_CTA nodes.  Phase 1: the encoder's hidden layer of all
+// the CTA's nodes (thread -> node i, units j, j+8, ...) lands in shared memory together with the node's time value.
+// Phase 2: thread k keeps its row of Wc2 (<= 32 floats), w_t and bc in registers and walks the nodes; the hidden
+// activations are warp-broadcast 128-bit shared loads, the stores are fully coalesced (fp32 h and the bf16 copy).
 // CTAs [0, lig_ctas) take ligand atoms, the rest pocket atoms (different encoder weights).
 constexpr int ENC_NODES_PER_CTA = 64;
 constexpr int ENC_MAX_HID = 32;
+constexpr int ENC_MAX_NF = 32;
 
 __global__ void __launch_bounds__(256)
 encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ xh_pok, int n_lig, int n_nodes,
                     int ld_lig, int ld_pok, const float* __restrict__ t, int t_len, const int* __restrict__ node_sample,
                     EncoderWeights wl, EncoderWeights wp, int lig_ctas, float* __restrict__ x0, float* __restrict__ xa,
                     float* __restrict__ xb, float* __restrict__ h, __nv_bfloat16* __restrict__ hcat) {
-    __shared__ float s_hid[8][ENC_MAX_HID];
-    __shared__ float s_t[8];
+    __shared__ __align__(16) float s_hid[ENC_NODES_PER_CTA][ENC_MAX_HID];
+    __shared__ float s_in[ENC_NODES_PER_CTA][ENC_MAX_NF + 4];
+    __shared__ float s_w1[ENC_MAX_HID][ENC_MAX_NF + 1];
+    __shared__ float s_t[ENC_NODES_PER_CTA];
     const bool is_lig = (int)blockIdx.x < lig_ctas;
     const EncoderWeights& w = is_lig ? wl : wp;
     const int first = is_lig ? blockIdx.x * ENC_NODES_PER_CTA : n_lig + (blockIdx.x - lig_ctas) * ENC_NODES_PER_CTA;
     const int last = min(first + ENC_NODES_PER_CTA, is_lig ? n_lig : n_nodes);
+    const int nn = last - first;
     const int k = threadIdx.x;
     const int hid = w.hid, nf = w.nf;
+    const int ld = is_lig ? ld_lig : ld_pok;                       // = 3 + nf
+    const float* src0 = is_lig ? xh_lig + (size_t)first * ld : xh_pok + (size_t)(first - n_lig) * ld;
+
+    // stage the CTA's input rows (contiguous in memory) and the first-layer weights
+    for (int q = k; q < nn * ld; q += 256) {
+        const int i = q / ld, c = q - i * ld;
+        const float v = src0[q];
+        s_in[i][c] = v;
+        if (c < 3) {
+            const int node = first + i;
+            x0[3 * node + c] = v; xa[3 * node + c] = v; xb[3 * node + c] = v;
+        }
+    }
+    for (int q = k; q < hid * nf; q += 256) s_w1[q / nf][q % nf] = w.w1[q];
+    if (k < nn) s_t[k] = t[t_len == 1 ? 0 : node_sample[first + k]];
     float wrow[ENC_MAX_HID];
 #pragma unroll
     for (int j = 0; j < ENC_MAX_HID; ++j) wrow[j] = (j < hid) ? w.wc2[k * hid + j] : 0.f;
     const float wt = w.wt[k], bc = w.bc[k];
-    for (int n0 = first; n0 < last; n0 += 8) {
-        const int nn = min(8, last - n0);
-        // hidden layer of the encoder: thread (i, j) -> node n0+i, unit j
-        {
-            const int i = threadIdx.x / ENC_MAX_HID, j = threadIdx.x % ENC_MAX_HID;
+    __syncthreads();
+
+    // phase 1: thread -> (node i = k % 64, units j = k / 64 + 4 u)
+    {
+        const int i = k & (ENC_NODES_PER_CTA - 1);
+        for (int j = k / ENC_NODES_PER_CTA; j < ENC_MAX_HID; j += 256 / ENC_NODES_PER_CTA) {
+            float a = 0.f;
             if (i < nn && j < hid) {
-                const int node = n0 + i;
-                const float* src = is_lig ? xh_lig + (size_t)node * ld_lig : xh_pok + (size_t)(node - n_lig) * ld_pok;
-                float a = w.b1[j];
-                for (int q = 0; q < nf; ++q) a = fmaf(w.w1[j * nf + q], src[3 + q], a);
-                s_hid[i][j] = silu_f(a);
-                if (j < 3) {
-                    const float c = src[j];
-                    x0[3 * node + j] = c; xa[3 * node + j] = c; xb[3 * node + j] = c;
-                }
-                if (j == 3) s_t[i] = t[t_len == 1 ? 0 : node_sample[node]];
+                a = w.b1[j];
+                for (int q = 0; q < nf; ++q) a = fmaf(s_w1[j][q], s_in[i][3 + q], a);
+                a = silu_f(a);
             }
+            s_hid[i][j] = a;
         }
-        __syncthreads();
-        for (int i = 0; i < nn; ++i) {
-            float o = fmaf(wt, s_t[i], bc);
+    }
+    __syncthreads();
+
+    // phase 2
+    for (int i = 0; i < nn; ++i) {
+        float o = fmaf(wt, s_t[i], bc);
 #pragma unroll
-            for (int j = 0; j < ENC_MAX_HID; ++j)
-                if (j < hid) o = fmaf(wrow[j], s_hid[i][j], o);
-            const int node = n0 + i;
-            h[(size_t)node * 256 + k] = o;
-            hcat[(size_t)node * 512 + k] = __float2bfloat16_rn(o);
+        for (int j = 0; j < ENC_MAX_HID; j += 4) {
+            const float4 sv = *reinterpret_cast<const float4*>(&s_hid[i][j]);
+            o = fmaf(wrow[j], sv.x, o);
+            o = fmaf(wrow[j + 1], sv.y, o);
+            o = fmaf(wrow[j + 2], sv.z, o);
+            o = fmaf(wrow[j + 3], sv.w, o);
         }
-        __syncthreads();
+        const int node = first + i;
+        h[(size_t)node * 256 + k] = o;
+        hcat[(size_t)node * 512 + k] = __float2bfloat16_rn(o);
     }
 }
 
