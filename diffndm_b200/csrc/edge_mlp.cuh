@@ -229,7 +229,10 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             if (lane < 8) meta[slot * 8 + l8] = make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
             __syncwarp();
         };
-        auto compute4 = [&](int slot, int half) {
+        // 4 edges: gather P[row], Q[col] (two 16-byte bf16 units per edge), first-layer activation, bf16 pack.  The results
+        // stay in registers until `before_store` returns, so that for the first half of a tile everything up to the
+        // shared-memory stores overlaps the previous tile's MMA (which is still reading the A tile).
+        auto compute4 = [&](int slot, int half, auto&& before_store) {
             uint4 pv[4], qv[4];
             int4 md[4];
 #pragma unroll
@@ -238,6 +241,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 pv[jj] = __ldg(Pb + (uint32_t)md[jj].x * ld4);
                 qv[jj] = __ldg(Qb + (uint32_t)md[jj].y * ld4);
             }
+            uint4 o[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const float rad = __int_as_float(md[jj].z), r0v = __int_as_float(md[jj].w);
@@ -251,11 +255,14 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                o[jj].x = pack_bf16x2(v[0], v[1]); o[jj].y = pack_bf16x2(v[2], v[3]);
+                o[jj].z = pack_bf16x2(v[4], v[5]); o[jj].w = pack_bf16x2(v[6], v[7]);
+            }
+            before_store();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
                 const uint32_t r = pw * 8 + half * 4 + jj;
-                *reinterpret_cast<uint4*>(sA_lane + r * 128 + ((u ^ (r & 7)) << 4)) = o;
+                *reinterpret_cast<uint4*>(sA_lane + r * 128 + ((u ^ (r & 7)) << 4)) = o[jj];
             }
         };
 
@@ -269,9 +276,10 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             const int buf = it & 1, slot = it & 1;
             meta_l2(m_next, slot ^ 1);                                           // next tile's metadata -> other slot
             m_next = meta_l1(tile + 2 * gridDim.x);                              // level-1 loads two tiles ahead
-            if (it >= 1) mbar_wait_park(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);   // A smem free again
-            compute4(slot, 0);
-            compute4(slot, 1);
+            compute4(slot, 0, [&] {
+                if (it >= 1) mbar_wait_park(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);   // A smem free again
+            });
+            compute4(slot, 1, [] {});
             fence_proxy_async_smem();
             tc_fence_before_sync();
             named_bar_sync(1, EK_PROD_THREADS);       // all producer warps have written their rows of A
