@@ -155,6 +155,15 @@ DNDM_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 DNDM_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but ties the destination registers of an earlier (still in-flight) tcgen05.ld to the wait so that the
+// compiler cannot schedule a read of them above it -- needed when other work is placed between the load and the wait.
+DNDM_DEVICE void tmem_ld_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 
 // registers -> TMEM (same shape)
 DNDM_DEVICE void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -184,6 +193,17 @@ DNDM_DEVICE uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices stored contiguously (128 B); `lbo` = byte distance
+// between the two core matrices of a K=16 slice, `sbo` = byte distance between consecutive 8-row groups.
+DNDM_DEVICE uint64_t make_kmajor_noswz_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
     return d;
 }
 

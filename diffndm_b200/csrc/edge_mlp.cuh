@@ -3,8 +3,8 @@
 // Algebra: the first Linear of every edge MLP acts on [h_row, h_col, e]; its h-parts are hoisted to the
 // nodes (P = W1a h + b1, Q = W1b h, one dense node GEMM), so per edge only
 //     a   = SiLU(P[row] + Q[col] + w_r * |x_r - x_c|^2 + w_0 * r0)            (gather + fp32 adds, bf16 out)
-//     D   = a . W2^T                                                          (tcgen05, M=128 edges, N=256, K=256)
-//     m   = SiLU(D + b2)
+//     D   = a . W2^T + b2                                                     (tcgen05, M=128 edges, N=256, K=256+16)
+//     m   = SiLU(D)
 //   GCL : att = sigmoid(w_a . m + b_a);  agg[row] += att * m / norm           (deterministic segmented sum)
 //   HEAD: out[e] = range * tanh(w5 . m)                                       (coord / cross scalar heads)
 // remains.
@@ -13,9 +13,12 @@
 //   warps 4-19  producers : gather + first-layer epilogue -> bf16 A tile in SWIZZLE_128B K-major smem (8 edges per
 //                           warp and tile, metadata prefetched a tile ahead); one elected lane issues the 16 tcgen05.mma
 //                           (M128 N256 K16) of the tile into TMEM accumulator (it & 1)
-//   warps 0-3   epilogue  : one thread per edge: tcgen05.ld -> m = SiLU(D + b2) -> dot with the attention / head
+//   warps 0-3   epilogue  : one thread per edge: tcgen05.ld -> m = SiLU(D) -> dot with the attention / head
 //                           weights; GCL stages m (bf16) in a swizzled smem slab per warp and TMA-stores it to the
 //                           message buffer, plus att[e]; HEAD writes the scalar
+// The second-layer bias rides on the tensor core: a 17th K=16 MMA step multiplies a constant A slice (columns 0,1 = 1)
+// with a B slice holding b2 split into two bf16 terms (hi + lo), so the accumulator already is the SiLU argument
+// (W2 and b2 are pre-halved on the host) and the epilogue spends no instruction on it.
 // W2 (128 KiB bf16) is TMA-loaded once per CTA and stays resident; the MMA of tile i and the production of tile i+1
 // run under the epilogue of tile i-1 (two TMEM accumulators).
 //
@@ -34,12 +37,16 @@ constexpr int EK_H = 256;         // hidden size (UMMA N and K)
 constexpr int EK_THREADS = 640;    // 4 epilogue + 16 producer warps, <= 96 registers each: latency hidden by warps
 constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
 constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
-constexpr int EK_MISC_BYTES = 256 + 16 * 2 * 8 * 16 + 3840 + 4 * 4096;   // barriers, metadata, pad to 1 KiB, message slabs
+constexpr int EK_SLAB_BYTES = 4 * 4096;                 // message staging, one [32 rows][128 B] SW128 slab per epilogue warp
+constexpr int EK_AX_BYTES = EK_TILE * 16 * 2;           //   4096  bias step, A slice (no swizzle)
+constexpr int EK_BX_BYTES = EK_H * 16 * 2;              //   8192  bias step, B slice (no swizzle)
+constexpr int EK_META_BYTES = 16 * 2 * 8 * 16;          //   4096
+constexpr int EK_MISC_BYTES = EK_SLAB_BYTES + EK_AX_BYTES + EK_BX_BYTES + EK_META_BYTES + 256;
 constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_MISC_BYTES;
 static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
 
 struct EdgeConsts {         // lives in the kernel-parameter constant bank: warp-uniform reads
-    float b2[EK_H];        // HALF of the second-layer bias (the SiLU argument is evaluated as x/2)
+    float b2[EK_H];        // HALF of the second-layer bias (the SiLU argument is evaluated as x/2); fed to the bias MMA step
     float wout[EK_H];
 };
 
@@ -74,6 +81,24 @@ DNDM_DEVICE float tanh_approx(float x) {
 // SiLU through one MUFU.TANH on the HALVED argument h = x/2:  x*sigmoid(x) = h + h*tanh(h)   (|rel err| ~ 2^-11).
 // The 1/2 is folded into the producing linear map on the host (exact: power of two), so callers pass h directly.
 DNDM_DEVICE float silu_half(float h) { return fmaf(h, tanh_approx(h), h); }
+// Packed bf16x2 arithmetic (one instruction for two channels) for the GCL producers: the first-layer activation is
+// rounded to bf16 for the tensor core anyway, so its pre-activation is assembled directly in bf16x2.
+DNDM_DEVICE uint32_t bf2_add(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+DNDM_DEVICE uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+DNDM_DEVICE uint32_t bf2_tanh(uint32_t a) {
+    uint32_t d;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+DNDM_DEVICE uint32_t bf2_silu_half(uint32_t h) { return bf2_fma(h, bf2_tanh(h), h); }
 DNDM_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 // mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of burning issue slots
@@ -89,7 +114,7 @@ DNDM_DEVICE void mbar_wait_park(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// Epilogue of one tile row (one thread = one edge): m = SiLU(D + b2) (b2 pre-halved), dot with wout.
+// Epilogue of one tile row (one thread = one edge): m = SiLU(D) (D = half pre-activation incl. bias), dot with wout.
 // GCL additionally writes m as bf16 to the message buffer (64 contiguous bytes per 32-column chunk).
 // `cc` must be one of the __grid_constant__ kernel parameters so that b2/wout become constant-bank operands.
 // GCL additionally stages m as bf16 in this warp's shared-memory slab ([32 rows][64 columns], SWIZZLE_128B) and hands
@@ -110,7 +135,7 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
         float m[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            m[j] = silu_half(fmaf(__uint_as_float(v[j]), 0.5f, cc.b2[col0 + j]));
+            m[j] = silu_half(__uint_as_float(v[j]));
             dot = fmaf(m[j], cc.wout[col0 + j], dot);
         }
         if (kGCL) {
@@ -152,12 +177,14 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     uint8_t* sW = smem;
     uint8_t* sA = smem + EK_W2_BYTES;
     uint8_t* misc = smem + EK_W2_BYTES + EK_A_BYTES;
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(misc);
+    uint8_t* sSlab = misc;                                       // [4 epilogue warps][32 rows][128 B] message staging
+    uint8_t* sAx = misc + EK_SLAB_BYTES;                         // bias step A slice: [16 row groups][2 k cores][8 rows][16 B]
+    uint8_t* sBx = sAx + EK_AX_BYTES;                            // bias step B slice: [32 row groups][2 k cores][8 rows][16 B]
+    int4* sMeta = reinterpret_cast<int4*>(sBx + EK_BX_BYTES);    // [16 producer warps][2 slots][8 edges]
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(sBx + EK_BX_BYTES + EK_META_BYTES);
     uint64_t* mma_done = w_bar + 1;                              // [2]
     uint64_t* tmem_empty = mma_done + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    int4* sMeta = reinterpret_cast<int4*>(misc + 256);           // [16 producer warps][2 slots][8 edges]
-    uint8_t* sSlab = misc + 8192;                          // [4 epilogue warps][32 rows][128 B] message staging
 
     const bool second = (blockIdx.y != 0);
     const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
@@ -178,6 +205,26 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
+    // bias step operands (K-major core matrices, no swizzle): A[r][0] = A[r][1] = 1 ; B[n][0] + B[n][1] = b2[n]
+    {
+        const EdgeConsts& cc = second ? c1 : c0;
+        for (int i = tid; i < (EK_AX_BYTES + EK_BX_BYTES) / 16; i += EK_THREADS) {
+            const int core = i >> 3, r8 = i & 7;                 // 16-byte row r8 of core matrix `core`
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if ((core & 1) == 0) {                               // k core 0 holds k = 0..7
+                if (i < EK_AX_BYTES / 16) {
+                    v.x = 0x3f803f80u;                           // bf16 (1, 1)
+                } else {
+                    const int n = ((core - EK_AX_BYTES / 128) >> 1) * 8 + r8;
+                    const float b = cc.b2[n];
+                    const float hi = __bfloat162float(__float2bfloat16_rn(b));
+                    v.x = pack_bf16x2(hi, b - hi);
+                }
+            }
+            *reinterpret_cast<uint4*>(sAx + (size_t)i * 16) = v;
+        }
+        fence_proxy_async_smem();
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -201,6 +248,12 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             const float4 d = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 8 * lane + 4));
             wr[0] = a.x; wr[1] = a.y; wr[2] = a.z; wr[3] = a.w; wr[4] = b.x; wr[5] = b.y; wr[6] = b.z; wr[7] = b.w;
             w0[0] = c.x; w0[1] = c.y; w0[2] = c.z; w0[3] = c.w; w0[4] = d.x; w0[5] = d.y; w0[6] = d.z; w0[7] = d.w;
+        }
+        uint32_t wr2[4], w02[4];                     // the same weights as bf16x2 pairs (GCL producers)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            wr2[i] = pack_bf16x2(wr[2 * i], wr[2 * i + 1]);
+            w02[i] = pack_bf16x2(w0[2 * i], w0[2 * i + 1]);
         }
         constexpr uint32_t idesc = make_idesc_bf16_f32(EK_TILE, EK_H);
         const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
@@ -226,7 +279,10 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             const float dy = g.x[3 * m.row + 1] - g.x[3 * m.col + 1];
             const float dz = g.x[3 * m.row + 2] - g.x[3 * m.col + 2];
             const float rad = dx * dx + dy * dy + dz * dz;
-            if (lane < 8) meta[slot * 8 + l8] = make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
+            // GCL: both radial features as duplicated bf16x2 words; HEAD: fp32
+            if (lane < 8)
+                meta[slot * 8 + l8] = kGCL ? make_int4(m.row, m.col, (int)pack_bf16x2(rad, rad), (int)pack_bf16x2(m.r0, m.r0))
+                                           : make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
             __syncwarp();
         };
         // 4 edges: gather P[row], Q[col] (two 16-byte bf16 units per edge), first-layer activation, bf16 pack.  The results
@@ -244,19 +300,28 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             uint4 o[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const float rad = __int_as_float(md[jj].z), r0v = __int_as_float(md[jj].w);
                 const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
                 const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
-                float v[8];
+                if (kGCL) {
+                    const uint32_t rad2 = (uint32_t)md[jj].z, r02 = (uint32_t)md[jj].w;
+                    uint32_t ow[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    v[2 * i] = __uint_as_float(pw_[i] << 16) + __uint_as_float(qw_[i] << 16);
-                    v[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u) + __uint_as_float(qw_[i] & 0xffff0000u);
+                    for (int i = 0; i < 4; ++i)
+                        ow[i] = bf2_silu_half(bf2_fma(w02[i], r02, bf2_fma(wr2[i], rad2, bf2_add(pw_[i], qw_[i]))));
+                    o[jj] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                } else {
+                    const float rad = __int_as_float(md[jj].z), r0v = __int_as_float(md[jj].w);
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[2 * i] = __uint_as_float(pw_[i] << 16) + __uint_as_float(qw_[i] << 16);
+                        v[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u) + __uint_as_float(qw_[i] & 0xffff0000u);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
+                    o[jj].x = pack_bf16x2(v[0], v[1]); o[jj].y = pack_bf16x2(v[2], v[3]);
+                    o[jj].z = pack_bf16x2(v[4], v[5]); o[jj].w = pack_bf16x2(v[6], v[7]);
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
-                o[jj].x = pack_bf16x2(v[0], v[1]); o[jj].y = pack_bf16x2(v[2], v[3]);
-                o[jj].z = pack_bf16x2(v[4], v[5]); o[jj].w = pack_bf16x2(v[6], v[7]);
             }
             before_store();
 #pragma unroll
@@ -297,6 +362,8 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                                   make_kmajor_sw128_desc(b0 + kk * 32768 + k * 32), idesc, (kk | k) != 0);
                     }
                 }
+                umma_bf16(d_tmem, make_kmajor_noswz_desc(smem_u32(sAx), 128, 256), make_kmajor_noswz_desc(smem_u32(sBx), 128, 256),
+                          idesc, 1u);                                               // + b2
                 umma_commit(&mma_done[buf]);
             }
             __syncwarp();   // re-converge the issuing lane: without it the warp stays split for the whole next tile

@@ -400,8 +400,13 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         RET_IF(upload(e, be, &L.bias_e)); RET_IF(upload(e, bcv, &L.bias_c));
         RET_IF(upload(e, edge_cols(e0w), &L.w1e_e)); RET_IF(upload(e, edge_cols(c0w), &L.w1e_c));
         RET_IF(upload(e, edge_cols(x0w), &L.w1e_x));
-        RET_IF(upload(e, to_bf(e2w, (size_t)H * H), &L.w2_e)); RET_IF(upload(e, to_bf(c2w, (size_t)H * H), &L.w2_c));
-        RET_IF(upload(e, to_bf(x2w, (size_t)H * H), &L.w2_x));
+        auto to_bf_half = [&](const float* w, size_t n) {       // edge-MLP second layers: the kernel evaluates SiLU on x/2
+            std::vector<__nv_bfloat16> v(n);
+            for (size_t i = 0; i < n; ++i) v[i] = f2bf(0.5f * w[i]);
+            return v;
+        };
+        RET_IF(upload(e, to_bf_half(e2w, (size_t)H * H), &L.w2_e)); RET_IF(upload(e, to_bf_half(c2w, (size_t)H * H), &L.w2_c));
+        RET_IF(upload(e, to_bf_half(x2w, (size_t)H * H), &L.w2_x));
         RET_IF(upload(e, to_bf(n0w, (size_t)H * 2 * H), &L.w3)); RET_IF(upload(e, to_bf(n2w, (size_t)H * H), &L.w4));
         RET_IF(upload(e, std::vector<float>(n0b, n0b + H), &L.b3)); RET_IF(upload(e, std::vector<float>(n2b, n2b + H), &L.b4));
         for (int o = 0; o < H; ++o) {
