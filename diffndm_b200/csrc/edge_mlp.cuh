@@ -255,6 +255,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             wr2[i] = pack_bf16x2(wr[2 * i], wr[2 * i + 1]);
             w02[i] = pack_bf16x2(w0[2 * i], w0[2 * i + 1]);
         }
+        constexpr bool kPacked = kGCL;               // bf16x2 producer arithmetic; the coordinate heads stay fp32 (measured: packed doubles the x error)
         constexpr uint32_t idesc = make_idesc_bf16_f32(EK_TILE, EK_H);
         const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
         const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
@@ -281,7 +282,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             const float rad = dx * dx + dy * dy + dz * dz;
             // GCL: both radial features as duplicated bf16x2 words; HEAD: fp32
             if (lane < 8)
-                meta[slot * 8 + l8] = kGCL ? make_int4(m.row, m.col, (int)pack_bf16x2(rad, rad), (int)pack_bf16x2(m.r0, m.r0))
+                meta[slot * 8 + l8] = kPacked ? make_int4(m.row, m.col, (int)pack_bf16x2(rad, rad), (int)pack_bf16x2(m.r0, m.r0))
                                            : make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
             __syncwarp();
         };
@@ -302,7 +303,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             for (int jj = 0; jj < 4; ++jj) {
                 const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
                 const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
-                if (kGCL) {
+                if (kPacked) {
                     const uint32_t rad2 = (uint32_t)md[jj].z, r02 = (uint32_t)md[jj].w;
                     uint32_t ow[4];
 #pragma unroll
