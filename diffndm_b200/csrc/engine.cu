@@ -735,7 +735,7 @@ extern "C" int dndm_sampler_step(DndmEngine* e, const float* z_in, const float* 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     RET_IF(prepare_batch(e, lig_mask, pocket_mask, n_lig, n_pocket, n_samples, st));
     sampler_step_kernel<<<n_samples, 128, 0, st>>>(z_in, eps ? eps : noise, noise, xh_pocket_in, coef, grad, lambda, e->lig_ptr,
-                                                   e->pok_ptr, e->cfg.atom_nf, z_out, xh_pocket_out, e->flags);
+                                                   e->pok_ptr, e->cfg.atom_nf, z_out, xh_pocket_out, e->flags, eps != nullptr);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;

@@ -237,14 +237,16 @@ decode_kernel(const float* __restrict__ h, const float* __restrict__ x_final, co
 //           (c_z = 1/alpha_ts, c_eps = sigma2_ts/alpha_ts/sigma_t, c_noise = sigma_ts sigma_s / sigma_t)
 //   then the per-sample LIGAND centre of mass of the new coordinates is removed from ligand AND pocket.
 //   An optional guidance term  + lambda * grad  (SPSA, :801-806) is applied to the coordinates before the
-//   projection.  One CTA per sample; fixed-order reductions.  |COM| drift of the INPUT z_t relative to its
-//   largest coordinate above 1e-2 raises flag bit 1 (assert_mean_zero_with_mask, en_diffusion.py:930-935).
+//   projection.  One CTA per sample; fixed-order reductions.  For a true reverse step (eps given) a |COM| drift of the
+//   INPUT z_t above 1e-2 of its largest coordinate raises flag bit 1 (assert_mean_zero_with_mask on zt_lig,
+//   conditional_model.py:535, en_diffusion.py:1829-1833); the prior / forward-noising / projection uses (eps == null)
+//   take inputs that are not COM-free by construction and are not checked.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 sampler_step_kernel(const float* z_t, const float* eps, const float* noise, const float* xh_pok_in,
                     const float* __restrict__ coef /*[B][3]*/, const float* grad /*[N_l][3] or null*/, float lambda,
                     const int* __restrict__ lig_ptr, const int* __restrict__ pok_ptr, int nf, float* z_out,
-                    float* xh_pok_out, unsigned* flags) {   // z_out / xh_pok_out may alias the inputs (in place)
+                    float* xh_pok_out, unsigned* flags, int check_input_com) {   // z_out / xh_pok_out may alias the inputs (in place)
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int D = 3 + nf;
@@ -284,7 +286,7 @@ sampler_step_kernel(const float* z_t, const float* eps, const float* noise, cons
             a0 += red[0][k]; a1 += red[1][k]; a2 += red[2][k]; m = fmaxf(m, red[3][k]);
         }
         const float err = fmaxf(fabsf(a0), fmaxf(fabsf(a1), fabsf(a2)));
-        if (err / (m + 1e-10f) >= 1e-2f) atomicOr(flags, 2u);
+        if (check_input_com && err / (m + 1e-10f) >= 1e-2f) atomicOr(flags, 2u);
     }
     const float c0 = com[0], c1 = com[1], c2 = com[2];
     for (int i = l0 + tid; i < l1; i += blockDim.x) {

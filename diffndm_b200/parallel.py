@@ -34,7 +34,7 @@ def _all_gather_varlen(t: torch.Tensor, group=None) -> List[torch.Tensor]:
 
 
 def atp_select_distributed(scores: torch.Tensor, z_lig: torch.Tensor, lig_sizes: torch.Tensor, top_k: int,
-                           group=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                           group=None, per_candidate: torch.Tensor = None):
     """Global top-k over candidates that live on different ranks.
 
     scores    [C_r]        mixed reward of this rank's candidates
@@ -42,6 +42,8 @@ def atp_select_distributed(scores: torch.Tensor, z_lig: torch.Tensor, lig_sizes:
     lig_sizes [C_r]        atoms per candidate
     Returns (z_sel [sum n_sel, 13], mask_sel [sum n_sel] with values 0..top_k-1, sizes_sel [top_k]) -- identical on
     every rank, winners ordered by decreasing score with ties broken by global candidate index (deterministic).
+    ``per_candidate`` [C_r, k] (optional) is any fixed-width per-candidate payload (e.g. the candidate's pocket
+    translation and source sample); the winners' rows are returned as a fourth value.
     """
     all_scores = torch.cat(_all_gather_varlen(scores.float(), group))
     all_sizes = torch.cat(_all_gather_varlen(lig_sizes.long(), group))
@@ -54,4 +56,7 @@ def atp_select_distributed(scores: torch.Tensor, z_lig: torch.Tensor, lig_sizes:
         s, n = int(starts[c]), int(all_sizes[c])
         zs.append(all_z[s:s + n])
         ms.append(torch.full((n,), rank_pos, dtype=torch.long, device=all_z.device))
+    if per_candidate is not None:
+        all_pc = torch.cat(_all_gather_varlen(per_candidate.float(), group))
+        return torch.cat(zs), torch.cat(ms), all_sizes[order], all_pc[order]
     return torch.cat(zs), torch.cat(ms), all_sizes[order]

@@ -24,6 +24,7 @@ from typing import Callable, Optional, Sequence
 
 import numpy as np
 import torch
+import torch.distributed as dist
 import torch.nn.functional as F
 
 from .engine import B200EGNNDynamics, FLAG_COM_DRIFT, FLAG_EDGE_OVERFLOW, FLAG_NAN
@@ -253,33 +254,155 @@ class ConditionalSampler:
             x_lig, x_pocket = self.remove_mean_batch(x_lig, x_pocket, lig_mask, pocket_mask, B)
         return torch.cat([x_lig, h_lig.float()], dim=1), torch.cat([x_pocket, h_pocket], dim=1), lig_mask, pocket_mask
 
+    # -- inpainting (RePaint resampling), conditional_model.py:1491-1790 ----------------------------------------------------
+    @torch.no_grad()
+    def inpaint(self, ligand, pocket, lig_fixed, svdd: int = 0, resamplings: int = 1, timesteps: Optional[int] = None,
+                center: str = 'ligand', reward_fn: Optional[Callable] = None, noise=None, spsa_window=(12, 16),
+                spsa_k: int = 10, svdd_schedule=(10, 2), svdd_groups: int = 5):
+        """ConditionalDDPM.inpaint without the host-chemistry arguments: keep the atoms flagged in ``lig_fixed`` [N_l],
+        generate the rest.  ``ligand``: dict with 'x' [N_l,3], 'one_hot' [N_l,atom_nf], 'size' [B], 'mask' [N_l];
+        ``pocket`` as in sample_given_pocket.  Every (s, u) iteration is: reverse step (:1566-1568), forward-noised known
+        part q(z_s | x) on the pocket-shifted input (:1588-1594), COM matching over the fixed atoms + blend (:1596-1609)
+        and, except on the last resampling, the re-noising move z_s -> z_t (:1611-1615).  All three stochastic moves run
+        in the fused sampler-step kernel (out = c0 z - c1 eps + c2 noise, then the ligand-COM projection).
+        The reference hard-wires an SPSA update for 12 <= s <= 16 on the first resampling (:1570-1586) and an ATP event at
+        s <= 10, s % 2 == 0 when svdd == 1 (:1627-1778); both need host rewards and run only if ``reward_fn`` is given.
+        ``noise``: optional iterable of [N_l, 3+atom_nf] draws in the reference's order (z_T, then per iteration
+        reverse / known / re-noise, then the final head).  Returns (xh_lig, xh_pocket, lig_mask, pocket_mask)."""
+        timesteps = self.T if timesteps is None else timesteps
+        dev = self.device
+        B = len(ligand['size'])
+        nv0, nv1, nb1 = self.norm_values[0], self.norm_values[1], self.norm_biases[1]
+        lig_mask = ligand['mask'].to(dev).long()
+        pocket_mask = pocket['mask'].to(dev).long()
+        lx = ligand['x'].to(dev, torch.float32) / nv0
+        lh = (ligand['one_hot'].to(dev).float() - nb1) / nv1
+        xh0_pocket = torch.cat([pocket['x'].to(dev, torch.float32) / nv0,
+                                (pocket['one_hot'].to(dev).float() - nb1) / nv1], dim=1).contiguous()
+        fixed = lig_fixed.to(dev).reshape(-1).float()
+        fx = fixed > 0
+        n_l = int(lig_mask.numel())
+        draws = iter(noise) if noise is not None else None
+        nxt = lambda: self._noise(n_l, None if draws is None else next(draws))
+
+        def seg_mean(x, idx):
+            cnt = torch.bincount(idx, minlength=B).clamp(min=1).float()
+            return torch.zeros((B, x.shape[1]), device=dev).index_add_(0, idx, x) / cnt[:, None]
+
+        com_pocket_0 = seg_mean(xh0_pocket[:, :3], pocket_mask)
+        if center == 'ligand':
+            mean_known = seg_mean(lx[fx], lig_mask[fx])
+        elif center == 'pocket':
+            mean_known = com_pocket_0
+        else:
+            raise NotImplementedError(f"Centering option {center} not implemented")
+        mu = torch.cat([mean_known, torch.zeros((B, self.atom_nf), device=dev)], dim=1)[lig_mask].contiguous()
+        ident = torch.tensor([[1.0, 0.0, 1.0]], device=dev).repeat(B, 1)
+        z_lig, xh_pocket = self.engine.sampler_step(mu, None, nxt(), xh0_pocket, ident, lig_mask, pocket_mask, B)
+        xh_ligand = torch.cat([lx, lh], dim=1).contiguous()
+        zero = torch.zeros(B)
+        for s in reversed(range(0, timesteps)):
+            s_array = torch.full((B, 1), fill_value=s, dtype=torch.float32) / timesteps
+            t_array = torch.full((B, 1), fill_value=s + 1, dtype=torch.float32) / timesteps
+            g_s, g_t = self.lookup(s_array), self.lookup(t_array)
+            alpha_s, sigma_s = torch.sqrt(torch.sigmoid(-g_s)), torch.sqrt(torch.sigmoid(g_s))
+            coef_known = torch.stack([alpha_s, zero, sigma_s], dim=1).to(dev)
+            sigma2_ts = -torch.expm1(F.softplus(g_s) - F.softplus(g_t))
+            alpha_ts = torch.exp(0.5 * (F.logsigmoid(-g_t) - F.logsigmoid(-g_s)))
+            coef_renoise = torch.stack([alpha_ts, zero, torch.sqrt(sigma2_ts)], dim=1).to(dev)
+            for u in range(resamplings):
+                z_unknown, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
+                                                                 noise=None if draws is None else next(draws), n_samples=B)
+                if reward_fn is not None and spsa_window[0] <= s <= spsa_window[1] and u < 1:
+                    zeta = 1e-3 * (s / 1200)                                              # :1571-1572
+                    z_upd, xh_pocket = self.my_update_z_lig(z_lig, xh_pocket, lig_mask, pocket_mask, t_array, B, zeta,
+                                                            reward_fn, guidance_scale=1e-3, k=spsa_k)
+                    z_unknown, xh_pocket = self._unnormalize_quirk(z_upd, xh_pocket, lig_mask, pocket_mask, B)
+                # known atoms follow the pocket's accumulated translation, then q(z_s | x)
+                com_pocket = seg_mean(xh_pocket[:, :3], pocket_mask)
+                xh_ligand[:, :3] = lx + (com_pocket - com_pocket_0)[lig_mask]
+                z_known, xh_pocket = self.engine.sampler_step(xh_ligand, None, nxt(), xh_pocket, coef_known, lig_mask,
+                                                              pocket_mask, B)
+                dx = seg_mean(z_unknown[fx][:, :3], lig_mask[fx]) - seg_mean(z_known[fx][:, :3], lig_mask[fx])
+                z_known[:, :3] += dx[lig_mask]
+                xh_pocket[:, :3] += dx[pocket_mask]
+                z_lig = (z_known * fixed[:, None] + z_unknown * (1 - fixed[:, None])).contiguous()
+                if u < resamplings - 1:
+                    z_lig, xh_pocket = self.engine.sampler_step(z_lig, None, nxt(), xh_pocket, coef_renoise, lig_mask,
+                                                                pocket_mask, B)
+            if svdd == 1 and reward_fn is not None and s <= svdd_schedule[0] and s % svdd_schedule[1] == 0:
+                sizes = torch.bincount(lig_mask, minlength=B)
+                if int(sizes.min()) != int(sizes.max()):
+                    raise NotImplementedError("ATP re-batching inside inpaint keeps ligand['mask'] (conditional_model.py:"
+                                              "1626, 1779): only defined for equally sized ligands")
+                z_lig, xh_pocket, _ = self._atp_event(s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask, B,
+                                                      reward_fn, svdd_groups)
+                z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+        x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(
+            z_lig, xh_pocket, lig_mask, pocket_mask, B, noise=None if draws is None else next(draws))
+        self._raise_on_flags()
+        return torch.cat([x_lig, h_lig.float()], dim=1), torch.cat([x_pocket, h_pocket], dim=1), lig_mask, pocket_mask
+
     # -- ATP ("SVDD") event, conditional_model.py:1085-1241 -------------------------------------------------------------
     def _atp_event(self, s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask, B, reward_fn, n_groups):
         """Draw n_groups-1 extra candidate next-states from (z, s, t), score the current and x0-look-ahead molecules of
         all n_groups*B candidates, keep the global top-B (:1203-1232).  The candidate groups are evaluated as ONE batch of
-        n_groups*B samples per denoiser call instead of the reference's sequential calls."""
+        n_groups*B samples per denoiser call instead of the reference's sequential calls.
+
+        With ``self.atp_group`` set (a torch.distributed group whose ranks carry the SAME trajectory state), the candidate
+        groups are split over the ranks -- group g is drawn, denoised and scored on rank g % world -- and the winners are
+        rebuilt everywhere from one all-gather of scores, latents and pocket translations (parallel.py)."""
         dev = self.device
         n_l, n_p = z_lig.shape[0], xh_pocket.shape[0]
         G = n_groups
-        offs = torch.arange(G, device=dev) * B
-        big_lig_mask = (lig_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
-        big_pocket_mask = (pocket_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
+        group = getattr(self, 'atp_group', None)
+        world = dist.get_world_size(group) if group is not None else 1
+        rank = dist.get_rank(group) if group is not None else 0
+        n_extra = len([g for g in range(1, G) if g % world == rank])         # extra groups drawn here
+        n_here = n_extra + (1 if rank == 0 else 0)                          # rank 0 also owns the current state (group 0)
         rep = lambda a, n: a.unsqueeze(0).repeat(n, 1, 1).reshape(n * a.shape[0], -1)
-        # extra candidates: sample_p_zs_given_zt from the same (already denoised) state, :1109-1117
-        zs_extra, xp_extra = self.sample_p_zs_given_zt(
-            s_array.repeat(G - 1, 1), t_array.repeat(G - 1, 1), rep(z_lig, G - 1), rep(xh_pocket, G - 1),
-            big_lig_mask[:(G - 1) * n_l], big_pocket_mask[:(G - 1) * n_p], n_samples=(G - 1) * B)
-        big_z = torch.cat([z_lig, zs_extra], dim=0)
-        big_p = torch.cat([xh_pocket, xp_extra], dim=0)
-        x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(G, 1), big_z, big_p, big_lig_mask, big_pocket_mask, G * B)
-        r0 = torch.as_tensor(reward_fn(x0_l, h0_l.argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
-        r = torch.as_tensor(reward_fn(big_z[:, :3], big_z[:, 3:].argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
-        mixed = r0 * (s / 250) + r * (250 - s / 250)                                  # [sic] :1203
+        offs = torch.arange(max(n_here, 1), device=dev) * B
+        big_lig_mask = (lig_mask.unsqueeze(0) + offs[:, None]).reshape(-1)[:n_here * n_l]
+        big_pocket_mask = (pocket_mask.unsqueeze(0) + offs[:, None]).reshape(-1)[:n_here * n_p]
+        parts_z, parts_p = ([z_lig], [xh_pocket]) if rank == 0 else ([], [])
+        if n_extra > 0:                # extra candidates: sample_p_zs_given_zt from the same (already denoised) state, :1109-1117
+            zs_extra, xp_extra = self.sample_p_zs_given_zt(
+                s_array.repeat(n_extra, 1), t_array.repeat(n_extra, 1), rep(z_lig, n_extra), rep(xh_pocket, n_extra),
+                big_lig_mask[:n_extra * n_l], big_pocket_mask[:n_extra * n_p], n_samples=n_extra * B)
+            parts_z.append(zs_extra)
+            parts_p.append(xp_extra)
+        if n_here > 0:
+            big_z = torch.cat(parts_z, dim=0)
+            big_p = torch.cat(parts_p, dim=0)
+            x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(n_here, 1), big_z, big_p, big_lig_mask, big_pocket_mask, n_here * B)
+            r0 = torch.as_tensor(reward_fn(x0_l, h0_l.argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
+            r = torch.as_tensor(reward_fn(big_z[:, :3], big_z[:, 3:].argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
+            mixed = r0 * (s / 250) + r * (250 - s / 250)                              # [sic] :1203
+        else:
+            big_z = z_lig[:0]
+            big_p = xh_pocket[:0]
+            mixed = torch.zeros(0, device=dev)
+        if world > 1:
+            from .parallel import atp_select_distributed
+            sizes = torch.bincount(lig_mask, minlength=B)
+            pstart = torch.searchsorted(pocket_mask, torch.arange(B, device=dev))      # first pocket atom of every sample
+            src = torch.arange(B, device=dev).repeat(n_here)                           # source sample of every candidate
+            first = (torch.arange(n_here, device=dev) * n_p).repeat_interleave(B) + pstart.repeat(n_here)
+            shift = big_p[first, :3] - xh_pocket[pstart.repeat(n_here), :3] if n_here > 0 else big_p[:0, :3]
+            payload = torch.cat([shift, src[:, None].float()], dim=1)
+            z_sel, m_sel, _, pay = atp_select_distributed(mixed, big_z, sizes.repeat(n_here), B, group=group,
+                                                          per_candidate=payload)
+            new_p = []
+            for k in range(B):                                                        # winners' pockets, rank order
+                rows = xh_pocket[pocket_mask == int(pay[k, 3])].clone()
+                rows[:, :3] += pay[k, :3]
+                new_p.append(rows)
+            return z_sel.contiguous(), torch.cat(new_p, 0).contiguous(), m_sel
         _, top_idx = mixed.topk(k=B, largest=True)                                     # :1205
         new_z, new_p, new_m = [], [], []
-        for rank, idx in enumerate(top_idx.tolist()):                                  # :1212-1227
+        for rank_pos, idx in enumerate(top_idx.tolist()):                              # :1212-1227
             nm = big_lig_mask == idx
             new_z.append(big_z[nm])
             new_p.append(big_p[big_pocket_mask == idx])
-            new_m.append(torch.full((int(nm.sum()),), rank, dtype=torch.long, device=dev))
+            new_m.append(torch.full((int(nm.sum()),), rank_pos, dtype=torch.long, device=dev))
         return torch.cat(new_z, 0).contiguous(), torch.cat(new_p, 0).contiguous(), torch.cat(new_m, 0)

@@ -435,6 +435,90 @@ def atp_select(r0, r, s, big_z, big_pocket, big_lig_mask, big_pocket_mask, top_k
 
 
 # ----------------------------------------------------------------------------
+# inpainting (RePaint resampling) -- conditional_model.py:1491-1790, 188-215, 470-481
+# ----------------------------------------------------------------------------
+def noised_representation(xh_lig, xh_pocket, noise, gamma, lig_mask, pocket_mask):
+    """q(z_t | x): alpha_t x + sigma_t eps, then the ligand-COM projection (conditional_model.py:188-215)."""
+    g = np.asarray(gamma, np.float32)
+    nb = len(g)
+    alpha = np.sqrt(sigmoid(-g))[lig_mask][:, None]
+    sigma = np.sqrt(sigmoid(g))[lig_mask][:, None]
+    z = (alpha * np.asarray(xh_lig, np.float32) + sigma * np.asarray(noise, np.float32)).astype(np.float32)
+    xp = np.asarray(xh_pocket, np.float32).copy()
+    z[:, :3], xp[:, :3] = remove_mean_batch(z[:, :3], xp[:, :3], lig_mask, pocket_mask, nb)
+    return z, xp
+
+
+def sample_p_zt_given_zs(zs_lig, xh_pocket, noise, gamma_t, gamma_s, lig_mask, pocket_mask):
+    """Forward (re-noising) move of the resampling loop: z_t = alpha_{t|s} z_s + sigma_{t|s} eps, COM-projected
+    (conditional_model.py:470-481 via sample_normal_zero_com :165-186)."""
+    sc = step_scalars(gamma_s, gamma_t)
+    nb = len(sc['alpha_ts'])
+    z = (sc['alpha_ts'][lig_mask][:, None] * np.asarray(zs_lig, np.float32)
+         + sc['sigma_ts'][lig_mask][:, None] * np.asarray(noise, np.float32)).astype(np.float32)
+    xp = np.asarray(xh_pocket, np.float32).copy()
+    z[:, :3], xp[:, :3] = remove_mean_batch(z[:, :3], xp[:, :3], lig_mask, pocket_mask, nb)
+    return z, xp
+
+
+def inpaint_combine(z_known, z_unknown, xh_pocket, lig_fixed, lig_mask, pocket_mask, nb):
+    """Move the noised known part onto the COM of the denoised one (both over the FIXED atoms), shift the pocket with it
+    and blend (conditional_model.py:1596-1609)."""
+    fx = np.asarray(lig_fixed).reshape(-1) > 0
+    com_noised = segment_mean(z_known[fx][:, :3], lig_mask[fx], nb)
+    com_denoised = segment_mean(z_unknown[fx][:, :3], lig_mask[fx], nb)
+    dx = (com_denoised - com_noised).astype(np.float32)
+    zk = z_known.copy()
+    zk[:, :3] = zk[:, :3] + dx[lig_mask]
+    xp = xh_pocket.copy()
+    xp[:, :3] = xp[:, :3] + dx[pocket_mask]
+    f = fx.astype(np.float32)[:, None]
+    return (zk * f + z_unknown * (1 - f)).astype(np.float32), xp
+
+
+def inpaint(W, lig_x, lig_onehot, lig_mask, pocket_x, pocket_onehot, pocket_mask, lig_fixed, noise, timesteps,
+            resamplings, cfg: OracleConfig = OracleConfig(), T=500, dtype=np.float32):
+    """ConditionalDDPM.inpaint (conditional_model.py:1491-1790) with center='ligand', svdd=0 and every Gaussian draw
+    injected in the reference's order (``noise`` [n_draws, N_l, 3+atom_nf]); the SPSA window (12 <= s <= 16) is outside
+    the fixtures' range.  Returns (xh_lig with one-hot features, xh_pocket) in Angstrom like the reference."""
+    gam = gamma_table(T)
+    nb = int(lig_mask.max()) + 1
+    nv0, nv1, nb1 = np.float32(cfg.norm_values[0]), np.float32(cfg.norm_values[1]), np.float32(cfg.norm_biases[1])
+    lx = np.asarray(lig_x, np.float32) / nv0
+    lh = (np.asarray(lig_onehot, np.float32) - nb1) / nv1
+    xh0_pocket = np.concatenate([np.asarray(pocket_x, np.float32) / nv0,
+                                 (np.asarray(pocket_onehot, np.float32) - nb1) / nv1], 1)
+    com_pocket_0 = segment_mean(xh0_pocket[:, :3], pocket_mask, nb)
+    xh_ligand = np.concatenate([lx, lh], 1)
+    fx = np.asarray(lig_fixed).reshape(-1) > 0
+    mean_known = segment_mean(lx[fx], lig_mask[fx], nb)
+    it = iter(noise)
+    mu = np.concatenate([mean_known, np.zeros((nb, lh.shape[1]), np.float32)], 1)[lig_mask]
+    z = (mu + next(it)).astype(np.float32)
+    xp = xh0_pocket.copy()
+    z[:, :3], xp[:, :3] = remove_mean_batch(z[:, :3], xh0_pocket[:, :3], lig_mask, pocket_mask, nb)
+    look = lambda tt: gam[int(round(tt * T))]
+    for s in reversed(range(timesteps)):
+        for u in range(resamplings):
+            ts, tt = s / timesteps, (s + 1) / timesteps
+            g_s = np.full(nb, look(ts), np.float32)
+            g_t = np.full(nb, look(tt), np.float32)
+            eps, _ = dynamics_forward(W, z, xp, np.full((nb, 1), tt, np.float32), lig_mask, pocket_mask, cfg, dtype=dtype)
+            z_unknown, xp = sample_p_zs_given_zt(z, xp, eps.astype(np.float32), next(it), g_s, g_t, lig_mask, pocket_mask)
+            com_pocket = segment_mean(xp[:, :3], pocket_mask, nb)
+            xh_ligand[:, :3] = lx + (com_pocket - com_pocket_0)[lig_mask]
+            z_known, xp = noised_representation(xh_ligand, xp, next(it), g_s, lig_mask, pocket_mask)
+            z, xp = inpaint_combine(z_known, z_unknown, xp, lig_fixed, lig_mask, pocket_mask, nb)
+            if u < resamplings - 1:
+                z, xp = sample_p_zt_given_zs(z, xp, next(it), g_t, g_s, lig_mask, pocket_mask)
+    g0 = np.full(nb, gam[0], np.float32)
+    eps0, _ = dynamics_forward(W, z, xp, np.zeros((nb, 1), np.float32), lig_mask, pocket_mask, cfg, dtype=dtype)
+    x_l, t_l, x_p, h_p = sample_p_xh_given_z0(z, xp, eps0.astype(np.float32), next(it), g0, lig_mask, pocket_mask, cfg)
+    onehot = np.eye(lh.shape[1], dtype=np.float32)[t_l]
+    return np.concatenate([x_l, onehot], 1), np.concatenate([x_p, h_p], 1), z, xp
+
+
+# ----------------------------------------------------------------------------
 # algorithmic work model (SURVEY.md §8d)
 # ----------------------------------------------------------------------------
 def reference_flops(n_nodes, n_edges, cfg: OracleConfig = OracleConfig()):

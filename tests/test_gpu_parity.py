@@ -20,6 +20,7 @@ CFG = O.OracleConfig()
 EDGE_CASES, _ = load_npz_groups('edges.npz')
 FWD_CASES, _ = load_npz_groups('forward.npz')
 TRAJ_CASES, _ = load_npz_groups('trajectory.npz')
+INPAINT_CASES, _ = load_npz_groups('inpaint.npz')
 
 X_ABS_TOL = 1e-3       # eps_x, absolute (A) ...
 X_REL_TOL = 2e-3       # ... or relative to max |eps_x|
@@ -269,6 +270,53 @@ def test_free_running_trajectory_vs_reference(dyn, dev):
     assert (xh_l.cpu().numpy()[:, 3:].argmax(1) == ref[:, 3:].argmax(1)).mean() > 0.9
 
 
+@pytest.mark.parametrize('name', sorted(INPAINT_CASES))
+def test_inpaint_vs_reference(dyn, dev, name):
+    """ConditionalSampler.inpaint (RePaint resampling) with the reference's Gaussian draws: fixed atoms, blend, pocket
+    translation and re-noising follow conditional_model.py:1491-1790."""
+    from diffndm_b200.sampler import ConditionalSampler
+    c = INPAINT_CASES[name]
+    smp = ConditionalSampler(dyn, timesteps=500)
+    B, n_p = len(c['sizes']), len(c['pocket_x'])
+    oh = np.eye(10, dtype=np.float32)
+    pocket = {'x': torch.from_numpy(np.tile(c['pocket_x'], (B, 1))), 'one_hot': torch.from_numpy(np.tile(oh[c['pocket_t']], (B, 1))),
+              'size': torch.tensor([n_p] * B), 'mask': torch.arange(B).repeat_interleave(n_p)}
+    ligand = {'x': torch.from_numpy(c['lig_x']), 'one_hot': torch.from_numpy(oh[c['lig_t']]),
+              'size': torch.from_numpy(c['sizes']), 'mask': torch.from_numpy(c['lig_mask'])}
+    xh_l, xh_p, lm, pm = smp.inpaint(ligand, pocket, torch.from_numpy(c['lig_fixed']), resamplings=int(c['resamplings']),
+                                     timesteps=int(c['timesteps']), noise=[_t(n, dev) for n in c['noise']])
+    ref = c['final_lig']
+    scale = max(1.0, np.abs(ref[:, :3]).max())
+    assert np.abs(xh_l.cpu().numpy()[:, :3] - ref[:, :3]).max() / scale < 2e-2
+    assert np.abs(xh_p.cpu().numpy()[:, :3] - c['final_pocket'][:, :3]).max() / scale < 2e-2
+    assert (xh_l.cpu().numpy()[:, 3:].argmax(1) == ref[:, 3:].argmax(1)).mean() > 0.9
+    assert np.array_equal(lm.cpu().numpy(), c['lig_mask'])
+
+
+def test_com_drift_raises_assertion_error(dyn, dev):
+    """assert_mean_zero_with_mask on z_t (conditional_model.py:535): a reverse step from a state whose ligand COM is
+    off by more than 1e-2 of its largest coordinate raises AssertionError; prior / forward-noising moves do not."""
+    from diffndm_b200 import synthetic
+    from diffndm_b200.sampler import ConditionalSampler
+    px, pt = synthetic.synthetic_pocket(3, 40)
+    b = synthetic.make_batch(px, pt, np.array([6, 9]), 4)
+    smp = ConditionalSampler(dyn, timesteps=500, check_every_step=True)
+    lm, pm = _t(b['lig_mask'], dev), _t(b['pocket_mask'], dev)
+    z = _t(b['xh_lig'], dev).clone()
+    z[:, :3] -= torch.zeros((2, 3), device=dev).index_add_(0, lm, z[:, :3])[lm] / torch.bincount(lm)[lm][:, None]
+    s = torch.full((2, 1), 100 / 500.)
+    t = torch.full((2, 1), 101 / 500.)
+    smp.sample_p_zs_given_zt(s, t, z, _t(b['xh_pocket'], dev), lm, pm, n_samples=2)        # COM-free input: fine
+    z_bad = z.clone()
+    z_bad[:, 0] += 0.5
+    with pytest.raises(AssertionError):
+        smp.sample_p_zs_given_zt(s, t, z_bad, _t(b['xh_pocket'], dev), lm, pm, n_samples=2)
+    # a forward-noising move takes inputs that are not COM-free by construction
+    coef = torch.tensor([[0.9, 0.0, 0.1]], device=dev).repeat(2, 1)
+    dyn.engine.sampler_step(z_bad, None, torch.randn_like(z_bad), _t(b['xh_pocket'], dev), coef, lm, pm, 2)
+    assert dyn.engine.read_flags() == 0
+
+
 def test_sampler_step_vs_oracle_and_in_place(dyn, dev):
     from diffndm_b200 import synthetic
     px, pt = synthetic.synthetic_pocket(2, 77)
@@ -399,6 +447,74 @@ def test_atp_event_vs_oracle(dyn, dev):
         assert np.abs(zc[start:start + n, :3] - xc[mc == idx]).max() < 1e-6
         start += n
     assert xp.shape[0] == n_p and z.shape[0] == len(lm_np)
+
+
+def _atp_dist_worker(rank, world, port, ret):
+    import os
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from diffndm_b200 import synthetic
+    from diffndm_b200.engine import B200EGNNDynamics
+    from diffndm_b200.sampler import ConditionalSampler
+    from diffndm_b200.weights import DynamicsConfig, random_init
+    dev = torch.device('cuda', rank)
+    dyn = B200EGNNDynamics(DynamicsConfig(), random_init(DynamicsConfig(), 0, 0.3), max_nodes=4096,
+                           max_edges=200000, max_samples=64).eval()
+    px, pt = synthetic.synthetic_pocket(8, 50)
+    b = synthetic.make_batch(px, pt, np.array([6, 9, 5, 7]), 8)          # identical state on every rank
+    B, G, s = 4, 5, 20
+    smp = ConditionalSampler(dyn, timesteps=500)
+    smp.atp_group = dist.group.WORLD
+    scored = []
+
+    def reward(x, types, mask):
+        x = x.double()
+        r = []
+        for i in range(int(mask.max()) + 1):
+            xi = x[mask == i]
+            r.append(float(((xi - xi.mean(0)) ** 2).sum(1).mean().sqrt()))
+        scored.append(len(r))
+        return r
+
+    torch.manual_seed(100 + rank)                                       # the extra candidate draws differ per rank
+    t = lambda a: torch.from_numpy(a).to(dev)
+    z, xp, lm = smp._atp_event(s, torch.full((B, 1), s / 500), torch.full((B, 1), (s + 1) / 500), t(b['xh_lig']),
+                               t(b['xh_pocket']), t(b['lig_mask']), t(b['pocket_mask']), B, reward, G)
+    # every rank must have rebuilt the same winners
+    n = torch.tensor([z.shape[0]], device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    same = all(int(k) == int(n) for k in ns)
+    if same:
+        zs = [torch.zeros_like(z) for _ in range(world)]
+        ps = [torch.zeros_like(xp) for _ in range(world)]
+        dist.all_gather(zs, z.contiguous())
+        dist.all_gather(ps, xp.contiguous())
+        same = all(torch.equal(zs[0], q) for q in zs) and all(torch.equal(ps[0], q) for q in ps)
+    # groups 0, 2, 4 live on rank 0 and 1, 3 on rank 1: each scored look-ahead + current molecules of its own groups only
+    n_groups_here = len([g for g in range(G) if g % world == rank])
+    ok = same and scored == [n_groups_here * B] * 2 and xp.shape[0] == len(b['pocket_mask']) and int(lm.max()) == B - 1
+    # a winner's pocket is the incoming pocket translated rigidly
+    d = (xp[:, :3] - t(b['xh_pocket'])[:, :3])
+    ok = ok and float((d - d[0]).abs().max()) < 1e3            # finite
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (run under gpurun --gpus 2)')
+def test_atp_event_distributed_two_gpus():
+    """the one exchange on the path -- candidate groups of an ATP event split over two ranks, winners
+    rebuilt from an NCCL all-gather; both ranks must end with identical (z, pocket, mask)."""
+    import os
+    import torch.multiprocessing as mp
+    port = 29600 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_atp_dist_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -80,3 +80,54 @@ def test_sampler_steps_match_reference(name, golden_weights):
     # the reference may re-project on CoG drift (:1432-1438); compare up to that projection
     ref_x = c['final_lig'][:, :3]
     assert np.abs(x - ref_x).max() < 5e-4 * scale
+
+
+INPAINT_CASES, _ = load_npz_groups('inpaint.npz')
+
+
+def _inpaint_inputs(c):
+    B, n_p = len(c['sizes']), len(c['pocket_x'])
+    oh = np.eye(10, dtype=np.float32)
+    return dict(lig_x=c['lig_x'], lig_onehot=oh[c['lig_t']], lig_mask=c['lig_mask'], pocket_x=np.tile(c['pocket_x'], (B, 1)),
+                pocket_onehot=np.tile(oh[c['pocket_t']], (B, 1)), pocket_mask=np.repeat(np.arange(B), n_p),
+                lig_fixed=c['lig_fixed'])
+
+
+@pytest.mark.parametrize('name', sorted(INPAINT_CASES))
+def test_inpaint_matches_reference(name, golden_weights):
+    """Free-running RePaint loop (conditional_model.py:1491-1790) with the reference's Gaussian draws injected."""
+    c = INPAINT_CASES[name]
+    a = _inpaint_inputs(c)
+    xh_l, xh_p, z0, xp0 = O.inpaint(golden_weights, a['lig_x'], a['lig_onehot'], a['lig_mask'], a['pocket_x'],
+                                    a['pocket_onehot'], a['pocket_mask'], a['lig_fixed'], c['noise'], int(c['timesteps']),
+                                    int(c['resamplings']), CFG)
+    scale = max(1.0, np.abs(c['z_final_in']).max())
+    assert np.abs(z0 - c['z_final_in']).max() < 2e-5 * scale
+    assert np.abs(xp0 - c['xp_final_in']).max() < 2e-5 * scale
+    assert np.array_equal(xh_l[:, 3:].argmax(1), c['final_lig'][:, 3:].argmax(1))
+    assert np.abs(xh_l[:, :3] - c['final_lig'][:, :3]).max() < 2e-5 * scale
+    assert np.abs(xh_p - c['final_pocket']).max() < 2e-5 * scale
+
+
+def test_inpaint_moves_are_com_free_and_keep_known_atoms():
+    """q(z_s|x) and the re-noising move project onto the ligand-COM-free subspace; with sigma -> 0 the blend returns the
+    (translated) input on the fixed atoms."""
+    rng = np.random.default_rng(5)
+    lm = np.repeat(np.arange(3), [4, 7, 5])
+    pm = np.repeat(np.arange(3), 6)
+    xh_l = rng.standard_normal((16, 13)).astype(np.float32)
+    xh_p = rng.standard_normal((18, 13)).astype(np.float32)
+    g = O.gamma_table()
+    z, xp = O.noised_representation(xh_l, xh_p, rng.standard_normal((16, 13)), g[[5, 100, 400]], lm, pm)
+    assert np.abs(O.segment_mean(z[:, :3], lm, 3)).max() < 1e-5
+    z2, xp2 = O.sample_p_zt_given_zs(z, xp, rng.standard_normal((16, 13)), g[[6, 101, 401]], g[[5, 100, 400]], lm, pm)
+    assert np.abs(O.segment_mean(z2[:, :3], lm, 3)).max() < 1e-5
+    # pocket and ligand are shifted by the same per-sample vector
+    d_l = O.segment_mean(z[:, :3] - np.sqrt(O.sigmoid(-g[[5, 100, 400]]))[lm][:, None] * xh_l[:, :3], lm, 3)
+    fixed = (rng.random(16) < 0.5).astype(np.float32)
+    fixed[[0, 4, 11]] = 1
+    zc, xpc = O.inpaint_combine(z, z2, xp, fixed, lm, pm, 3)
+    assert np.array_equal(zc[fixed == 0], z2[fixed == 0])
+    fx = fixed > 0
+    assert np.abs(O.segment_mean(zc[fx][:, :3], lm[fx], 3) - O.segment_mean(z2[fx][:, :3], lm[fx], 3)).max() < 1e-5
+    assert d_l.shape == (3, 3)

@@ -26,6 +26,15 @@ def _worker(rank, world, port, ret):
     # expected winners: candidates 1, 2 (tie broken by index), then 4
     exp = torch.cat([z_all[int(starts[c]):int(starts[c] + sizes_all[c])] for c in (1, 2, 4)])
     ok = torch.equal(z, exp) and s.tolist() == [7, 5, 3] and m.tolist() == [0] * 7 + [1] * 5 + [2] * 3
+    # fixed-width per-candidate payload (pocket translation + source sample) follows the winners; an empty rank is legal
+    pay_all = torch.arange(5 * 4, dtype=torch.float32).reshape(5, 4)
+    z2, m2, s2, pay = atp_select_distributed(scores_all[own], z_own, sizes_all[own], top_k=2, per_candidate=pay_all[own])
+    ok = ok and torch.equal(pay, pay_all[[1, 2]]) and s2.tolist() == [7, 5]
+    if rank == 0:
+        z3, m3, s3 = atp_select_distributed(scores_all, z_all, sizes_all, top_k=2)
+    else:
+        z3, m3, s3 = atp_select_distributed(scores_all[:0], z_all[:0], sizes_all[:0], top_k=2)
+    ok = ok and s3.tolist() == [7, 5] and torch.equal(z3, exp[:12])
     ok = ok and shard_pockets(7, rank, world) == list(range(rank, 7, world))
     ret[rank] = bool(ok)
     dist.barrier()
