@@ -34,6 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            '--use_fast_math' if os.environ.get('DNDM_FAST_MATH') else '-DDNDM_NO_FAST_MATH',
            '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static',
            '-o', LIB_PATH, os.path.join(CSRC, 'engine.cu')]
+    cmd[1:1] = os.environ.get('DNDM_EXTRA_NVCC_FLAGS', '').split()      # development switches (e.g. -DDNDM_EK_TRACE)
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

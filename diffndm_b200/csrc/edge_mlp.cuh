@@ -9,11 +9,16 @@
 //   HEAD: out[e] = range * tanh(w5 . m)                                       (coord / cross scalar heads)
 // remains.
 //
-// Persistent, warp-specialised CTA (640 threads, 1 CTA / SM, <= 96 registers per thread):
-//   warps 4-19  producers : gather + first-layer epilogue -> bf16 A tile in SWIZZLE_128B K-major smem (8 edges per
-//                           warp and tile, metadata prefetched a tile ahead); one elected lane issues the 16 tcgen05.mma
-//                           (M128 N256 K16) of the tile into TMEM accumulator (it & 1)
-//   warps 0-3   epilogue  : one thread per edge: tcgen05.ld -> m = SiLU(D) -> dot with the attention / head
+// Persistent, warp-specialised CTA (800 threads, 1 CTA / SM, <= 80 registers per thread):
+//   warps 8-23  producers : gather + first-layer epilogue -> bf16 A tile in SWIZZLE_128B K-major smem (8 edges per
+//                           warp and tile, metadata prefetched a tile ahead); each warp arrives on the `a_full`
+//                           mbarrier when its rows are written -- producers never wait for each other
+//   warp 24     MMA issuer: one lane waits for a_full and a drained accumulator, issues the 17 tcgen05.mma
+//                           (M128 N256 K16) of the tile into TMEM accumulator (it & 1) and commits to mma_done
+//   warps 0-7   epilogue  : every tile is drained by all eight warps -- warp w reads TMEM lane quarter w % 4 (32 edges)
+//                           and column half w / 4 (128 of the 256 channels), so the accumulator is free again after half
+//                           the time; per edge: tcgen05.ld -> m = SiLU(D) -> partial dot with the attention / head
+//                           weights (the two halves meet through shared memory and a 64-thread named barrier)
 //                           weights; GCL stages m (bf16) in a swizzled smem slab per warp and TMA-stores it to the
 //                           message buffer, plus att[e]; HEAD writes the scalar
 // The second-layer bias rides on the tensor core: a 17th K=16 MMA step multiplies a constant A slice (columns 0,1 = 1)
@@ -34,14 +39,15 @@ namespace dndm {
 
 constexpr int EK_TILE = 128;      // edges per tile (UMMA M)
 constexpr int EK_H = 256;         // hidden size (UMMA N and K)
-constexpr int EK_THREADS = 640;    // 4 epilogue + 16 producer warps, <= 96 registers each: latency hidden by warps
+constexpr int EK_THREADS = 800;    // 8 epilogue + 16 producer warps + 1 MMA-issue warp, <= 80 registers each
 constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
 constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
-constexpr int EK_SLAB_BYTES = 4 * 4096;                 // message staging, one [32 rows][128 B] SW128 slab per epilogue warp
+constexpr int EK_SLAB_BYTES = 8 * 2048;                 // message staging, one [32 rows][64 B] SW64 slab per epilogue warp
 constexpr int EK_AX_BYTES = EK_TILE * 16 * 2;           //   4096  bias step, A slice (no swizzle)
 constexpr int EK_BX_BYTES = EK_H * 16 * 2;              //   8192  bias step, B slice (no swizzle)
 constexpr int EK_META_BYTES = 16 * 2 * 8 * 16;          //   4096
-constexpr int EK_MISC_BYTES = EK_SLAB_BYTES + EK_AX_BYTES + EK_BX_BYTES + EK_META_BYTES + 256;
+constexpr int EK_DOT_BYTES = 2 * EK_TILE * 4;           //   1024  partial dot products of the upper column half, per accumulator
+constexpr int EK_MISC_BYTES = EK_SLAB_BYTES + EK_AX_BYTES + EK_BX_BYTES + EK_META_BYTES + EK_DOT_BYTES + 256;
 constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_MISC_BYTES;
 static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
 
@@ -120,14 +126,15 @@ DNDM_DEVICE void mbar_wait_park(uint64_t* bar, uint32_t parity) {
 // GCL additionally stages m as bf16 in this warp's shared-memory slab ([32 rows][64 columns], SWIZZLE_128B) and hands
 // every finished 64-column quarter to a TMA store into the message buffer.
 // `cc` must be one of the __grid_constant__ kernel parameters so that b2/wout become constant-bank operands.
-template <bool kGCL>
+template <bool kGCL, int kHalf>
 DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* slab, const CUtensorMap* tmap_msg, int row0,
                                int lane) {
     float dot = 0.f;
-    uint8_t* rowp = slab + lane * 128;
-    const uint32_t sw = lane & 7;
+    uint8_t* rowp = slab + lane * 64;                  // slab = [32 rows][32 bf16 = 64 B], SWIZZLE_64B
+    const uint32_t sw = (lane >> 1) & 3;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    for (int cc_ = 0; cc_ < 8; ++cc_) {
+        const int c = kHalf * 8 + cc_;                 // 16-column chunk of the 256 channels
         const int col0 = c * 16;
         uint32_t v[16];
         tmem_ld16(d_tmem + col0, v);
@@ -139,7 +146,7 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
             dot = fmaf(m[j], cc.wout[col0 + j], dot);
         }
         if (kGCL) {
-            if ((c & 3) == 0) {                        // slab reuse: the previous quarter's TMA store has read it
+            if ((c & 1) == 0) {                        // slab reuse: the previous 32-column TMA store has read it
                 if (lane == 0) tma_store_wait_read();
                 __syncwarp();
             }
@@ -148,14 +155,14 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
                 uint4 o;
                 o.x = pack_bf16x2(m[j], m[j + 1]);     o.y = pack_bf16x2(m[j + 2], m[j + 3]);
                 o.z = pack_bf16x2(m[j + 4], m[j + 5]); o.w = pack_bf16x2(m[j + 6], m[j + 7]);
-                const uint32_t unit = (c & 3) * 2 + (j >> 3);
+                const uint32_t unit = (c & 1) * 2 + (j >> 3);
                 *reinterpret_cast<uint4*>(rowp + ((unit ^ sw) << 4)) = o;
             }
-            if ((c & 3) == 3) {
+            if ((c & 1) == 1) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(tmap_msg, slab, (c >> 2) * 64, row0);
+                    tma_store_2d(tmap_msg, slab, (c >> 1) * 32, row0);
                     tma_store_commit();
                 }
             }
@@ -164,8 +171,20 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
     return dot;
 }
 
-constexpr int EK_EPI_WARPS = 4;                     // warps 0-3: epilogue (one TMEM lane quarter each)
-constexpr int EK_PROD_WARPS = 16;                   // warps 4-19: producers, 8 edges of every tile each
+#ifdef DNDM_EK_TRACE
+// Development aid (build with DNDM_EXTRA_NVCC_FLAGS=-DDNDM_EK_TRACE): clock64 stamps of CTA 0 of the GCL kernel,
+// [iteration][event], read back through dndm_debug_copy(what = 5).  See scripts/ek_timeline.py for the event list.
+__device__ unsigned long long g_ek_trace[64 * 16];
+#define EK_STAMP(it, ev)                                                                       \
+    do {                                                                                       \
+        if (kGCL && blockIdx.x == 0 && (it) < 64) g_ek_trace[(it) * 16 + (ev)] = clock64();   \
+    } while (0)
+#else
+#define EK_STAMP(it, ev) do {} while (0)
+#endif
+
+constexpr int EK_EPI_WARPS = 8;                     // warps 0-7: epilogue, column half = warp / 4, TMEM lane quarter = warp % 4
+constexpr int EK_PROD_WARPS = 16;                   // warps 8-23: producers, 8 edges of every tile each
 constexpr int EK_PROD_THREADS = EK_PROD_WARPS * 32;
 
 template <bool kGCL>
@@ -177,14 +196,16 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     uint8_t* sW = smem;
     uint8_t* sA = smem + EK_W2_BYTES;
     uint8_t* misc = smem + EK_W2_BYTES + EK_A_BYTES;
-    uint8_t* sSlab = misc;                                       // [4 epilogue warps][32 rows][128 B] message staging
+    uint8_t* sSlab = misc;                                       // [8 epilogue warps][32 rows][64 B] message staging
     uint8_t* sAx = misc + EK_SLAB_BYTES;                         // bias step A slice: [16 row groups][2 k cores][8 rows][16 B]
     uint8_t* sBx = sAx + EK_AX_BYTES;                            // bias step B slice: [32 row groups][2 k cores][8 rows][16 B]
     int4* sMeta = reinterpret_cast<int4*>(sBx + EK_BX_BYTES);    // [16 producer warps][2 slots][8 edges]
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(sBx + EK_BX_BYTES + EK_META_BYTES);
+    float* sDot = reinterpret_cast<float*>(sBx + EK_BX_BYTES + EK_META_BYTES);   // [2 accumulators][128 rows]
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(sBx + EK_BX_BYTES + EK_META_BYTES + EK_DOT_BYTES);
     uint64_t* mma_done = w_bar + 1;                              // [2]
     uint64_t* tmem_empty = mma_done + 2;                         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* a_full = tmem_empty + 2;                           // A tile of the current iteration completely written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
 
     const bool second = (blockIdx.y != 0);
     const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
@@ -202,6 +223,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         mbar_init(&mma_done[1], 1);
         mbar_init(&tmem_empty[0], EK_EPI_WARPS * 32);
         mbar_init(&tmem_empty[1], EK_EPI_WARPS * 32);
+        mbar_init(a_full, EK_PROD_WARPS);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -230,15 +252,41 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= EK_EPI_WARPS) {
-        // =========================== producers (+ MMA issue) ===========================
-        const int pw = warp - EK_EPI_WARPS;
-        const bool issuer = (tid == EK_EPI_WARPS * 32);
-        if (issuer && (int)blockIdx.x < num_tiles) {
+    if (warp == EK_EPI_WARPS + EK_PROD_WARPS) {
+        // =========================== MMA issuer (one lane) ===========================
+        if (lane == 0 && (int)blockIdx.x < num_tiles) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(EK_TILE, EK_H);
             mbar_arrive_expect_tx(w_bar, EK_W2_BYTES);
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW);
+            const uint64_t ax = make_kmajor_noswz_desc(smem_u32(sAx), 128, 256), bx = make_kmajor_noswz_desc(smem_u32(sBx), 128, 256);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait_park(a_full, it & 1);                                       // all 16 producer warps wrote their rows
+                if (it >= 2) mbar_wait_park(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained by the epilogue
+                EK_STAMP(it, 5);
+                tc_fence_after_sync();
+                if (it == 0) mbar_wait(w_bar, 0);
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_bf16(d_tmem, make_kmajor_sw128_desc(a0 + kk * 16384 + k * 32),
+                                  make_kmajor_sw128_desc(b0 + kk * 32768 + k * 32), idesc, (kk | k) != 0);
+                    }
+                }
+                umma_bf16(d_tmem, ax, bx, idesc, 1u);                                 // + b2
+                umma_commit(&mma_done[buf]);
+                EK_STAMP(it, 6);
+            }
         }
+        __syncwarp();
+    } else if (warp >= EK_EPI_WARPS) {
+        // =========================== producers ===========================
+        const int pw = warp - EK_EPI_WARPS;
         // lane owns k = 8*lane .. 8*lane+7 of the (halved) first-layer pre-activation: one 16-byte bf16 unit
         float wr[8], w0[8];
         {
@@ -256,7 +304,6 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             w02[i] = pack_bf16x2(w0[2 * i], w0[2 * i + 1]);
         }
         constexpr bool kPacked = kGCL;               // bf16x2 producer arithmetic; the coordinate heads stay fp32 (measured: packed doubles the x error)
-        constexpr uint32_t idesc = make_idesc_bf16_f32(EK_TILE, EK_H);
         const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
         const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
         const uint32_t ld4 = (uint32_t)g.ldpq / 8;
@@ -340,57 +387,58 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1, slot = it & 1;
+            if (lane == 0 && pw == 0) EK_STAMP(it, 0);
+            if (lane == 0 && pw == 15) EK_STAMP(it, 9);
             meta_l2(m_next, slot ^ 1);                                           // next tile's metadata -> other slot
             m_next = meta_l1(tile + 2 * gridDim.x);                              // level-1 loads two tiles ahead
             compute4(slot, 0, [&] {
+                if (lane == 0 && pw == 0) EK_STAMP(it, 1);
                 if (it >= 1) mbar_wait_park(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);   // A smem free again
+                if (lane == 0 && pw == 0) EK_STAMP(it, 2);
             });
             compute4(slot, 1, [] {});
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            named_bar_sync(1, EK_PROD_THREADS);       // all producer warps have written their rows of A
-            if (issuer) {
-                if (it >= 2) mbar_wait_park(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained by the epilogue
-                tc_fence_after_sync();
-                if (it == 0) mbar_wait(w_bar, 0);
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H;
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_bf16(d_tmem, make_kmajor_sw128_desc(a0 + kk * 16384 + k * 32),
-                                  make_kmajor_sw128_desc(b0 + kk * 32768 + k * 32), idesc, (kk | k) != 0);
-                    }
-                }
-                umma_bf16(d_tmem, make_kmajor_noswz_desc(smem_u32(sAx), 128, 256), make_kmajor_noswz_desc(smem_u32(sBx), 128, 256),
-                          idesc, 1u);                                               // + b2
-                umma_commit(&mma_done[buf]);
-            }
-            __syncwarp();   // re-converge the issuing lane: without it the warp stays split for the whole next tile
+            if (lane == 0 && pw == 0) EK_STAMP(it, 3);
+            if (lane == 0 && pw == 15) EK_STAMP(it, 10);
+            fence_proxy_async_smem();                 // this thread's rows are visible to the tensor core's proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+            if (lane == 0 && pw == 0) EK_STAMP(it, 4);
         }
     } else {
-        // =========================== epilogue (warps 0-3, one thread per edge of the tile) ===========================
-        const int q = warp;                // TMEM lane quarter
+        // ============ epilogue (warps 0-7: TMEM lane quarter q = warp % 4, column half hf = warp / 4) ============
+        const int hf = warp >> 2;
+        const int q = warp & 3;
         const int trow = q * 32 + lane;
+        uint8_t* slab = sSlab + warp * 2048;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const int e = tile * EK_TILE + trow;
             const bool valid = e < E;
             mbar_wait_park(&mma_done[buf], (it >> 1) & 1);
+            if (lane == 0 && warp == 0) EK_STAMP(it, 7);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H + ((uint32_t)(q * 32) << 16);
-            uint8_t* slab = sSlab + q * 4096;
             const int row0 = tile * EK_TILE + q * 32;
-            const float dot = second ? epilogue_row<kGCL>(c1, d_tmem, slab, &tmap_msg, row0, lane)
-                                     : epilogue_row<kGCL>(c0, d_tmem, slab, &tmap_msg, row0, lane);
+            float dot;
+            if (hf) {
+                dot = second ? epilogue_row<kGCL, 1>(c1, d_tmem, slab, &tmap_msg, row0, lane)
+                             : epilogue_row<kGCL, 1>(c0, d_tmem, slab, &tmap_msg, row0, lane);
+                sDot[buf * EK_TILE + trow] = dot;
+                asm volatile("bar.arrive %0, %1;" ::"r"(2 + q), "r"(64) : "memory");   // partial published to the lower-half warp
+            } else {
+                dot = second ? epilogue_row<kGCL, 0>(c1, d_tmem, slab, &tmap_msg, row0, lane)
+                             : epilogue_row<kGCL, 0>(c0, d_tmem, slab, &tmap_msg, row0, lane);
+                named_bar_sync(2 + q, 64);
+                dot += sDot[buf * EK_TILE + trow];
+                if (valid) {
+                    if (kGCL) g.att[e] = sigmoid_fast(dot + pr.bout) * pr.out_scale;
+                    else pr.head_out[e] = pr.out_scale * tanhf(dot);
+                }
+            }
+            if (lane == 0 && warp == 0) EK_STAMP(it, 8);
             tc_fence_before_sync();
             mbar_arrive(&tmem_empty[buf]);             // accumulator drained: the MMA of tile it+2 may overwrite it
-            if (valid) {
-                if (kGCL) g.att[e] = sigmoid_fast(dot + pr.bout) * pr.out_scale;
-                else pr.head_out[e] = pr.out_scale * tanhf(dot);
-            }
         }
     }
     if (kGCL && warp < EK_EPI_WARPS && lane == 0) tma_store_wait_all();   // message writes complete before exit

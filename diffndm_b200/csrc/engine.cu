@@ -222,7 +222,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(make_tmap_bf16(&e->to_hid, e->hid, N, 256, 256, 32));
     RET_IF(make_tmap_bf16(&e->to_hcat, e->hcat, N, 512, 512, 32));
     RET_IF(make_tmap_f32_out(&e->to_h, e->h, N, 256, 256));
-    RET_IF(make_tmap_bf16(&e->to_msg, e->msg, E + 128, 256, 256, 32));
+    RET_IF(make_tmap_bf16_box(&e->to_msg, e->msg, E + 128, 256, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_pq32, e->pq, N, 1536, 1536, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_hcat32, e->hcat, N, 512, 512, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
@@ -768,6 +768,13 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
             break;
         }
         case 4: src = e->scalars; bytes = 16; break;
+#ifdef DNDM_EK_TRACE
+        case 5: {
+            bytes = sizeof(g_ek_trace) < (size_t)dst_bytes ? sizeof(g_ek_trace) : dst_bytes;
+            CU_CHECK(cudaMemcpyFromSymbolAsync(dst, g_ek_trace, bytes, 0, cudaMemcpyDeviceToDevice, st));
+            return bytes;
+        }
+#endif
         default: return set_err(DNDM_EINVAL, "unknown buffer id %d", what);
     }
     if (bytes > dst_bytes) bytes = dst_bytes;
