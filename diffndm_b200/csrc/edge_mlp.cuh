@@ -425,11 +425,13 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
                 dot = second ? epilogue_row<kGCL, 1>(c1, d_tmem, slab, &tmap_msg, row0, lane)
                              : epilogue_row<kGCL, 1>(c0, d_tmem, slab, &tmap_msg, row0, lane);
                 sDot[buf * EK_TILE + trow] = dot;
-                asm volatile("bar.arrive %0, %1;" ::"r"(2 + q), "r"(64) : "memory");   // partial published to the lower-half warp
+                // partial published to the lower-half warp.  The barrier id alternates with the accumulator: this warp may
+                // run one tile ahead of its partner, and two arrivals on ONE barrier would complete it without the partner.
+                asm volatile("bar.arrive %0, %1;" ::"r"(2 + 2 * q + buf), "r"(64) : "memory");
             } else {
                 dot = second ? epilogue_row<kGCL, 0>(c1, d_tmem, slab, &tmap_msg, row0, lane)
                              : epilogue_row<kGCL, 0>(c0, d_tmem, slab, &tmap_msg, row0, lane);
-                named_bar_sync(2 + q, 64);
+                named_bar_sync(2 + 2 * q + buf, 64);
                 dot += sDot[buf * EK_TILE + trow];
                 if (valid) {
                     if (kGCL) g.att[e] = sigmoid_fast(dot + pr.bout) * pr.out_scale;
