@@ -131,46 +131,87 @@ def workload_config(batch):
 # clocks
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 10 ms from a thread (the timed
+    region can be shorter than nvidia-smi's start-up), with the nvidia-smi loop of the profiling recipe as fallback."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
+        self.samples = []          # (time, sm_mhz, set(reasons))
+        self.smax = None
+        self.stop_flag = False
         self.proc = None
-        self.lines = []
+        self.mode = None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = gpu_index
+            if vis and all(v.strip().isdigit() for v in vis.split(',')):
+                idx = int(vis.split(',')[gpu_index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = 'nvml'
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20',
                                           '-i', str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.mode = 'smi'
+            self.th = threading.Thread(target=self._read_smi, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for l in self.proc.stdout:
-            self.lines.append((time.time(), l.strip()))
+    def _poll_nvml(self):
+        nv = self.nv
+        bits = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(self.h))
+                self.samples.append((time.time(), mhz, {n for n, b in bits.items() if r & b}))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
+    def _read_smi(self):
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ts, l in self.lines:
-            p = [x.strip() for x in l.split(',')]
+        for l in self.proc.stdout:
+            p = [x.strip() for x in l.strip().split(',')]
             if len(p) < 7:
                 continue
             try:
-                smax = float(p[1])
-                if t0 - 0.05 <= ts <= t1 + 0.15:
-                    sm.append(float(p[0]))
-                    for n, v in zip(names, p[3:7]):
-                        if v.lower().startswith('active'):
-                            reasons.add(n)
+                self.smax = float(p[1])
+                self.samples.append((time.time(), float(p[0]),
+                                     {n for n, v in zip(names, p[3:7]) if v.lower().startswith('active')}))
             except ValueError:
                 continue
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+
+    def stop(self, t0, t1):
+        if self.mode is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml and nvidia-smi unavailable'], 'samples': 0}
+        time.sleep(0.05)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, reasons = [], set()
+        for ts, mhz, rs in self.samples:
+            if t0 <= ts <= t1:
+                sm.append(mhz)
+                reasons |= rs
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.smax, 'reasons': sorted(reasons),
+                'samples': len(sm), 'source': self.mode}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -320,9 +361,9 @@ def run_b200(args):
         achieved = edges_timed * EXEC_FLOP_PER_EDGE_GCL / (g_ms * 1e-3) / 1e12
         # DRAM traffic of the kernel from the committed `ncu --set full` capture of this exact workload
         # (profiles/r1_edge_kernel_ncu_raw.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch); other batch sizes: null
-        traffic = (47.57e6 + 284.61e6) * (edges_timed / max(g_n, 1)) / 615e3 if (B == 100 and POCKET_ATOMS == 330) else None
+        traffic = (47.63e6 + 287.92e6) * (edges_timed / max(g_n, 1)) / 613e3 if (B == 100 and POCKET_ATOMS == 330) else None
         roof = {'bound': 'tensor', 'kernel': 'edge_mlp_kernel<GCL>', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': 'profiles/r1_edge_kernel_ncu_raw.txt (332 MB at 615k edges, scaled to the mean edges per launch)',
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': 'profiles/r1_edge_kernel_ncu_raw.txt (335.5 MB at 613k edges, scaled to the mean edges per launch)',
                 'peak_source': peak_src,
                 'us_per_launch': t_launch * 1e6, 'edges_per_launch': edges_timed / max(g_n, 1), 'edges': E_edges,
                 'edges_last_block': E_last,
