@@ -133,7 +133,7 @@ struct DndmEngine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     CUtensorMap tm_hcat, tm_hid;
     CUtensorMap to_pq, to_hid, to_hcat, to_h;
-    CUtensorMap to_pq32, to_hcat32;              // 32-column bf16 boxes (SWIZZLE_64B) for the weight-resident GEMM
+    CUtensorMap to_pq32, to_hcat32, to_hid32;    // 32-column bf16 boxes (SWIZZLE_64B) for the weight-resident GEMM
     CUtensorMap to_msg;                          // TMA-store destination of the edge messages (box 32 rows x 64 cols)   // TMA-store destinations of the node GEMMs (32-row boxes)
     // weights
     std::vector<LayerWeights> layers;
@@ -233,7 +233,9 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(make_tmap_bf16_box(&e->to_msg, e->msg, E + 128, 256, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_pq32, e->pq, N, 1536, 1536, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_hcat32, e->hcat, N, 512, 512, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
+    RET_IF(make_tmap_bf16_box(&e->to_hid32, e->hid, N, 256, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
@@ -490,6 +492,7 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
 }
 
 // n_full column groups over M rows followed by n_tail groups over the first M_tail rows (see gemm_wres_kernel)
+template <int kK = 256, int kBN = 256>
 static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to16, int M,
                        int n_full, int g0, int a_col0, const WresEpilogue& ep, int n_tail = 0, int M_tail = 0) {
     if (M <= 0) return DNDM_OK;
@@ -506,7 +509,7 @@ static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
     if (ctas_full < 1) ctas_full = 1;
     if (ctas_full > m_tiles) ctas_full = m_tiles;
     const int grid = n_full * ctas_full + n_tail * ctas_tail;
-    gemm_wres_kernel<<<grid, WR_THREADS, WR_SMEM_BYTES, st>>>(ta, tw, to16, M, M_tail, a_col0, g0, n_full, ctas_full,
+    gemm_wres_kernel<kK, kBN><<<grid, WR_THREADS, WR_SMEM_BYTES, st>>>(ta, tw, to16, M, M_tail, a_col0, g0, n_full, ctas_full,
                                                               ctas_tail > 0 ? ctas_tail : 1, ep);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
@@ -655,8 +658,8 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         // ---- node MLP with residual ----
         {
             ProfScope ps(e, PROF_GEMM, st);
-            GemmEpilogue ep1{L.b3, 1, nullptr, 0, 0, 0, 1, 0};
-            RET_IF(launch_gemm(st, e->tm_hcat, L.tm_w3, e->to_hid, e->to_h, N, 256, 512, 0, ep1));
+            WresEpilogue ep1{L.b3, nullptr, 0, nullptr, 0, 0, 1, 0, 1};          // hid = SiLU(W3 [h | agg] + b3), K = 512
+            RET_IF((launch_wres<512, 128>(st, e->tm_hcat, L.tm_w3, e->to_hid32, N, 2, 0, 0, ep1)));
             WresEpilogue ep2{L.b4, e->h, 256, e->h, 256, 0, 1, 0};       // h += W4 hid + b4 ; bf16 copy -> hcat[:, :256]
             RET_IF(launch_wres(st, e->tm_hid, L.tm_w4r, e->to_hcat32, N, 1, 0, 0, ep2));
         }

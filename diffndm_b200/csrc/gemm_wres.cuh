@@ -1,15 +1,15 @@
-// Weight-resident node GEMM for K = 256:   C[M, 256*G] = epilogue( A[M,256] (bf16) x W[256*G, 256]^T (bf16) )
+// Weight-resident node GEMM:   C[M, BN*G] = epilogue( A[M,K] (bf16) x W[BN*G, K]^T (bf16) ),  (K, BN) = (256, 256) or (512, 128)
 //
-// A CTA owns one 256-column group of W -- 128 KiB, TMA-loaded once and resident for the CTA's lifetime, exactly like W2
-// in the edge kernel -- and streams the A row blocks assigned to it through a 4-stage ring (one full 128 x 256 row block
-// of prefetch).  The accumulator drain is a pure latency chain (tcgen05.ld -> bias/residual -> cvt -> st.shared -> fence
+// A CTA owns one BN-column group of W -- BN x K bf16 = 128 KiB, TMA-loaded once and resident for the CTA's lifetime,
+// exactly like W2 in the edge kernel -- and streams the A row blocks assigned to it through a 4-stage ring of 128 x 64
+// k-blocks.  The accumulator drain is a pure latency chain (tcgen05.ld -> bias/residual -> cvt -> st.shared -> fence
 // -> TMA store, ~1000 cycles per 32-column chunk for one warp; ncu: profiles/r1_wres_*), so it is spread over
 // 4 * WR_EPI_SPLIT epilogue warps: each TMEM lane quarter is served by WR_EPI_SPLIT warps that split the 256 columns.
 //
 // Persistent, warp-specialised (1 CTA / SM, grid = (ceil(#SMs / G), G)):
 //   warp 0     TMA producer : W group once; A tiles (128 x 64 bf16, SWIZZLE_128B) into the ring
-//   warp 1     MMA issuer   : 16 x tcgen05.mma M128 N256 K16 per row block into one of two TMEM accumulators (2 x 256)
-//   warps 2..  epilogue     : tcgen05.ld (32 columns at a time) -> bias / residual -> fp32 rows straight to global
+//   warp 1     MMA issuer   : K/16 x tcgen05.mma M128 N=BN K16 per row block into one of two TMEM accumulators (2 x BN)
+//   warps 2..  epilogue     : tcgen05.ld (32 columns at a time) -> bias / residual / SiLU -> fp32 rows straight to global
 //                             (each thread owns one row: full 128-byte runs) and/or bf16 through a swizzled smem slab
 //                             and a TMA store; no block-level barrier
 #pragma once
@@ -18,15 +18,12 @@
 namespace dndm {
 
 constexpr int WR_BM = 128;
-constexpr int WR_BN = 256;
-constexpr int WR_K = 256;
 constexpr int WR_STAGES = 4;
 constexpr int WR_EPI_SPLIT = 4;                               // epilogue warps per TMEM lane quarter (2 or 4)
 constexpr int WR_EPI_WARPS = 4 * WR_EPI_SPLIT;
 constexpr int WR_THREADS = 64 + 32 * WR_EPI_WARPS;
-constexpr int WR_CHUNKS = WR_BN / 32 / WR_EPI_SPLIT;          // 32-column chunks per epilogue warp and row block
-constexpr int WR_NSLAB = WR_EPI_SPLIT == 2 ? 2 : 1;           // bf16 slabs per warp (double-buffered when a warp has 4 chunks)
-constexpr int WR_W_BYTES = WR_BN * WR_K * 2;                 // 131072
+constexpr int WR_NSLAB = 1;                                   // bf16 slabs per epilogue warp
+constexpr int WR_W_BYTES = 131072;                            // BN x K bf16 for both supported shapes
 constexpr int WR_STAGE_BYTES = WR_BM * 64 * 2;               //  16384  (128 rows x 64 k)
 constexpr int WR_SLAB16_BYTES = 32 * 32 * 2;                 //   2048  [32 rows][32 bf16], SWIZZLE_64B
 constexpr int WR_OUT_BYTES = WR_EPI_WARPS * WR_NSLAB * WR_SLAB16_BYTES;
@@ -42,14 +39,20 @@ struct WresEpilogue {
     int col0_f32;
     int has_bf16;             // store bf16 through tmap_o16 at column offset col0_bf16
     int col0_bf16;
+    int act;                  // 1: SiLU
 };
 
+template <int kK, int kBN>
 __global__ void __launch_bounds__(WR_THREADS, 1)
 gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_o16, int M, int M_tail, int a_col0, int g0, int n_full,
                  int ctas_full, int ctas_tail, WresEpilogue ep) {
+    static_assert(kK * kBN * 2 == WR_W_BYTES && (kBN == 256 || kBN == 128), "unsupported shape");
+    constexpr int WR_BN = kBN;
+    constexpr int KB = kK / 64;                                   // 64-column k-blocks per row block
+    constexpr int WR_CHUNKS = kBN / 32 / WR_EPI_SPLIT;            // 32-column chunks per epilogue warp and row block
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sW = smem;                                           // [4 k-chunks][256 rows][128 B]
+    uint8_t* sW = smem;                                           // [KB k-chunks][BN rows][128 B]
     uint8_t* sA = smem + WR_W_BYTES;                              // ring of [128 rows][128 B]
     uint8_t* sOut = sA + WR_STAGES * WR_STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + WR_OUT_BYTES);
@@ -102,14 +105,14 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (elect_one() && has_work) {
             mbar_arrive_expect_tx(w_bar, WR_W_BYTES);
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, &tmap_w, w_bar, kc * 64, grp * WR_BN);
+            for (int kc = 0; kc < KB; ++kc) tma_load_2d(sW + kc * (WR_BN * 128), &tmap_w, w_bar, kc * 64, grp * WR_BN);
             int kq = 0;
             for (int m_blk = cta_rank; m_blk < m_tiles; m_blk += cta_stride) {
                 if (ep.residual && ep.ldr == WR_BN) {             // the row block of the fp32 residual is one contiguous range
                     const int rows = min(WR_BM, M - m_blk * WR_BM);
                     bulk_prefetch_l2(ep.residual + (size_t)m_blk * WR_BM * WR_BN, (uint32_t)rows * WR_BN * 4);
                 }
-                for (int kb = 0; kb < 4; ++kb, ++kq) {
+                for (int kb = 0; kb < KB; ++kb, ++kq) {
                     const int s = kq % WR_STAGES;
                     const uint32_t ph = (kq / WR_STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
@@ -129,13 +132,13 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (it >= 2) mbar_wait(&acc_empty[buf], ((it - 2) >> 1) & 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + buf * WR_BN;
-                for (int kb = 0; kb < 4; ++kb, ++kq) {
+                for (int kb = 0; kb < KB; ++kb, ++kq) {
                     const int s = kq % WR_STAGES;
                     const uint32_t ph = (kq / WR_STAGES) & 1;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after_sync();
                     const uint32_t sa = smem_u32(sA + s * WR_STAGE_BYTES);
-                    const uint32_t sb = smem_u32(sW + kb * 32768);
+                    const uint32_t sb = smem_u32(sW + kb * (WR_BN * 128));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(d_tmem, make_kmajor_sw128_desc(sa + k * 32), make_kmajor_sw128_desc(sb + k * 32), idesc,
@@ -193,6 +196,10 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+                if (ep.act) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+                }
                 if (ep.out_f32 && row_ok) {
                     float* op = ep.out_f32 + grow * ep.ld_f32 + ep.col0_f32 + col0;
 #pragma unroll
