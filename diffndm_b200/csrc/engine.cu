@@ -236,6 +236,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(make_tmap_bf16_box(&e->to_hid32, e->hid, N, 256, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
@@ -661,7 +662,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             WresEpilogue ep1{L.b3, nullptr, 0, nullptr, 0, 0, 1, 0, 1};          // hid = SiLU(W3 [h | agg] + b3), K = 512
             RET_IF((launch_wres<512, 128>(st, e->tm_hcat, L.tm_w3, e->to_hid32, N, 2, 0, 0, ep1)));
             WresEpilogue ep2{L.b4, e->h, 256, e->h, 256, 0, 1, 0};       // h += W4 hid + b4 ; bf16 copy -> hcat[:, :256]
-            RET_IF(launch_wres(st, e->tm_hid, L.tm_w4r, e->to_hcat32, N, 1, 0, 0, ep2));
+            RET_IF((launch_wres<256, 128>(st, e->tm_hid, L.tm_w4, e->to_hcat32, N, 2, 0, 0, ep2)));
         }
         // ---- node projections: this block's coordinate heads (sender parts for every node, receiver parts for the
         //      ligand rows) and the next block's edge model, one weight-resident GEMM over the new h ----

@@ -23,7 +23,7 @@ constexpr int WR_EPI_SPLIT = 4;                               // epilogue warps 
 constexpr int WR_EPI_WARPS = 4 * WR_EPI_SPLIT;
 constexpr int WR_THREADS = 64 + 32 * WR_EPI_WARPS;
 constexpr int WR_NSLAB = 1;                                   // bf16 slabs per epilogue warp
-constexpr int WR_W_BYTES = 131072;                            // BN x K bf16 for both supported shapes
+constexpr int WR_W_BYTES = 131072;                            // BN x K bf16 of the largest supported shapes
 constexpr int WR_STAGE_BYTES = WR_BM * 64 * 2;               //  16384  (128 rows x 64 k)
 constexpr int WR_SLAB16_BYTES = 32 * 32 * 2;                 //   2048  [32 rows][32 bf16], SWIZZLE_64B
 constexpr int WR_OUT_BYTES = WR_EPI_WARPS * WR_NSLAB * WR_SLAB16_BYTES;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(WR_THREADS, 1)
 gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_o16, int M, int M_tail, int a_col0, int g0, int n_full,
                  int ctas_full, int ctas_tail, WresEpilogue ep) {
-    static_assert(kK * kBN * 2 == WR_W_BYTES && (kBN == 256 || kBN == 128), "unsupported shape");
+    static_assert(kK * kBN * 2 <= WR_W_BYTES && (kBN == 256 || kBN == 128), "unsupported shape");
     constexpr int WR_BN = kBN;
     constexpr int KB = kK / 64;                                   // 64-column k-blocks per row block
     constexpr int WR_CHUNKS = kBN / 32 / WR_EPI_SPLIT;            // 32-column chunks per epilogue warp and row block
@@ -103,14 +103,14 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     if (warp == 0) {
         if (elect_one() && has_work) {
-            mbar_arrive_expect_tx(w_bar, WR_W_BYTES);
+            mbar_arrive_expect_tx(w_bar, kK * kBN * 2);
 #pragma unroll
             for (int kc = 0; kc < KB; ++kc) tma_load_2d(sW + kc * (WR_BN * 128), &tmap_w, w_bar, kc * 64, grp * WR_BN);
             int kq = 0;
             for (int m_blk = cta_rank; m_blk < m_tiles; m_blk += cta_stride) {
-                if (ep.residual && ep.ldr == WR_BN) {             // the row block of the fp32 residual is one contiguous range
+                if (ep.residual && ep.ldr == 256 && (kBN == 256 || grp == g0)) {   // fp32 residual rows of the block: contiguous
                     const int rows = min(WR_BM, M - m_blk * WR_BM);
-                    bulk_prefetch_l2(ep.residual + (size_t)m_blk * WR_BM * WR_BN, (uint32_t)rows * WR_BN * 4);
+                    bulk_prefetch_l2(ep.residual + (size_t)m_blk * WR_BM * 256, (uint32_t)rows * 256 * 4);
                 }
                 for (int kb = 0; kb < KB; ++kb, ++kq) {
                     const int s = kq % WR_STAGES;
