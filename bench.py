@@ -241,6 +241,7 @@ def run_b200(args):
                              max_samples=B, check_nan=False)
     dyn.compute_pocket_output = False            # every conditional caller discards it (`eps, _ =`)
     eng = dyn.engine
+    eng.set_static_masks(True)      # the masks of a trajectory are fixed tensors (as in ConditionalSampler.sample_given_pocket)
     smp = ConditionalSampler(dyn, timesteps=T_STEPS)
 
     # per-step scalars for every s (device tables): t, coefficients

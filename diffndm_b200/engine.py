@@ -28,7 +28,7 @@ FLAG_EDGE_OVERFLOW = 4
 EXPORTED_SYMBOLS = [
     'dndm_version', 'dndm_last_error', 'dndm_launch_count', 'dndm_engine_create', 'dndm_engine_destroy', 'dndm_engine_load_weights',
     'dndm_egnn_forward', 'dndm_radius_graph', 'dndm_sampler_step', 'dndm_read_flags', 'dndm_debug_copy',
-    'dndm_set_trace', 'dndm_set_profile', 'dndm_get_profile', 'dndm_test_gemm',
+    'dndm_set_trace', 'dndm_set_profile', 'dndm_get_profile', 'dndm_set_static_masks', 'dndm_test_gemm',
 ]
 
 
@@ -77,6 +77,7 @@ def load_library() -> ctypes.CDLL:
     lib.dndm_debug_copy.restype = i64
     lib.dndm_set_trace.argtypes = [vp, vp, vp, i32]
     lib.dndm_set_profile.argtypes = [vp, i32]
+    lib.dndm_set_static_masks.argtypes = [vp, i32]
     lib.dndm_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32), i32]
     lib.dndm_test_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     _lib = lib
@@ -229,6 +230,11 @@ class Engine:
         self.lib.dndm_set_trace(self._h, None, None, 0)
 
     PROFILE_CATEGORIES = ('gcl_edge_kernel', 'head_edge_kernel', 'node_gemm', 'radius_graph', 'node_other')
+
+    def set_static_masks(self, on: bool):
+        """Promise that mask tensors passed again (same storage, same sizes) still hold the same values; the engine then
+        skips re-deriving the per-sample offsets.  Turn it off (or toggle it) whenever a mask tensor is rewritten."""
+        _check(self.lib, self.lib.dndm_set_static_masks(self._h, int(bool(on))), 'dndm_set_static_masks')
 
     def set_profile(self, on: bool):
         _check(self.lib, self.lib.dndm_set_profile(self._h, int(on)), 'dndm_set_profile')

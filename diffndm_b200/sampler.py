@@ -230,6 +230,7 @@ class ConditionalSampler:
         z_lig, xh_pocket = self.engine.sampler_step(mu, None, self._noise(n_l, None if noise is None else noise[0]),
                                                     xh0_pocket, ident, lig_mask, pocket_mask, B)
         step = 0
+        self.engine.set_static_masks(True)          # lig_mask / pocket_mask are fixed tensors between ATP events
         for s in reversed(range(0, timesteps)):
             s_array = torch.full((B, 1), fill_value=s, dtype=torch.float32) / timesteps
             t_array = torch.full((B, 1), fill_value=s + 1, dtype=torch.float32) / timesteps
@@ -237,9 +238,11 @@ class ConditionalSampler:
             z_lig, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
                                                          noise=None if noise is None else noise[step], n_samples=B)
             if svdd == 1 and s <= svdd_schedule[0] and s % svdd_schedule[1] == 0:
+                self.engine.set_static_masks(False)     # candidate batches use other masks; the winners get a new one
                 z_lig, xh_pocket, lig_mask = self._atp_event(s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
                                                              B, reward_fn, svdd_groups)
                 z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+                self.engine.set_static_masks(True)
             if spsa == 1 and s <= spsa_schedule[0] and s % spsa_schedule[1] == 0:
                 zeta = 1e-3 * (s / 500)                                                   # :1244-1245
                 z_lig, xh_pocket = self.my_update_z_lig(z_lig, xh_pocket, lig_mask, pocket_mask, t_array, B, zeta,
@@ -247,6 +250,7 @@ class ConditionalSampler:
                 z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
         x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(
             z_lig, xh_pocket, lig_mask, pocket_mask, B, noise=None if noise is None else noise[timesteps + 1])
+        self.engine.set_static_masks(False)
         self._raise_on_flags()
         # CoG drift correction (:1431-1438)
         cog = torch.zeros((B, 3), device=dev).index_add_(0, lig_mask, x_lig).abs().max().item()

@@ -122,6 +122,12 @@ int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64_t dst_byte
  * Categories: 0 fused GCL edge kernel, 1 fused coordinate-head edge kernel, 2 node GEMMs, 3 radius graph,
  * 4 remaining node kernels. */
 int dndm_set_profile(DndmEngine* e, int32_t on);
+
+/* Static batch layout.  Every entry point derives the per-sample offsets from the int64 masks (two small launches).
+ * While `on` != 0 the caller promises that the CONTENTS of the mask buffers do not change between calls that pass the
+ * same pointers and sizes (the sampling loop: utils.py:145-153 masks are built once per trajectory), and the engine
+ * skips that derivation when pointers and sizes repeat.  Switching the option (either way) drops the cached layout. */
+int dndm_set_static_masks(DndmEngine* e, int32_t on);
 int dndm_get_profile(DndmEngine* e, double* ms_per_category, int32_t* launches_per_category, int32_t n_cat);
 
 /* Trace hook for parity tests: when set (DEVICE, [n_layers, max_trace_nodes, 256] fp32 and

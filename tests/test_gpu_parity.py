@@ -205,6 +205,36 @@ def test_forward_se3_equivariance(dyn, dev):
     assert np.abs(a[:, 3:] - b[:, 3:]).max() < H_REL_TOL * np.abs(a[:, 3:]).max()
 
 
+def test_static_mask_layout_cache(dyn, dev):
+    """dndm_set_static_masks: repeated calls with the same mask tensors skip the offset derivation and give the same
+    result; other tensors (different storage) are picked up; toggling drops the cache."""
+    from diffndm_b200 import synthetic
+    px, pt = synthetic.synthetic_pocket(5, 64)
+    b1 = synthetic.make_batch(px, pt, np.array([9, 4, 14]), 1)
+    b2 = synthetic.make_batch(px, pt, np.array([6, 11]), 2)
+    def run(b, lm, pm):
+        B = int(lm.max().item()) + 1
+        out, _ = dyn(_t(b['xh_lig'], dev), _t(b['xh_pocket'], dev), torch.full((B, 1), 0.3, device=dev), lm, pm, n_samples=B)
+        return out.clone()
+    lm1, pm1 = _t(b1['lig_mask'], dev), _t(b1['pocket_mask'], dev)
+    lm2, pm2 = _t(b2['lig_mask'], dev), _t(b2['pocket_mask'], dev)
+    ref1, ref2 = run(b1, lm1, pm1), run(b2, lm2, pm2)
+    n0 = dyn.engine.lib.dndm_launch_count()
+    run(b1, lm1, pm1)
+    per_call = dyn.engine.lib.dndm_launch_count() - n0
+    dyn.engine.set_static_masks(True)
+    try:
+        assert torch.equal(run(b1, lm1, pm1), ref1)
+        n1 = dyn.engine.lib.dndm_launch_count()
+        assert torch.equal(run(b1, lm1, pm1), ref1)                       # cached layout: two launches fewer
+        assert dyn.engine.lib.dndm_launch_count() - n1 == per_call - 2
+        assert torch.equal(run(b2, lm2, pm2), ref2)                       # other tensors -> layout rebuilt
+        assert torch.equal(run(b1, lm1, pm1), ref1)
+    finally:
+        dyn.engine.set_static_masks(False)
+    assert torch.equal(run(b2, lm2, pm2), ref2)
+
+
 def test_nan_raises_value_error(dyn, dev):
     c = FWD_CASES['synth60_b3']
     xl = c['xh_lig'].copy()
