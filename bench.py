@@ -362,9 +362,9 @@ def run_b200(args):
         achieved = edges_timed * EXEC_FLOP_PER_EDGE_GCL / (g_ms * 1e-3) / 1e12
         # DRAM traffic of the kernel from the committed `ncu --set full` capture of this exact workload
         # (profiles/r1_edge_kernel_ncu_raw.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch); other batch sizes: null
-        traffic = (47.63e6 + 287.92e6) * (edges_timed / max(g_n, 1)) / 613e3 if (B == 100 and POCKET_ATOMS == 330) else None
+        traffic = (47.59e6 + 289.15e6) * (edges_timed / max(g_n, 1)) / 613e3 if (B == 100 and POCKET_ATOMS == 330) else None
         roof = {'bound': 'tensor', 'kernel': 'edge_mlp_kernel<GCL>', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': 'profiles/r1_edge_kernel_ncu_raw.txt (335.5 MB at 613k edges, scaled to the mean edges per launch)',
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': 'profiles/r1_edge_kernel_ncu_raw.txt (336.7 MB at 613k edges, scaled to the mean edges per launch)',
                 'peak_source': peak_src,
                 'us_per_launch': t_launch * 1e6, 'edges_per_launch': edges_timed / max(g_n, 1), 'edges': E_edges,
                 'edges_last_block': E_last,
