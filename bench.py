@@ -31,8 +31,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version / debug lines on stdout by default; stdout is reserved for the one JSON line
+# stdout is reserved for the ONE JSON line.  NCCL (version banner), torch and child processes write to file descriptor 1
+# directly, so the descriptor itself is pointed at stderr for the whole run and the JSON line goes to a private duplicate
+# of the original stdout.
 os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+sys.stdout.flush()
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(line):
+    os.write(_JSON_FD, (json.dumps(line) + '\n').encode())
+
 
 T_STEPS = 500
 CALLS_PER_TRAJ = T_STEPS + 1
@@ -117,7 +127,7 @@ def run_reference(args):
         'e2e': {'value': val, 'unit': 'ligands/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def workload_config(batch):
@@ -441,7 +451,7 @@ def run_b200(args):
             'config': cfgd, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps),
             'gpu_launches_per_step': int(launches_per_step), 'roofline': roof, 'cpu_baseline': cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
