@@ -394,9 +394,11 @@ def run_b200(args):
         coef_cpu, t_cpu = coef_tab.cpu(), t_tab.cpu()
         n_e2e = min(args.steps, 50)
 
-        def e2e_step(s):
-            ht.copy_(t_cpu[s].expand(B, 1))
-            hc.copy_(coef_cpu[s].expand(B, 3))
+        # One step through the public API with HOST buffers: H2D of every input of the call (state, pocket, time, step
+        # coefficients, both masks), denoiser forward, noise draw, p(z_s|z_t), D2H of the new state and pocket.  The chain is
+        # sequential (the output of a step is the next step's input, via the host).  Like the device-resident loop, the
+        # call sequence is captured once in a CUDA graph (copy nodes read / write the pinned host buffers at replay time).
+        def e2e_body():
             dz = hz.to(dev, non_blocking=True)
             dp = hp.to(dev, non_blocking=True)
             dt_ = ht.to(dev, non_blocking=True)
@@ -408,6 +410,33 @@ def run_b200(args):
             zo, po = eng.sampler_step(dz, e_, nz, dp, dc, dml, dmp, B)
             hout.copy_(zo, non_blocking=True)
             hp.copy_(po, non_blocking=True)
+
+        e2e_graph = None
+        eng.set_static_masks(False)                 # the masks arrive from the host on every call
+        if not args.no_graph:
+            ht.copy_(t_cpu[T_STEPS - 1].expand(B, 1))
+            hc.copy_(coef_cpu[T_STEPS - 1].expand(B, 3))
+            hp_keep, hz_keep = hp.clone(), hz.clone()
+            side2 = torch.cuda.Stream()
+            side2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side2):
+                e2e_body()
+            torch.cuda.current_stream().wait_stream(side2)
+            torch.cuda.synchronize()
+            e2e_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(e2e_graph):
+                e2e_body()
+            torch.cuda.synchronize()
+            hp.copy_(hp_keep)
+            hz.copy_(hz_keep)
+
+        def e2e_step(s):
+            ht.copy_(t_cpu[s].expand(B, 1))
+            hc.copy_(coef_cpu[s].expand(B, 3))
+            if e2e_graph is not None:
+                e2e_graph.replay()
+            else:
+                e2e_body()
             torch.cuda.synchronize()
             hz.copy_(hout)
 
@@ -430,7 +459,7 @@ def run_b200(args):
         h2d = hz.numel() * 4 + p0.numel() * 4 + B * 4 * 4 + (n_l + n_p) * 8
         d2h = hz.numel() * 4 + p0.numel() * 4
         e2e = {'value': world * B / (CALLS_PER_TRAJ * ms_e2e * 1e-3), 'unit': 'ligands/s', 'h2d_bytes_per_step': int(h2d),
-               'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms_e2e, 'steps': n_e2e}
+               'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms_e2e, 'steps': n_e2e, 'cuda_graph': e2e_graph is not None}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----
     cpu = None
