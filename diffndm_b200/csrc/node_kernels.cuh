@@ -208,6 +208,7 @@ decode_kernel(const float* __restrict__ h, const float* __restrict__ x_final, co
         hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
     }
     float s = 0.f;     // lane j keeps hidden unit j
+#pragma unroll 4
     for (int j = 0; j < w.hid; ++j) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(w.wc + (size_t)j * 256 + 4 * lane));
         const float4 b = __ldg(reinterpret_cast<const float4*>(w.wc + (size_t)j * 256 + 128 + 4 * lane));
@@ -252,8 +253,7 @@ sampler_step_kernel(const float* z_t, const float* eps, const float* noise, cons
     const int D = 3 + nf;
     const int l0 = lig_ptr[b], l1 = lig_ptr[b + 1];
     const float cz = coef[3 * b], ce = coef[3 * b + 1], cn = coef[3 * b + 2];
-    __shared__ float red[4][128];
-    __shared__ float com[3];
+    __shared__ float red[4][8];
     float s[3] = {0.f, 0.f, 0.f}, si[3] = {0.f, 0.f, 0.f}, mx = 0.f;
     for (int i = l0 + tid; i < l1; i += blockDim.x) {
         for (int d = 0; d < D; ++d) {
@@ -269,26 +269,33 @@ sampler_step_kernel(const float* z_t, const float* eps, const float* noise, cons
             z_out[o] = v;
         }
     }
-    red[0][tid] = s[0]; red[1][tid] = s[1]; red[2][tid] = s[2];
-    __syncthreads();
-    if (tid < 3) {
-        float a = 0.f;
-        for (int k = 0; k < (int)blockDim.x; ++k) a += red[tid][k];
-        com[tid] = a / (float)(l1 - l0);
+    // block reduction of the 7 per-thread partials in one pass: fixed xor tree inside each warp, then the four warp
+    // partials added in warp order by every thread (deterministic, one barrier)
+    float q[7] = {s[0], s[1], s[2], si[0], si[1], si[2], mx};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+        q[6] = fmaxf(q[6], __shfl_xor_sync(0xffffffffu, q[6], o));
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) red[tid >> 5][k] = q[k];
     }
     __syncthreads();
-    // COM-drift check of the input (reference asserts on z_t after the step)
-    red[0][tid] = si[0]; red[1][tid] = si[1]; red[2][tid] = si[2]; red[3][tid] = mx;
-    __syncthreads();
+    float tot[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        tot[k] = red[0][k];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) tot[k] = k < 6 ? tot[k] + red[w][k] : fmaxf(tot[k], red[w][k]);
+    }
+    const float inv_n = 1.0f / (float)(l1 - l0);
+    // COM-drift check of the input (reference asserts on z_t, conditional_model.py:535)
     if (tid == 0) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, m = 0.f;
-        for (int k = 0; k < (int)blockDim.x; ++k) {
-            a0 += red[0][k]; a1 += red[1][k]; a2 += red[2][k]; m = fmaxf(m, red[3][k]);
-        }
-        const float err = fmaxf(fabsf(a0), fmaxf(fabsf(a1), fabsf(a2)));
-        if (check_input_com && err / (m + 1e-10f) >= 1e-2f) atomicOr(flags, 2u);
+        const float err = fmaxf(fabsf(tot[3]), fmaxf(fabsf(tot[4]), fabsf(tot[5])));
+        if (check_input_com && err / (tot[6] + 1e-10f) >= 1e-2f) atomicOr(flags, 2u);
     }
-    const float c0 = com[0], c1 = com[1], c2 = com[2];
+    const float c0 = tot[0] * inv_n, c1 = tot[1] * inv_n, c2 = tot[2] * inv_n;
     for (int i = l0 + tid; i < l1; i += blockDim.x) {
         z_out[(size_t)i * D] -= c0;
         z_out[(size_t)i * D + 1] -= c1;
