@@ -15,6 +15,7 @@
 #include "gemm_wres.cuh"
 #include "edge_mlp.cuh"
 #include "graph.cuh"
+#include "bonds.cuh"
 #include "node_kernels.cuh"
 
 using namespace dndm;
@@ -127,6 +128,7 @@ struct DndmEngine {
     int *deg_act = nullptr, *rp_act = nullptr, *erow_c = nullptr, *ecol_c = nullptr;   // last-block compacted graph
     float* r0_c = nullptr;
     unsigned* flags = nullptr;
+    long long* mol_off = nullptr;                // [max_samples + 1] byte offsets of the per-molecule bond matrices
     // the radius graph only needs coordinates: it is built on a side stream while the main stream encodes the features
     float* xg = nullptr;                         // [N,3] coordinates gathered for the graph branch
     cudaStream_t side = nullptr;
@@ -222,6 +224,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(dev_alloc(&e->ecol_c, E)); RET_IF(dev_alloc(&e->r0_c, E));
     RET_IF(dev_alloc(&e->flags, 1));
     RET_IF(dev_alloc(&e->xg, N * 3));
+    RET_IF(dev_alloc(&e->mol_off, B + 1));
     CU_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
@@ -261,7 +264,7 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->msg, e->att, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
                     e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->deg_act, e->rp_act, e->erow_c,
-                    e->ecol_c, e->r0_c, e->flags, e->xg};
+                    e->ecol_c, e->r0_c, e->flags, e->xg, e->mol_off};
     for (void* p : bufs) cudaFree(p);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -772,6 +775,36 @@ extern "C" int dndm_sampler_step(DndmEngine* e, const float* z_in, const float* 
     sampler_step_kernel<<<n_samples, 128, 0, st>>>(z_in, eps ? eps : noise, noise, xh_pocket_in, coef, grad, lambda, e->lig_ptr,
                                                    e->pok_ptr, e->cfg.atom_nf, z_out, xh_pocket_out, e->flags, eps != nullptr);
     COUNT_LAUNCH(1);
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bond perception (pre-filter of candidate molecules)
+// ------------------------------------------------------------------------------------------------
+extern "C" int dndm_bond_orders(DndmEngine* e, const float* x, int32_t ld_x, const int64_t* atom_type, const int64_t* mol_mask,
+                                int32_t n_atoms, int32_t n_mols, const float* bonds1, const float* bonds2, const float* bonds3,
+                                int32_t n_types, float margin1, float margin2, float margin3, const int32_t* allowed_valence,
+                                int8_t* e_out, int64_t e_capacity, int32_t* valence_out, int32_t* mol_stats, void* stream) {
+    if (!e || !x || !atom_type || !mol_mask || !bonds1 || !bonds2 || !bonds3 || !valence_out || !mol_stats)
+        return set_err(DNDM_EINVAL, "null argument");
+    if (n_atoms < 1 || n_mols < 1 || n_types < 1 || ld_x < 3) return set_err(DNDM_EINVAL, "bad sizes");
+    if (n_atoms > e->cfg.max_nodes || n_mols > e->cfg.max_samples)
+        return set_err(DNDM_ECAPACITY, "batch (%d atoms, %d molecules) exceeds engine capacity (%d, %d)", n_atoms, n_mols,
+                       e->cfg.max_nodes, e->cfg.max_samples);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    e->last_lm = e->last_pm = nullptr;                       // lig_ptr / node_sample are reused as scratch below
+    {
+        const int n = n_atoms > n_mols + 1 ? n_atoms : n_mols + 1;
+        mask_to_ptr_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(mol_mask), n_atoms, n_mols,
+                                                            e->lig_ptr, e->node_sample);
+    }
+    bond_offsets_kernel<<<1, 32, 0, st>>>(e->lig_ptr, n_mols, e->mol_off);
+    BondTables tb{bonds1, bonds2, bonds3, allowed_valence, n_types, margin1, margin2, margin3};
+    bond_orders_kernel<<<n_mols, BOND_THREADS, 0, st>>>(x, ld_x, reinterpret_cast<const long long*>(atom_type), e->lig_ptr, tb,
+                                                        e->mol_off, reinterpret_cast<signed char*>(e_out), e_capacity,
+                                                        valence_out, mol_stats, e->flags);
+    COUNT_LAUNCH(3);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
 }

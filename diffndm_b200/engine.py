@@ -24,11 +24,12 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'lib
 FLAG_NAN = 1
 FLAG_COM_DRIFT = 2
 FLAG_EDGE_OVERFLOW = 4
+FLAG_MOL_TOO_LARGE = 8
 
 EXPORTED_SYMBOLS = [
     'dndm_version', 'dndm_last_error', 'dndm_launch_count', 'dndm_engine_create', 'dndm_engine_destroy', 'dndm_engine_load_weights',
     'dndm_egnn_forward', 'dndm_radius_graph', 'dndm_sampler_step', 'dndm_read_flags', 'dndm_debug_copy',
-    'dndm_set_trace', 'dndm_set_profile', 'dndm_get_profile', 'dndm_set_static_masks', 'dndm_test_gemm',
+    'dndm_set_trace', 'dndm_set_profile', 'dndm_get_profile', 'dndm_set_static_masks', 'dndm_bond_orders', 'dndm_test_gemm',
 ]
 
 
@@ -78,6 +79,7 @@ def load_library() -> ctypes.CDLL:
     lib.dndm_set_trace.argtypes = [vp, vp, vp, i32]
     lib.dndm_set_profile.argtypes = [vp, i32]
     lib.dndm_set_static_masks.argtypes = [vp, i32]
+    lib.dndm_bond_orders.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp]
     lib.dndm_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32), i32]
     lib.dndm_test_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     _lib = lib

@@ -30,6 +30,7 @@ extern "C" {
 /* sticky device flags (dndm_read_flags) */
 #define DNDM_FLAG_NAN 1u          /* NaN in the predicted velocity  -> ValueError, dynamics.py:155-159 */
 #define DNDM_FLAG_COM_DRIFT 2u    /* ligand COM of z_t not ~0        -> AssertionError, en_diffusion.py:930-935 */
+#define DNDM_FLAG_MOL_TOO_LARGE 8u /* dndm_bond_orders: a molecule has more than 256 atoms (its stats are -1) */
 #define DNDM_FLAG_EDGE_OVERFLOW 4u /* more edges than max_edges (results invalid) */
 
 typedef struct DndmEngine DndmEngine;
@@ -122,6 +123,20 @@ int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64_t dst_byte
  * Categories: 0 fused GCL edge kernel, 1 fused coordinate-head edge kernel, 2 node GEMMs, 3 radius graph,
  * 4 remaining node kernels. */
 int dndm_set_profile(DndmEngine* e, int32_t on);
+
+/* Bond perception for candidate pre-filtering -- replaces the numeric part of make_mol_edm / get_bond_order_batch
+ * (reference analysis/molecule_builder.py:30-55, 100-113).  All pointers DEVICE.
+ *   x [n_atoms, ld_x] fp32 coordinates in Angstrom (first 3 columns), atom_type [n_atoms] int64 decoder indices,
+ *   mol_mask [n_atoms] int64 sorted molecule ids 0..n_mols-1, bonds1/2/3 [n_types, n_types] fp32 lengths in pm
+ *   (dataset_info['bonds1'] ...), margins in pm (constants.py:17), allowed_valence [n_types] int32 or NULL.
+ * Outputs: e_out (or NULL): per molecule a dense row-major int8 [n_b, n_b] block holding the DIRECTED lower-triangular
+ *   bond orders (0/1/2/3), blocks concatenated in molecule order (sum n_b^2 bytes; flag bit 2 if e_capacity is too small);
+ *   valence_out [n_atoms] int32 (sum of the symmetrised orders); mol_stats [n_mols, 4] int32 =
+ *   (n_bonds, n_components of the bond graph, size of the largest component, atoms exceeding allowed_valence). */
+int dndm_bond_orders(DndmEngine* e, const float* x, int32_t ld_x, const int64_t* atom_type, const int64_t* mol_mask,
+                     int32_t n_atoms, int32_t n_mols, const float* bonds1, const float* bonds2, const float* bonds3,
+                     int32_t n_types, float margin1, float margin2, float margin3, const int32_t* allowed_valence,
+                     int8_t* e_out, int64_t e_capacity, int32_t* valence_out, int32_t* mol_stats, void* stream);
 
 /* Static batch layout.  Every entry point derives the per-sample offsets from the int64 masks (two small launches).
  * While `on` != 0 the caller promises that the CONTENTS of the mask buffers do not change between calls that pass the

@@ -519,6 +519,55 @@ def inpaint(W, lig_x, lig_onehot, lig_mask, pocket_x, pocket_onehot, pocket_mask
 
 
 # ----------------------------------------------------------------------------
+# bond perception: analysis/molecule_builder.py:30-55 (get_bond_order_batch), :100-116 (make_mol_edm)
+# ----------------------------------------------------------------------------
+def bond_orders(x, atom_types, mol_mask, bonds1, bonds2, bonds3, margins=(3.0, 2.0, 1.0)):
+    """Per molecule, the directed lower-triangular bond-order matrix E of make_mol_edm (molecule_builder.py:107-113):
+    E[i, j] (i > j) = 3 / 2 / 1 / 0 by the distance tables (pm) + margins, later rules overwriting earlier ones exactly
+    like get_bond_order_batch (:43-53).  Distances are fp32: 100 * sqrt((dx*dx + dy*dy) + dz*dz), one rounding per
+    operation (torch.cdist's arithmetic is backend dependent; the fixtures count the pairs near a threshold).
+    Returns a list of int8 [n_b, n_b] matrices, the per-atom valence (sum of the symmetrised orders) and per molecule
+    (n_bonds, n_components, largest_component)."""
+    x = np.asarray(x, np.float32)
+    t = np.asarray(atom_types, np.int64)
+    b1, b2, b3 = (np.asarray(b, np.float32) for b in (bonds1, bonds2, bonds3))
+    m1, m2, m3 = (np.float32(m) for m in margins)
+    nb = int(mol_mask.max()) + 1
+    mats, stats = [], []
+    valence = np.zeros(len(t), np.int32)
+    for b in range(nb):
+        idx = np.nonzero(mol_mask == b)[0]
+        xi, ti = x[idx], t[idx]
+        d = xi[:, None, :] - xi[None, :, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        dist = np.float32(100.0) * np.sqrt(d2.astype(np.float32))
+        ta, tb = ti[:, None], ti[None, :]
+        e = np.zeros(dist.shape, np.int8)
+        e[dist < b1[ta, tb] + m1] = 1
+        e[dist < b2[ta, tb] + m2] = 2
+        e[dist < b3[ta, tb] + m3] = 3
+        e = np.tril(e, -1)
+        mats.append(e)
+        sym = e.astype(np.int32) + e.astype(np.int32).T
+        valence[idx] = sym.sum(1)
+        # connected components of the bond graph (process_molecule's largest_frag works on these fragments)
+        n = len(idx)
+        label = np.arange(n)
+        adj = sym > 0
+        changed = True
+        while changed:
+            changed = False
+            for i in range(n):
+                m = min(label[i], label[adj[i]].min()) if adj[i].any() else label[i]
+                if m < label[i]:
+                    label[i] = m
+                    changed = True
+        _, counts = np.unique(label, return_counts=True)
+        stats.append((int((e > 0).sum()), len(counts), int(counts.max())))
+    return mats, valence, np.asarray(stats, np.int32)
+
+
+# ----------------------------------------------------------------------------
 # algorithmic work model (SURVEY.md §8d)
 # ----------------------------------------------------------------------------
 def reference_flops(n_nodes, n_edges, cfg: OracleConfig = OracleConfig()):

@@ -547,6 +547,54 @@ def test_atp_event_distributed_two_gpus():
     assert ret.get(0) and ret.get(1)
 
 
+BOND_CASES, BOND_META = load_npz_groups('bonds.npz')
+
+
+@pytest.mark.parametrize('name', sorted(BOND_CASES))
+def test_bond_orders_bit_exact(dyn, dev, name):
+    """dndm_bond_orders vs the reference's get_bond_order_batch / make_mol_edm fixtures (bit-exact) and the oracle's
+    valences / fragments."""
+    from diffndm_b200.chem import BondPerception
+    c = BOND_CASES[name]
+    info = {'bonds1': BOND_META['bonds1'].tolist(), 'bonds2': BOND_META['bonds2'].tolist(), 'bonds3': BOND_META['bonds3'].tolist(),
+            'atom_decoder': ['C', 'N', 'O', 'S', 'B', 'Br', 'Cl', 'P', 'I', 'F']}
+    bp = BondPerception(dyn.engine, info, margins=BOND_META['margins'].tolist())
+    dyn.engine.read_flags()                              # the flag word is sticky across calls: start clean
+    B = len(c['sizes'])
+    out = bp(_t(c['x'], dev), _t(c['types'], dev), _t(c['mask'], dev), B)
+    flat = torch.cat([m.reshape(-1) for m in out['E']]).cpu().numpy()
+    assert np.array_equal(flat, c['e_flat'])
+    mats, val, stats = O.bond_orders(c['x'], c['types'], c['mask'], BOND_META['bonds1'], BOND_META['bonds2'],
+                                     BOND_META['bonds3'], BOND_META['margins'])
+    assert np.array_equal(out['valence'].cpu().numpy(), val)
+    assert np.array_equal(out['n_bonds'].cpu().numpy(), stats[:, 0])
+    assert np.array_equal(out['n_components'].cpu().numpy(), stats[:, 1])
+    assert np.array_equal(out['largest_component'].cpu().numpy(), stats[:, 2])
+    allowed = np.array([4, 3, 2, 4, 3, 1, 1, 5, 1, 1])
+    viol = np.array([(val[c['mask'] == b] > allowed[c['types'][c['mask'] == b]]).sum() for b in range(B)])
+    assert np.array_equal(out['valence_violations'].cpu().numpy(), viol)
+    keep = bp.keep_mask(out, torch.from_numpy(c['sizes']))
+    assert keep.shape == (B,)
+    assert dyn.engine.read_flags() == 0
+
+
+def test_bond_orders_random_vs_oracle(dyn, dev):
+    from diffndm_b200.chem import BondPerception
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(1, 60, size=40)
+    x = np.concatenate([np.cumsum(rng.normal(size=(n, 3)) * 0.85, 0) for n in sizes]).astype(np.float32)
+    types = rng.integers(0, 10, size=int(sizes.sum()))
+    mask = np.repeat(np.arange(len(sizes)), sizes)
+    info = {'bonds1': BOND_META['bonds1'].tolist(), 'bonds2': BOND_META['bonds2'].tolist(), 'bonds3': BOND_META['bonds3'].tolist()}
+    bp = BondPerception(dyn.engine, info)
+    out = bp(_t(x, dev), _t(types, dev), _t(mask, dev), len(sizes))
+    mats, val, stats = O.bond_orders(x, types, mask, BOND_META['bonds1'], BOND_META['bonds2'], BOND_META['bonds3'])
+    for a, b in zip(out['E'], mats):
+        assert np.array_equal(a.cpu().numpy(), b)
+    assert np.array_equal(out['valence'].cpu().numpy(), val)
+    assert np.array_equal(torch.stack([out['n_bonds'], out['n_components'], out['largest_component']], 1).cpu().numpy(), stats)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full benchmark size: properties that do not need the oracle to finish
 # ---------------------------------------------------------------------------------------------------------------

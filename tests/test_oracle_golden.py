@@ -131,3 +131,23 @@ def test_inpaint_moves_are_com_free_and_keep_known_atoms():
     fx = fixed > 0
     assert np.abs(O.segment_mean(zc[fx][:, :3], lm[fx], 3) - O.segment_mean(z2[fx][:, :3], lm[fx], 3)).max() < 1e-5
     assert d_l.shape == (3, 3)
+
+
+BOND_CASES, BOND_META = load_npz_groups('bonds.npz')
+
+
+@pytest.mark.parametrize('name', sorted(BOND_CASES))
+def test_bond_orders_match_reference(name):
+    """get_bond_order_batch as called by make_mol_edm (analysis/molecule_builder.py:30-55, 100-113): bit-exact."""
+    c = BOND_CASES[name]
+    assert int(c['pairs_near_threshold']) == 0          # no pair where cdist and direct differences could disagree
+    mats, val, stats = O.bond_orders(c['x'], c['types'], c['mask'], BOND_META['bonds1'], BOND_META['bonds2'],
+                                     BOND_META['bonds3'], BOND_META['margins'])
+    assert np.array_equal(np.concatenate([m.reshape(-1) for m in mats]), c['e_flat'])
+    # derived quantities are consistent with E
+    off = 0
+    for b, n in enumerate(c['sizes']):
+        e = c['e_flat'][off:off + n * n].reshape(n, n).astype(np.int32)
+        off += n * n
+        assert np.array_equal(val[c['mask'] == b], (e + e.T).sum(1))
+        assert stats[b, 0] == int((e > 0).sum()) and 1 <= stats[b, 1] <= n and stats[b, 2] <= n
