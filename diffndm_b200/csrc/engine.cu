@@ -103,12 +103,12 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // engine state
 // ------------------------------------------------------------------------------------------------
 struct LayerWeights {
-    __nv_bfloat16 *wproj_e, *wproj_c, *w2_e, *w2_c, *w2_x, *w3, *w4;   // device bf16
+    __nv_bfloat16 *wproj_e, *w2_e, *w2_c, *w2_x, *w3, *w4;             // device bf16
     __nv_bfloat16* wm;                                                  // merged projections [next-edge P|Q ; coord Q ; cross Q ; coord P ; cross P]
     float* bias_m;
-    CUtensorMap tm_wm, tm_we0, tm_w4r;                            // 256-row boxes for the weight-resident GEMM
-    float *bias_e, *bias_c, *b3, *b4, *w1e_e, *w1e_c, *w1e_x;          // device fp32
-    CUtensorMap tm_proj_e, tm_proj_c, tm_w2_e, tm_w2_c, tm_w2_x, tm_w3, tm_w4;
+    CUtensorMap tm_wm, tm_we0;                                    // 256-row boxes for the weight-resident GEMM
+    float *bias_e, *b3, *b4, *w1e_e, *w1e_c, *w1e_x;                   // device fp32
+    CUtensorMap tm_w2_e, tm_w2_c, tm_w2_x, tm_w3, tm_w4;
     EdgeConsts c_e, c_c, c_x;                                            // host copies (kernel parameters)
     float att_bias;
 };
@@ -138,7 +138,6 @@ struct DndmEngine {
     const int64_t *last_lm = nullptr, *last_pm = nullptr;
     int last_nl = -1, last_np = -1, last_ns = -1;
     CUtensorMap tm_hcat, tm_hid;
-    CUtensorMap to_pq, to_hid, to_hcat, to_h;
     CUtensorMap to_pq32, to_hcat32, to_hid32;    // 32-column bf16 boxes (SWIZZLE_64B) for the weight-resident GEMM
     CUtensorMap to_msg;                          // TMA-store destination of the edge messages (box 32 rows x 64 cols)   // TMA-store destinations of the node GEMMs (32-row boxes)
     // weights
@@ -233,10 +232,6 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaMemset(e->hid, 0, N * 256 * 2));
     RET_IF(make_tmap_bf16(&e->tm_hcat, e->hcat, N, 512, 512, GEMM_BM));
     RET_IF(make_tmap_bf16(&e->tm_hid, e->hid, N, 256, 256, GEMM_BM));
-    RET_IF(make_tmap_bf16(&e->to_pq, e->pq, N, 1536, 1536, 32));
-    RET_IF(make_tmap_bf16(&e->to_hid, e->hid, N, 256, 256, 32));
-    RET_IF(make_tmap_bf16(&e->to_hcat, e->hcat, N, 512, 512, 32));
-    RET_IF(make_tmap_f32_out(&e->to_h, e->h, N, 256, 256));
     RET_IF(make_tmap_bf16_box(&e->to_msg, e->msg, E + 128, 256, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_pq32, e->pq, N, 1536, 1536, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_hcat32, e->hcat, N, 512, 512, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
@@ -411,14 +406,14 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
             for (size_t i = 0; i < n; ++i) v[i] = f2bf(w[i]);
             return v;
         };
-        std::vector<__nv_bfloat16> pe((size_t)2 * H * H), pc((size_t)4 * H * H);
+        // this block's own edge-model projection [P | Q] (only block 0's is launched: later blocks get theirs from the
+        // previous block's merged projection)
+        std::vector<__nv_bfloat16> pe((size_t)2 * H * H);
         split_first(e0w, pe, 0, H);
-        split_first(c0w, pc, 0, 2 * H);
-        split_first(x0w, pc, H, 3 * H);
-        std::vector<float> be(2 * H, 0.f), bcv(4 * H, 0.f);
-        for (int o = 0; o < H; ++o) { be[o] = 0.5f * e0b[o]; bcv[o] = 0.5f * c0b[o]; bcv[H + o] = 0.5f * x0b[o]; }
-        RET_IF(upload(e, pe, &L.wproj_e)); RET_IF(upload(e, pc, &L.wproj_c));
-        RET_IF(upload(e, be, &L.bias_e)); RET_IF(upload(e, bcv, &L.bias_c));
+        std::vector<float> be(2 * H, 0.f);
+        for (int o = 0; o < H; ++o) be[o] = 0.5f * e0b[o];
+        RET_IF(upload(e, pe, &L.wproj_e));
+        RET_IF(upload(e, be, &L.bias_e));
         RET_IF(upload(e, edge_cols(e0w), &L.w1e_e)); RET_IF(upload(e, edge_cols(c0w), &L.w1e_c));
         RET_IF(upload(e, edge_cols(x0w), &L.w1e_x));
         auto to_bf_half = [&](const float* w, size_t n) {       // edge-MLP second layers: the kernel evaluates SiLU on x/2
@@ -436,8 +431,6 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
             L.c_x.b2[o] = 0.5f * x2b[o]; L.c_x.wout[o] = x4w[o];
         }
         L.att_bias = ab[0];
-        RET_IF(make_tmap_bf16(&L.tm_proj_e, L.wproj_e, 2 * H, H, H, GEMM_BN));
-        RET_IF(make_tmap_bf16(&L.tm_proj_c, L.wproj_c, 4 * H, H, H, GEMM_BN));
         RET_IF(make_tmap_bf16(&L.tm_w3, L.w3, H, 2 * H, 2 * H, GEMM_BN));
         RET_IF(make_tmap_bf16(&L.tm_w4, L.w4, H, H, H, GEMM_BN));
         RET_IF(make_tmap_bf16(&L.tm_w2_e, L.w2_e, H, H, H, 256));
@@ -478,7 +471,6 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         RET_IF(upload(e, wm, &L.wm)); RET_IF(upload(e, bm, &L.bias_m));
         RET_IF(make_tmap_bf16(&L.tm_wm, L.wm, 6 * H, H, H, 256));
         RET_IF(make_tmap_bf16(&L.tm_we0, L.wproj_e, 2 * H, H, H, 256));
-        RET_IF(make_tmap_bf16(&L.tm_w4r, L.w4, H, H, H, 256));
     }
     e->weights_loaded = true;
     return DNDM_OK;
