@@ -132,7 +132,7 @@ struct DndmEngine {
     // the radius graph only needs coordinates: it is built on a side stream while the main stream encodes the features
     float* xg = nullptr;                         // [N,3] coordinates gathered for the graph branch
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_last = nullptr;
     // cached batch layout (dndm_set_static_masks)
     bool static_masks = false;
     const int64_t *last_lm = nullptr, *last_pm = nullptr;
@@ -227,6 +227,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&e->ev_join_last, cudaEventDisableTiming));
     CU_CHECK(cudaMemset(e->flags, 0, 4));
     CU_CHECK(cudaMemset(e->hcat, 0, N * 512 * 2));
     CU_CHECK(cudaMemset(e->hid, 0, N * 256 * 2));
@@ -263,6 +264,7 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     for (void* p : bufs) cudaFree(p);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_join_last) cudaEventDestroy(e->ev_join_last);
     if (e->side) cudaStreamDestroy(e->side);
     delete e;
 }
@@ -619,9 +621,11 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, gs>>>(e->xg, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
         COUNT_LAUNCH(2);
         RET_IF(build_graph(e, e->xg, n_lig, N, gs));
+        if (fork) CU_CHECK(cudaEventRecord(e->ev_join, gs));   // blocks 0..L-2 only need the full graph
+        // the compacted edge list is first read by the LAST block: it keeps running on the side stream under block 0
         if (prune_last) RET_IF(build_last_block_edges(e, n_lig, N, gs));
+        if (fork && prune_last) CU_CHECK(cudaEventRecord(e->ev_join_last, gs));
     }
-    if (fork) CU_CHECK(cudaEventRecord(e->ev_join, gs));
 
     // ---- feature branch: encoder + embedding, first-layer projections of block 0's edge model (pq columns [0,512)) ----
     {
@@ -645,6 +649,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     for (int l = 0; l < e->cfg.n_layers; ++l) {
         LayerWeights& L = e->layers[l];
         const bool pruned = prune_last && (l + 1 == e->cfg.n_layers);
+        if (pruned && fork) CU_CHECK(cudaStreamWaitEvent(st, e->ev_join_last, 0));
         // ---- GCL edge model + attention + deterministic aggregation ----
         EdgeGraph g{pruned ? e->erow_c : e->erow, pruned ? e->ecol_c : e->ecol, pruned ? e->r0_c : e->r0, x_cur,
                     e->scalars + (pruned ? 2 : 0), 1536, e->msg, e->att};
