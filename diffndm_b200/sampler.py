@@ -47,6 +47,48 @@ def polynomial_gamma(timesteps: int, precision: float, power: float) -> torch.Te
     return torch.from_numpy(-(np.log(alphas2) - np.log(sigmas2))).float()
 
 
+class _GraphedReverseStep:
+    """One unguided reverse step (denoiser forward + noise draw + fused p(z_s|z_t) update, in place on the state buffers)
+    captured once in a CUDA graph and replayed with new (t, coefficient) values -- removes the ~60 kernel launches and the
+    per-call host work from every step of a trajectory.  Valid while the mask tensors and the batch layout stay the same
+    (between ATP events); flags are sticky on the device and read by the caller."""
+
+    def __init__(self, sampler: 'ConditionalSampler', z_lig, xh_pocket, lig_mask, pocket_mask, B):
+        eng = sampler.engine
+        dev = sampler.device
+        self.z, self.xp = z_lig, xh_pocket                     # updated in place
+        self.t_buf = torch.zeros((B, 1), device=dev)
+        self.coef_buf = torch.zeros((B, 3), device=dev)
+
+        def body():
+            eps, _ = eng.forward(self.z, self.xp, self.t_buf, lig_mask, pocket_mask, B, want_pocket=False)
+            nz = torch.randn_like(self.z)
+            eng.sampler_step(self.z, eps, nz, self.xp, self.coef_buf, lig_mask, pocket_mask, B, z_out=self.z,
+                             pocket_out=self.xp)
+
+        keep_z, keep_p = self.z.clone(), self.xp.clone()
+        rng = torch.cuda.get_rng_state(dev)                    # the dry runs below must not consume the caller's noise stream
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()                                             # warm-up outside capture (allocator, layout cache)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+        self.z.copy_(keep_z)
+        self.xp.copy_(keep_p)
+        torch.cuda.synchronize(dev)
+        torch.cuda.set_rng_state(rng, dev)
+        eng.read_flags()                                       # the two dry runs may have tripped the COM-drift flag
+
+    def __call__(self, t_dev: torch.Tensor, coef_dev: torch.Tensor):
+        """t_dev: 0-d device tensor, coef_dev: [3] device tensor (same for every sample of an unguided step)."""
+        self.t_buf.copy_(t_dev.expand_as(self.t_buf))
+        self.coef_buf.copy_(coef_dev.expand_as(self.coef_buf))
+        self.graph.replay()
+
+
 class ConditionalSampler:
     """Sampler over a ``B200EGNNDynamics``; all state lives on the GPU."""
 
@@ -90,6 +132,17 @@ class ConditionalSampler:
         return torch.stack([1.0 / alpha_ts, sigma2_ts / alpha_ts / sigma_t, sigma_ts * sigma_s / sigma_t], dim=1)
 
     # -- elementary moves -------------------------------------------------------------------------------------------
+    def _eps(self, z_lig, xh_pocket, t, lig_mask, pocket_mask, B):
+        """Ligand part of the denoiser output.  Every conditional call site discards the pocket part (`eps, _ = ...`,
+        conditional_model.py:143, 458, 504), so it is not computed: the last block then skips the pocket atoms that no
+        ligand atom reads (bit-identical ligand output)."""
+        keep = self.dynamics.compute_pocket_output
+        self.dynamics.compute_pocket_output = False
+        try:
+            return self.dynamics(z_lig, xh_pocket, t, lig_mask, pocket_mask, n_samples=B)[0]
+        finally:
+            self.dynamics.compute_pocket_output = keep
+
     def _noise(self, n, noise=None):
         if noise is not None:
             return noise.to(self.device, torch.float32)
@@ -99,7 +152,7 @@ class ConditionalSampler:
         """conditional_model.py:483-540 (optimize=0; AdjustNet is training-only and off the sampling path)."""
         B = int(n_samples if n_samples is not None else t.numel())
         coef = self.step_coefficients(self.lookup(s), self.lookup(t)).to(self.device)
-        eps, _ = self.dynamics(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, n_samples=B)
+        eps = self._eps(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, B)
         zs, xp = self.engine.sampler_step(zt_lig, eps, self._noise(len(ligand_mask), noise), xh0_pocket, coef,
                                           ligand_mask, pocket_mask, B)
         if self.check_every_step:
@@ -111,7 +164,7 @@ class ConditionalSampler:
         B = int(batch_size)
         t0 = torch.zeros((B, 1), device=self.device)
         g0 = self.lookup(t0)
-        eps0, _ = self.dynamics(z0_lig, xh0_pocket, t0, lig_mask, pocket_mask, n_samples=B)
+        eps0 = self._eps(z0_lig, xh0_pocket, t0, lig_mask, pocket_mask, B)
         sigma_x = torch.exp(0.5 * g0)                                   # SNR(-0.5 gamma_0)
         sigma0, alpha0 = torch.sqrt(torch.sigmoid(g0)), torch.sqrt(torch.sigmoid(-g0))
         coef = torch.stack([1.0 / alpha0, sigma0 / alpha0, sigma_x], dim=1).to(self.device)   # compute_x_pred
@@ -127,7 +180,7 @@ class ConditionalSampler:
     def my_to_x0(self, t, zt_lig, xh0_pocket, ligand_mask, pocket_mask, n_samples, noise=None):
         """conditional_model.py:457-468: x0 look-ahead (two denoiser calls)."""
         B = int(n_samples)
-        eps_t, _ = self.dynamics(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, n_samples=B)
+        eps_t = self._eps(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, B)
         gt = self.lookup(t)
         alpha_t = torch.exp(0.5 * F.logsigmoid(-gt)).to(self.device)
         sigma_t = torch.sqrt(torch.sigmoid(gt)).to(self.device)
@@ -204,12 +257,16 @@ class ConditionalSampler:
     @torch.no_grad()
     def sample_given_pocket(self, pocket, num_nodes_lig, timesteps: Optional[int] = None, svdd: int = 0, spsa: int = 0,
                             reward_fn: Optional[Callable] = None, noise: Optional[torch.Tensor] = None,
-                            spsa_schedule=(30, 2), svdd_schedule=(50, 10), svdd_groups: int = 5, spsa_k: int = 10):
+                            spsa_schedule=(30, 2), svdd_schedule=(50, 10), svdd_groups: int = 5, spsa_k: int = 10,
+                            use_cuda_graph: bool = True):
         """ConditionalDDPM.sample_given_pocket (conditional_model.py:886-1489) without the host chemistry arguments.
 
         ``pocket``: dict with 'x' [N_p,3], 'one_hot' [N_p,residue_nf], 'size' [B], 'mask' [N_p] (prepare_pocket layout,
         lightning_modules.py:763-801).  ``noise`` [timesteps+2, N_l, 13] injects the Gaussian draws in the reference's
         order (z_T, one per step, final head) -- only valid for the unguided path.
+        ``use_cuda_graph``: replay the unguided reverse step from a CUDA graph (re-captured after every ATP event, whose
+        re-batching changes the masks); the NaN / COM-drift flags are then checked at guidance events and at the end
+        instead of at the failing step (``check_every_step=True`` keeps the reference's per-step behaviour, eagerly).
         Returns (xh_lig [N_l, 3+atom_nf] with one-hot features, xh_pocket, lig_mask, pocket_mask) like the reference.
         """
         timesteps = self.T if timesteps is None else timesteps
@@ -231,23 +288,45 @@ class ConditionalSampler:
                                                     xh0_pocket, ident, lig_mask, pocket_mask, B)
         step = 0
         self.engine.set_static_masks(True)          # lig_mask / pocket_mask are fixed tensors between ATP events
-        for s in reversed(range(0, timesteps)):
-            s_array = torch.full((B, 1), fill_value=s, dtype=torch.float32) / timesteps
-            t_array = torch.full((B, 1), fill_value=s + 1, dtype=torch.float32) / timesteps
-            step += 1
-            z_lig, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
-                                                         noise=None if noise is None else noise[step], n_samples=B)
-            if svdd == 1 and s <= svdd_schedule[0] and s % svdd_schedule[1] == 0:
-                self.engine.set_static_masks(False)     # candidate batches use other masks; the winners get a new one
-                z_lig, xh_pocket, lig_mask = self._atp_event(s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
-                                                             B, reward_fn, svdd_groups)
-                z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
-                self.engine.set_static_masks(True)
-            if spsa == 1 and s <= spsa_schedule[0] and s % spsa_schedule[1] == 0:
-                zeta = 1e-3 * (s / 500)                                                   # :1244-1245
-                z_lig, xh_pocket = self.my_update_z_lig(z_lig, xh_pocket, lig_mask, pocket_mask, t_array, B, zeta,
-                                                        reward_fn, guidance_scale=1e-3, k=spsa_k)
-                z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+        graphed = use_cuda_graph and noise is None and not self.check_every_step
+        gstep = None
+        if graphed:                                 # per-step scalars of the whole trajectory, on the device, once
+            s_all = torch.arange(timesteps, dtype=torch.float32)
+            coef_all = self.step_coefficients(self.lookup(s_all / timesteps), self.lookup((s_all + 1) / timesteps)).to(dev)
+            t_all = ((s_all + 1) / timesteps).to(dev)
+        nan_check, self.dynamics.check_nan = self.dynamics.check_nan, (self.dynamics.check_nan and not graphed)
+        try:
+            for s in reversed(range(0, timesteps)):
+                s_array = torch.full((B, 1), fill_value=s, dtype=torch.float32) / timesteps
+                t_array = torch.full((B, 1), fill_value=s + 1, dtype=torch.float32) / timesteps
+                step += 1
+                if graphed:
+                    if gstep is None:
+                        z_lig, xh_pocket = z_lig.contiguous(), xh_pocket.contiguous()
+                        gstep = _GraphedReverseStep(self, z_lig, xh_pocket, lig_mask, pocket_mask, B)
+                    gstep(t_all[s], coef_all[s])
+                else:
+                    z_lig, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
+                                                                 noise=None if noise is None else noise[step], n_samples=B)
+                if svdd == 1 and s <= svdd_schedule[0] and s % svdd_schedule[1] == 0:
+                    if graphed:
+                        self._raise_on_flags()
+                    self.engine.set_static_masks(False)     # candidate batches use other masks; the winners get a new one
+                    z_lig, xh_pocket, lig_mask = self._atp_event(s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
+                                                                 B, reward_fn, svdd_groups)
+                    z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+                    self.engine.set_static_masks(True)
+                    gstep = None                            # new state tensors and ligand mask: capture again
+                if spsa == 1 and s <= spsa_schedule[0] and s % spsa_schedule[1] == 0:
+                    if graphed:
+                        self._raise_on_flags()
+                    zeta = 1e-3 * (s / 500)                                                   # :1244-1245
+                    z_lig, xh_pocket = self.my_update_z_lig(z_lig, xh_pocket, lig_mask, pocket_mask, t_array, B, zeta,
+                                                            reward_fn, guidance_scale=1e-3, k=spsa_k)
+                    z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+                    gstep = None
+        finally:
+            self.dynamics.check_nan = nan_check
         x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(
             z_lig, xh_pocket, lig_mask, pocket_mask, B, noise=None if noise is None else noise[timesteps + 1])
         self.engine.set_static_masks(False)
