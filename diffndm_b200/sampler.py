@@ -300,7 +300,10 @@ class ConditionalSampler:
                 s_array = torch.full((B, 1), fill_value=s, dtype=torch.float32) / timesteps
                 t_array = torch.full((B, 1), fill_value=s + 1, dtype=torch.float32) / timesteps
                 step += 1
-                if graphed:
+                # inside a guidance window the state is replaced every few steps (and ATP re-batches it): capturing a graph
+                # there costs more than the launches it saves, so those steps run eagerly (without per-step host syncs)
+                in_window = (svdd == 1 and s <= svdd_schedule[0]) or (spsa == 1 and s <= spsa_schedule[0])
+                if graphed and not in_window:
                     if gstep is None:
                         z_lig, xh_pocket = z_lig.contiguous(), xh_pocket.contiguous()
                         gstep = _GraphedReverseStep(self, z_lig, xh_pocket, lig_mask, pocket_mask, B)
