@@ -237,9 +237,9 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(make_tmap_bf16_box(&e->to_pq32, e->pq, N, 1536, 1536, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_hcat32, e->hcat, N, 512, 512, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_hid32, e->hid, N, 256, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
@@ -511,7 +511,7 @@ static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
     if (ctas_full < 1) ctas_full = 1;
     if (ctas_full > m_tiles) ctas_full = m_tiles;
     const int grid = n_full * ctas_full + n_tail * ctas_tail;
-    gemm_wres_kernel<kK, kBN><<<grid, WR_THREADS, WR_SMEM_BYTES, st>>>(ta, tw, to16, M, M_tail, a_col0, g0, n_full, ctas_full,
+    gemm_wres_kernel<kK, kBN><<<grid, WR_THREADS, WresShape<kK, kBN>::smem_bytes, st>>>(ta, tw, to16, M, M_tail, a_col0, g0, n_full, ctas_full,
                                                               ctas_tail > 0 ? ctas_tail : 1, ep);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
@@ -834,6 +834,11 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
         }
         case 4: src = e->scalars; bytes = 16; break;
 #ifdef DNDM_EK_TRACE
+        case 6: {
+            bytes = sizeof(g_wr_trace) < (size_t)dst_bytes ? sizeof(g_wr_trace) : dst_bytes;
+            CU_CHECK(cudaMemcpyFromSymbolAsync(dst, g_wr_trace, bytes, 0, cudaMemcpyDeviceToDevice, st));
+            return bytes;
+        }
         case 5: {
             bytes = sizeof(g_ek_trace) < (size_t)dst_bytes ? sizeof(g_ek_trace) : dst_bytes;
             CU_CHECK(cudaMemcpyFromSymbolAsync(dst, g_ek_trace, bytes, 0, cudaMemcpyDeviceToDevice, st));

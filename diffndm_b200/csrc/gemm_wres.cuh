@@ -18,7 +18,7 @@
 namespace dndm {
 
 constexpr int WR_BM = 128;
-constexpr int WR_STAGES = 4;
+constexpr int WR_MAX_STAGES = 4;   // 8 (two row blocks for BN = 128) was measured: no gain for the node MLP, see DESIGN.md
 constexpr int WR_EPI_SPLIT = 4;                               // epilogue warps per TMEM lane quarter (2 or 4)
 constexpr int WR_EPI_WARPS = 4 * WR_EPI_SPLIT;
 constexpr int WR_THREADS = 64 + 32 * WR_EPI_WARPS;
@@ -27,8 +27,18 @@ constexpr int WR_W_BYTES = 131072;                            // BN x K bf16 of 
 constexpr int WR_STAGE_BYTES = WR_BM * 64 * 2;               //  16384  (128 rows x 64 k)
 constexpr int WR_SLAB16_BYTES = 32 * 32 * 2;                 //   2048  [32 rows][32 bf16], SWIZZLE_64B
 constexpr int WR_OUT_BYTES = WR_EPI_WARPS * WR_NSLAB * WR_SLAB16_BYTES;
-constexpr int WR_SMEM_BYTES = WR_W_BYTES + WR_STAGES * WR_STAGE_BYTES + WR_OUT_BYTES + 256;
-static_assert(WR_SMEM_BYTES <= 232448, "gemm_wres shared memory");
+// The A ring takes what the resident weights leave, up to WR_MAX_STAGES.  With a one-row-block ring a stage can only be
+// refilled after the MMA that read it has completed, so every row block exposes most of a TMA round trip (~1 us under
+// load; scripts/wr_timeline.py: row-block period 4 100 cycles against 1 100 of MMA) -- the reason these kernels sit at
+// ~2 TB/s of DRAM traffic.  A deeper ring needs BN = 128, which doubles the A re-reads from L2 and ends up equal.
+template <int kK, int kBN>
+struct WresShape {
+    static constexpr int w_bytes = kK * kBN * 2;
+    static constexpr int avail = 232448 - 256 - WR_OUT_BYTES - w_bytes;
+    static constexpr int stages = avail / WR_STAGE_BYTES > WR_MAX_STAGES ? WR_MAX_STAGES : avail / WR_STAGE_BYTES;
+    static constexpr int smem_bytes = w_bytes + stages * WR_STAGE_BYTES + WR_OUT_BYTES + 256;
+    static_assert(stages >= 4, "gemm_wres: A ring too shallow");
+};
 
 struct WresEpilogue {
     const float* bias;        // [256*G] or nullptr
@@ -42,6 +52,16 @@ struct WresEpilogue {
     int act;                  // 1: SiLU
 };
 
+#ifdef DNDM_EK_TRACE
+__device__ unsigned long long g_wr_trace[64 * 8];
+#define WR_STAMP(it, ev)                                                                                      \
+    do {                                                                                                      \
+        if (kK == 256 && kBN == 256 && blockIdx.x == 0 && (it) < 64) g_wr_trace[(it) * 8 + (ev)] = clock64(); \
+    } while (0)
+#else
+#define WR_STAMP(it, ev) do {} while (0)
+#endif
+
 template <int kK, int kBN>
 __global__ void __launch_bounds__(WR_THREADS, 1)
 gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -49,11 +69,13 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  int ctas_full, int ctas_tail, WresEpilogue ep) {
     static_assert(kK * kBN * 2 <= WR_W_BYTES && (kBN == 256 || kBN == 128), "unsupported shape");
     constexpr int WR_BN = kBN;
+    constexpr int WR_STAGES = WresShape<kK, kBN>::stages;
+    constexpr int kWBytes = WresShape<kK, kBN>::w_bytes;
     constexpr int KB = kK / 64;                                   // 64-column k-blocks per row block
     constexpr int WR_CHUNKS = kBN / 32 / WR_EPI_SPLIT;            // 32-column chunks per epilogue warp and row block
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sW = smem;                                           // [KB k-chunks][BN rows][128 B]
-    uint8_t* sA = smem + WR_W_BYTES;                              // ring of [128 rows][128 B]
+    uint8_t* sA = smem + kWBytes;                                 // ring of [128 rows][128 B]
     uint8_t* sOut = sA + WR_STAGES * WR_STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + WR_OUT_BYTES);
     uint64_t* empty_bar = full_bar + WR_STAGES;
@@ -106,8 +128,9 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_arrive_expect_tx(w_bar, kK * kBN * 2);
 #pragma unroll
             for (int kc = 0; kc < KB; ++kc) tma_load_2d(sW + kc * (WR_BN * 128), &tmap_w, w_bar, kc * 64, grp * WR_BN);
-            int kq = 0;
-            for (int m_blk = cta_rank; m_blk < m_tiles; m_blk += cta_stride) {
+            int kq = 0, itp = 0;
+            for (int m_blk = cta_rank; m_blk < m_tiles; m_blk += cta_stride, ++itp) {
+                WR_STAMP(itp, 0);
                 if (ep.residual && ep.ldr == 256 && (kBN == 256 || grp == g0)) {   // fp32 residual rows of the block: contiguous
                     const int rows = min(WR_BM, M - m_blk * WR_BM);
                     bulk_prefetch_l2(ep.residual + (size_t)m_blk * WR_BM * 256, (uint32_t)rows * 256 * 4);
@@ -119,6 +142,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_arrive_expect_tx(&full_bar[s], WR_STAGE_BYTES);
                     tma_load_2d(sA + s * WR_STAGE_BYTES, &tmap_a, &full_bar[s], a_col0 + kb * 64, m_blk * WR_BM);
                 }
+                WR_STAMP(itp, 1);
             }
         }
         __syncwarp();
@@ -136,6 +160,8 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int s = kq % WR_STAGES;
                     const uint32_t ph = (kq / WR_STAGES) & 1;
                     mbar_wait(&full_bar[s], ph);
+                    if (kb == 0) WR_STAMP(it, 2);
+                    if (kb == KB - 1) WR_STAMP(it, 3);
                     tc_fence_after_sync();
                     const uint32_t sa = smem_u32(sA + s * WR_STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + kb * (WR_BN * 128));
@@ -146,6 +172,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&acc_full[buf]);
+                WR_STAMP(it, 4);
             }
         }
         __syncwarp();
@@ -185,6 +212,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float f[32];
             load_addend(part * WR_CHUNKS, f);
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            if (warp == 2 && lane == 0) WR_STAMP(it, 5);
             tc_fence_after_sync();
 #pragma unroll
             for (int cc = 0; cc < WR_CHUNKS; ++cc) {
@@ -229,6 +257,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
             }
+            if (warp == 2 && lane == 0) WR_STAMP(it, 6);
             tc_fence_before_sync();
             mbar_arrive(&acc_empty[buf]);
         }
