@@ -272,7 +272,7 @@ def run_b200(args):
     def body():
         noise.normal_()
         eng.forward(z, xp, t_buf, lig_mask, pocket_mask, B, out_lig=eps, want_pocket=False)
-        eng.sampler_step(z, eps, noise, xp, coef_buf, lig_mask, pocket_mask, B, z_out=z, pocket_out=xp)
+        eng.sampler_step(z, eps, noise, xp, coef_buf, lig_mask, pocket_mask, B, z_out=z, pocket_out=xp, check_com=True)
 
     def set_step(s):
         t_buf.copy_(t_tab[s].expand(B, 1))
@@ -407,7 +407,7 @@ def run_b200(args):
             dmp = hm_p.to(dev, non_blocking=True)
             e_, _ = dyn(dz, dp, dt_, dml, dmp, n_samples=B)
             nz = torch.randn_like(dz)
-            zo, po = eng.sampler_step(dz, e_, nz, dp, dc, dml, dmp, B)
+            zo, po = eng.sampler_step(dz, e_, nz, dp, dc, dml, dmp, B, check_com=True)
             hout.copy_(zo, non_blocking=True)
             hp.copy_(po, non_blocking=True)
 

@@ -764,13 +764,13 @@ extern "C" int dndm_radius_graph(DndmEngine* e, const float* xh_lig, const float
 extern "C" int dndm_sampler_step(DndmEngine* e, const float* z_in, const float* eps, const float* noise,
                                  const float* xh_pocket_in, const float* coef, const float* grad, float lambda,
                                  const int64_t* lig_mask, const int64_t* pocket_mask, int32_t n_lig, int32_t n_pocket,
-                                 int32_t n_samples, float* z_out, float* xh_pocket_out, void* stream) {
+                                 int32_t n_samples, float* z_out, float* xh_pocket_out, int32_t check_input_com, void* stream) {
     if (!e || !z_in || !noise || !coef || !lig_mask || !z_out) return set_err(DNDM_EINVAL, "null argument");
     if (e->cfg.atom_nf != e->cfg.residue_nf) return set_err(DNDM_EINVAL, "sampler step requires atom_nf == residue_nf");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     RET_IF(prepare_batch(e, lig_mask, pocket_mask, n_lig, n_pocket, n_samples, st));
     sampler_step_kernel<<<n_samples, 128, 0, st>>>(z_in, eps ? eps : noise, noise, xh_pocket_in, coef, grad, lambda, e->lig_ptr,
-                                                   e->pok_ptr, e->cfg.atom_nf, z_out, xh_pocket_out, e->flags, eps != nullptr);
+                                                   e->pok_ptr, e->cfg.atom_nf, z_out, xh_pocket_out, e->flags, check_input_com != 0);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;

@@ -72,7 +72,7 @@ def load_library() -> ctypes.CDLL:
     lib.dndm_engine_load_weights.argtypes = [vp, ctypes.POINTER(DndmWeight), i32]
     lib.dndm_egnn_forward.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.dndm_radius_graph.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, ctypes.POINTER(i32), vp]
-    lib.dndm_sampler_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.dndm_sampler_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp, vp, i32, vp]
     lib.dndm_read_flags.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), vp]
     lib.dndm_debug_copy.argtypes = [vp, i32, vp, i64, vp]
     lib.dndm_debug_copy.restype = i64
@@ -144,7 +144,10 @@ class Engine:
             pass
 
     # -- weights -----------------------------------------------------------------------------------
+    weights_version = 0          # bumped by load_weights: captured CUDA graphs hold pointers into the packed weights
+
     def load_weights(self, state: Mapping[str, object]):
+        self.weights_version += 1
         """``state``: reference ``EGNNDynamics.state_dict()`` (tensors) or a dict of numpy arrays."""
         keep, arr = [], (DndmWeight * len(expected_keys(self.cfg)))()
         for i, (name, shape) in enumerate(expected_keys(self.cfg)):
@@ -195,7 +198,7 @@ class Engine:
         return row_ptr, col[:ne.value]
 
     def sampler_step(self, z_in, eps, noise, xh_pocket, coef, lig_mask, pocket_mask, n_samples: int, grad=None,
-                     lam: float = 0.0, z_out=None, pocket_out=None):
+                     lam: float = 0.0, z_out=None, pocket_out=None, check_com: bool = False):
         z_in = _dev_f32(z_in, 'z')
         noise = _dev_f32(noise, 'noise')
         xh_pocket = _dev_f32(xh_pocket, 'xh_pocket')
@@ -210,7 +213,8 @@ class Engine:
             pocket_out = torch.empty_like(xh_pocket)
         rc = self.lib.dndm_sampler_step(self._h, _ptr(z_in), _ptr(eps), _ptr(noise), _ptr(xh_pocket), _ptr(coef), _ptr(grad),
                                         ctypes.c_float(lam), _ptr(lig_mask), _ptr(pocket_mask), z_in.shape[0],
-                                        xh_pocket.shape[0], int(n_samples), _ptr(z_out), _ptr(pocket_out), _stream())
+                                        xh_pocket.shape[0], int(n_samples), _ptr(z_out), _ptr(pocket_out), int(bool(check_com)),
+                                        _stream())
         _check(self.lib, rc, 'dndm_sampler_step')
         return z_out, pocket_out
 

@@ -57,6 +57,7 @@ class _GraphedReverseStep:
         eng = sampler.engine
         dev = sampler.device
         self.z, self.xp = z_lig, xh_pocket                     # updated in place
+        self.lig_mask, self.pocket_mask = lig_mask, pocket_mask   # the graph reads these buffers on every replay
         self.t_buf = torch.zeros((B, 1), device=dev)
         self.coef_buf = torch.zeros((B, 3), device=dev)
 
@@ -64,7 +65,7 @@ class _GraphedReverseStep:
             eps, _ = eng.forward(self.z, self.xp, self.t_buf, lig_mask, pocket_mask, B, want_pocket=False)
             nz = torch.randn_like(self.z)
             eng.sampler_step(self.z, eps, nz, self.xp, self.coef_buf, lig_mask, pocket_mask, B, z_out=self.z,
-                             pocket_out=self.xp)
+                             pocket_out=self.xp, check_com=True)
 
         keep_z, keep_p = self.z.clone(), self.xp.clone()
         rng = torch.cuda.get_rng_state(dev)                    # the dry runs below must not consume the caller's noise stream
@@ -104,6 +105,7 @@ class ConditionalSampler:
         self.norm_values = norm_values
         self.norm_biases = norm_biases
         self.check_every_step = check_every_step
+        self._graph_cache = {}                     # (weights version, B, N_l, N_p) -> _GraphedReverseStep
         assert noise_schedule.startswith('polynomial_')
         self.gamma = polynomial_gamma(timesteps, noise_precision, float(noise_schedule.split('_')[1]))   # CPU fp32
         self.device = torch.device('cuda', self.engine.device)
@@ -154,7 +156,7 @@ class ConditionalSampler:
         coef = self.step_coefficients(self.lookup(s), self.lookup(t)).to(self.device)
         eps = self._eps(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, B)
         zs, xp = self.engine.sampler_step(zt_lig, eps, self._noise(len(ligand_mask), noise), xh0_pocket, coef,
-                                          ligand_mask, pocket_mask, B)
+                                          ligand_mask, pocket_mask, B, check_com=True)     # assert on z_t, :535
         if self.check_every_step:
             self._raise_on_flags()
         return zs, xp
@@ -305,8 +307,21 @@ class ConditionalSampler:
                 in_window = (svdd == 1 and s <= svdd_schedule[0]) or (spsa == 1 and s <= spsa_schedule[0])
                 if graphed and not in_window:
                     if gstep is None:
-                        z_lig, xh_pocket = z_lig.contiguous(), xh_pocket.contiguous()
-                        gstep = _GraphedReverseStep(self, z_lig, xh_pocket, lig_mask, pocket_mask, B)
+                        # graphs are kept across trajectories: the same pocket with the same ligand sizes (the usual
+                        # "n_samples per pocket" loop) replays the graph captured for the first batch
+                        key = (self.engine.weights_version, B, int(z_lig.shape[0]), int(xh_pocket.shape[0]))
+                        gstep = self._graph_cache.get(key)
+                        if gstep is not None and torch.equal(gstep.lig_mask, lig_mask) and \
+                                torch.equal(gstep.pocket_mask, pocket_mask):
+                            gstep.z.copy_(z_lig)
+                            gstep.xp.copy_(xh_pocket)
+                        else:
+                            gstep = _GraphedReverseStep(self, z_lig.contiguous().clone(), xh_pocket.contiguous().clone(),
+                                                        lig_mask, pocket_mask, B)
+                            if len(self._graph_cache) >= 4:
+                                self._graph_cache.pop(next(iter(self._graph_cache)))
+                            self._graph_cache[key] = gstep
+                        z_lig, xh_pocket = gstep.z, gstep.xp
                     gstep(t_all[s], coef_all[s])
                 else:
                     z_lig, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,

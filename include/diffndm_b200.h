@@ -101,11 +101,15 @@ int dndm_radius_graph(DndmEngine* e, const float* xh_lig, const float* xh_pocket
  *   z_out = z_in * coef[b][0] - coef[b][1] * eps + coef[b][2] * noise  (+ lambda * grad on coordinates)
  *   then the per-sample ligand COM is removed from z_out[:, :3] and from the pocket coordinates.
  * coef DEVICE [n_samples, 3]; eps / noise DEVICE [n_lig, 3+atom_nf] (eps may be NULL when coef[.][1] == 0);
- * grad DEVICE [n_lig, 3] or NULL.  In-place operation (z_out == z_in, pocket_out == pocket_in) is allowed. */
+ * grad DEVICE [n_lig, 3] or NULL.  In-place operation (z_out == z_in, pocket_out == pocket_in) is allowed.
+ * check_input_com != 0 reproduces assert_mean_zero_with_mask on the INPUT state (conditional_model.py:535, only the
+ * true reverse step has it): |sum of a sample's ligand coordinates| >= 1e-2 * max|coordinate| raises DNDM_FLAG_COM_DRIFT.
+ * The x0 head, the prior draw, q(z_s|x), the re-noising move and the SPSA update pass 0 (their inputs need not be
+ * COM-free). */
 int dndm_sampler_step(DndmEngine* e, const float* z_in, const float* eps, const float* noise,
                       const float* xh_pocket_in, const float* coef, const float* grad, float lambda,
                       const int64_t* lig_mask, const int64_t* pocket_mask, int32_t n_lig, int32_t n_pocket,
-                      int32_t n_samples, float* z_out, float* xh_pocket_out, void* stream);
+                      int32_t n_samples, float* z_out, float* xh_pocket_out, int32_t check_input_com, void* stream);
 
 /* Reads and clears the sticky flag word (synchronises `stream`). */
 int dndm_read_flags(DndmEngine* e, uint32_t* flags_host, void* stream);

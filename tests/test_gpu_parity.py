@@ -341,6 +341,11 @@ def test_com_drift_raises_assertion_error(dyn, dev):
     z_bad[:, 0] += 0.5
     with pytest.raises(AssertionError):
         smp.sample_p_zs_given_zt(s, t, z_bad, _t(b['xh_pocket'], dev), lm, pm, n_samples=2)
+    # the x0 head (sample_p_xh_given_z0 inside my_to_x0) takes z0 = (z_t - sigma eps)/alpha, which is not COM-free either:
+    # the reference has no assertion there (conditional_model.py:136-160)
+    smp.my_to_x0(t, z, _t(b['xh_pocket'], dev), lm, pm, 2)
+    smp.sample_p_xh_given_z0(z_bad, _t(b['xh_pocket'], dev), lm, pm, 2)
+    assert dyn.engine.read_flags() & 2 == 0
     # a forward-noising move takes inputs that are not COM-free by construction
     coef = torch.tensor([[0.9, 0.0, 0.1]], device=dev).repeat(2, 1)
     dyn.engine.sampler_step(z_bad, None, torch.randn_like(z_bad), _t(b['xh_pocket'], dev), coef, lm, pm, 2)
