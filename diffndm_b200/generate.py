@@ -1,0 +1,137 @@
+"""``generate_ligands`` operator surface on top of the engine: PDB file in, molecules out.
+
+Mirrors ``LigandPocketDDPM.generate_ligands`` (lightning_modules.py:803-949) and the batch loop of the
+``generate_ligands.py`` script (:92-108) -- same argument names and meaning -- with the pocket served from a
+``PocketCache`` (one parse + one upload per pocket instead of one per batch), the denoising loop on the B200 engine
+(``ConditionalSampler``) and the bond perception of the whole batch in one GPU launch.  Host chemistry (OpenBabel bond
+perception, RDKit sanitisation / UFF relaxation / QED-SA rewards) stays external: ``mol_builder`` and ``reward_fn`` are the
+hooks a host that has those packages plugs them into.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Mapping, Optional, Sequence
+
+import torch
+
+from . import ingest, output
+from .chem import BondPerception
+from .sampler import ConditionalSampler
+
+
+def state_dict_from_checkpoint(ckpt, prefix: str = 'ddpm.dynamics.'):
+    """Denoiser weights out of a Lightning checkpoint of the reference (``LigandPocketDDPM.load_from_checkpoint``,
+    generate_ligands.py:57-58): ``ckpt`` is a path or the loaded dict; keys ``ddpm.dynamics.*`` lose their prefix
+    (SURVEY.md section 9.1).  Returns (state, hyper_parameters or {})."""
+    if not isinstance(ckpt, Mapping):
+        ckpt = torch.load(ckpt, map_location='cpu', weights_only=False)
+    sd = ckpt.get('state_dict', ckpt)
+    state = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    if not state:
+        raise KeyError(f'no "{prefix}*" entries in the checkpoint')
+    return state, dict(ckpt.get('hyper_parameters', {}) or {})
+
+
+class LigandGenerator:
+    """The part of ``LigandPocketDDPM`` that ``generate_ligands.py`` / ``my_test.py`` / ``inpaint.py`` use at inference."""
+
+    def __init__(self, sampler: ConditionalSampler, dataset_info: Mapping[str, object],
+                 size_histogram=None, pocket_representation: str = 'full-atom',
+                 pocket_cache: Optional[ingest.PocketCache] = None,
+                 mol_builder: Optional[Callable] = None):
+        self.ddpm = sampler
+        self.dataset_info = dataset_info
+        self.device = sampler.device
+        self.x_dims = 3
+        self.atom_nf = sampler.atom_nf
+        self.pocket_representation = pocket_representation
+        self.pocket_type_encoder = dataset_info.get('pocket_encoder') or (
+            dataset_info['aa_encoder'] if pocket_representation == 'CA' else dataset_info['atom_encoder'])
+        self.size_distribution = None if size_histogram is None else ingest.DistributionNodes(size_histogram)
+        self.pockets = pocket_cache or ingest.PocketCache(self.pocket_type_encoder, self.device, pocket_representation)
+        self.perception = BondPerception(sampler.engine, dataset_info)
+        self.mol_builder = mol_builder
+
+    # lightning_modules.py:763-801 (kept as a method because callers use it as one)
+    def prepare_pocket(self, biopython_residues, repeats: int = 1):
+        return ingest.prepare_pocket(biopython_residues, repeats, pocket_type_encoder=self.pocket_type_encoder,
+                                     device=self.device, pocket_representation=self.pocket_representation)
+
+    def _com(self, x: torch.Tensor, mask: torch.Tensor, n: int) -> torch.Tensor:
+        cnt = torch.bincount(mask, minlength=n).clamp(min=1).to(x.dtype)
+        return torch.zeros((n, x.shape[1]), device=x.device, dtype=x.dtype).index_add_(0, mask, x) / cnt[:, None]
+
+    @torch.no_grad()
+    def generate_ligands(self, pdb_file, n_samples: int, pocket_ids: Optional[Sequence[str]] = None,
+                         ref_ligand: Optional[str] = None, num_nodes_lig=None, sanitize: bool = False,
+                         largest_frag: bool = False, relax_iter: int = 0, timesteps: Optional[int] = None,
+                         n_nodes_bias: int = 0, n_nodes_min: int = 0, svdd: int = 0, spsa: int = 0,
+                         reward_fn: Optional[Callable] = None, return_tensors: bool = False, **kwargs) -> List:
+        """Generate ligands given a pocket (lightning_modules.py:803-949).  ``pdb_file``, ``pocket_ids`` (list of
+        ``<chain>:<resi>``) xor ``ref_ligand`` (``<chain>:<resi>`` or an SDF path), ``num_nodes_lig`` (tensor of sizes, drawn
+        from the size prior if None), ``n_nodes_bias`` / ``n_nodes_min``, ``timesteps``, ``svdd`` (ATP) / ``spsa`` flags as
+        in the reference; ``reward_fn`` replaces the reference's in-line RDKit scoring for the guided modes.
+        Returns the list of molecules (``output.Molecule`` or whatever ``mol_builder`` returns; None results dropped)."""
+        assert (pocket_ids is None) ^ (ref_ligand is None)
+        pocket = self.pockets.get(pdb_file, pocket_ids, ref_ligand, repeats=n_samples)
+        pocket_com_before = self._com(pocket['x'], pocket['mask'], n_samples)
+        if num_nodes_lig is None:
+            if self.size_distribution is None:
+                raise ValueError('num_nodes_lig is None and no size histogram was given')
+            num_nodes_lig = self.size_distribution.sample_conditional(n1=None, n2=pocket['size'])
+        num_nodes_lig = torch.as_tensor(num_nodes_lig, device=self.device).long() + n_nodes_bias
+        num_nodes_lig = torch.clamp(num_nodes_lig, min=n_nodes_min)
+        xh_lig, xh_pocket, lig_mask, pocket_mask = self.ddpm.sample_given_pocket(
+            pocket, num_nodes_lig, timesteps=timesteps, svdd=svdd, spsa=spsa, reward_fn=reward_fn, **kwargs)
+        return self._finish(xh_lig, xh_pocket, lig_mask, pocket_mask, pocket_com_before, n_samples, sanitize,
+                            largest_frag, relax_iter, return_tensors)
+
+    @torch.no_grad()
+    def inpaint_ligands(self, pdb_file, n_samples: int, ligand: Mapping[str, torch.Tensor], lig_fixed: torch.Tensor,
+                        pocket_ids: Optional[Sequence[str]] = None, ref_ligand: Optional[str] = None,
+                        sanitize: bool = False, largest_frag: bool = False, relax_iter: int = 0,
+                        timesteps: Optional[int] = None, resamplings: int = 1, center: str = 'ligand',
+                        return_tensors: bool = False, **kwargs) -> List:
+        """The model call of ``inpaint.py:inpaint_ligand`` (inpaint.py:120-181): fixed atoms flagged in ``lig_fixed``,
+        ``ligand`` = dict x / one_hot / size / mask for ``n_samples`` copies."""
+        assert (pocket_ids is None) ^ (ref_ligand is None)
+        pocket = self.pockets.get(pdb_file, pocket_ids, ref_ligand, repeats=n_samples)
+        pocket_com_before = self._com(pocket['x'], pocket['mask'], n_samples)
+        xh_lig, xh_pocket, lig_mask, pocket_mask = self.ddpm.inpaint(
+            ligand, pocket, lig_fixed, resamplings=resamplings, timesteps=timesteps, center=center, **kwargs)
+        return self._finish(xh_lig, xh_pocket, lig_mask, pocket_mask, pocket_com_before, n_samples, sanitize,
+                            largest_frag, relax_iter, return_tensors)
+
+    def _finish(self, xh_lig, xh_pocket, lig_mask, pocket_mask, pocket_com_before, n_samples, sanitize, largest_frag,
+                relax_iter, return_tensors):
+        # move the generated molecules back to the original pocket position (:918-925)
+        pocket_com_after = self._com(xh_pocket[:, :self.x_dims], pocket_mask, n_samples)
+        shift = pocket_com_before - pocket_com_after
+        xh_pocket[:, :self.x_dims] += shift[pocket_mask]
+        xh_lig[:, :self.x_dims] += shift[lig_mask]
+        x = xh_lig[:, :self.x_dims].contiguous()
+        atom_type = xh_lig[:, self.x_dims:].argmax(1)
+        if self.mol_builder is not None:            # host chemistry of the reference, per molecule (:935-947)
+            xs, ts = x.cpu(), atom_type.cpu()
+            mols = [self.mol_builder(px, pt, self.dataset_info, sanitize=sanitize, relax_iter=relax_iter,
+                                     largest_frag=largest_frag)
+                    for px, pt in zip(ingest.batch_to_list(xs, lig_mask.cpu()), ingest.batch_to_list(ts, lig_mask.cpu()))]
+        else:
+            mols = [output.process_molecule(m, add_hydrogens=False, sanitize=sanitize, relax_iter=relax_iter,
+                                            largest_frag=largest_frag)
+                    for m in output.build_molecules(x, atom_type, lig_mask, n_samples, self.dataset_info, self.perception)]
+        mols = [m for m in mols if m is not None]
+        if return_tensors:
+            return mols, (xh_lig, xh_pocket, lig_mask, pocket_mask)
+        return mols
+
+    def generate_to_sdf(self, pdb_file, outfile, n_samples: int = 20, batch_size: Optional[int] = None,
+                        num_nodes_lig: Optional[int] = None, all_frags: bool = False, **kw) -> int:
+        """The body of the ``generate_ligands.py`` script (:92-108): ``n_samples // batch_size`` batches, largest fragment
+        unless ``all_frags``, one SDF file.  Returns the number of molecules written."""
+        batch_size = n_samples if batch_size is None else batch_size
+        sizes = None if num_nodes_lig is None else torch.ones(batch_size, dtype=torch.long) * num_nodes_lig
+        molecules = []
+        for _ in range(n_samples // batch_size):
+            molecules.extend(self.generate_ligands(pdb_file, batch_size, num_nodes_lig=sizes,
+                                                   largest_frag=not all_frags, **kw))
+        return output.write_sdf_file(outfile, molecules)

@@ -659,3 +659,68 @@ def test_graphed_sampling_matches_eager(dyn, dev):
     assert float((outs[0][0][:, 3:].argmax(1) == outs[1][0][:, 3:].argmax(1)).float().mean()) > 0.9
     assert float((outs[0][1] - outs[1][1]).abs().max()) / scale < 5e-4
     assert dyn.engine.read_flags() & 5 == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# generate_ligands surface: PDB file -> pocket cache -> sampler -> GPU bond perception -> SDF
+# ---------------------------------------------------------------------------------------------------------------
+def _write_pdb(path, px, pt, lig_xyz):
+    """Synthetic pocket as a PDB file: one GLY-named residue per 4 atoms plus a hetero ligand residue 900."""
+    names = ['C', 'N', 'O', 'S']
+    lines = []
+    for i, (p, t) in enumerate(zip(px, pt)):
+        el = names[int(t)] if int(t) < 4 else 'C'
+        lines.append(f"ATOM  {i + 1:5d}  {el + str(i % 4):<3s} GLY A{i // 4 + 1:4d}    {p[0]:8.3f}{p[1]:8.3f}{p[2]:8.3f}"
+                     f"  1.00  0.00          {el:>2s}")
+    for k, p in enumerate(lig_xyz):
+        lines.append(f"HETATM{len(px) + k + 1:5d}  C{k:<2d} LIG A 900    {p[0]:8.3f}{p[1]:8.3f}{p[2]:8.3f}  1.00  0.00           C")
+    with open(path, 'w') as f:
+        f.write('\n'.join(lines) + '\nEND\n')
+
+
+def test_generate_ligands_pdb_to_sdf(dyn, dev, tmp_path):
+    from diffndm_b200 import ingest, output, synthetic
+    from diffndm_b200.datasets import crossdock_dataset_info
+    from diffndm_b200.generate import LigandGenerator
+    from diffndm_b200.sampler import ConditionalSampler
+    info = crossdock_dataset_info()
+    px, pt = synthetic.synthetic_pocket(4, 120)
+    px = (np.round(px, 3) + np.array([12.0, -30.0, 7.5], np.float32)).astype(np.float32)     # a pocket away from the origin
+    pt = np.minimum(pt, 3)
+    pdb = tmp_path / 'pocket.pdb'
+    _write_pdb(pdb, px, pt, px.mean(0, keepdims=True) + np.array([[0, 0, 0], [1.4, 0, 0]], np.float32))
+    hist = np.zeros((40, 200))
+    hist[8:20, 100:130] = 1.0
+    gen = LigandGenerator(ConditionalSampler(dyn, timesteps=500), info, size_histogram=hist)
+    torch.manual_seed(5)
+    torch.cuda.manual_seed(5)
+    mols, (xh_lig, xh_pocket, lig_mask, pocket_mask) = gen.generate_ligands(
+        str(pdb), 4, ref_ligand='A:900', timesteps=20, n_nodes_min=9, return_tensors=True)
+    assert len(mols) == 4 and gen.pockets.misses == 1
+    sizes = torch.bincount(lig_mask).tolist()
+    assert all(9 <= s < 20 for s in sizes) and [m.GetNumAtoms() for m in mols] == sizes
+    # the pocket went back to where the PDB file has it (lightning_modules.py:918-925), the ligands sit inside it
+    n_p = int(xh_pocket.shape[0]) // 4
+    sel = ingest.pocket_arrays(ingest.get_pocket_from_ligand(ingest.parse_pdb(pdb), 'A:900'), info['atom_encoder'])[0]
+    assert n_p == len(sel)
+    assert np.abs(xh_pocket[:n_p, :3].cpu().numpy() - sel).max() < 2e-3
+    com = sel.mean(0)
+    assert all(np.linalg.norm(m.positions.mean(0) - com) < 15.0 for m in mols)
+    # bonds of every molecule = the oracle's make_mol_edm on the same coordinates (bit-exact rule evaluation)
+    x = xh_lig[:, :3].cpu().numpy()
+    types = xh_lig[:, 3:].argmax(1).cpu().numpy()
+    E_ref, _ = O.bond_orders(x, types, lig_mask.cpu().numpy(), np.asarray(info['bonds1'], np.float32),
+                             np.asarray(info['bonds2'], np.float32), np.asarray(info['bonds3'], np.float32))[:2]
+    for m, E in zip(mols, E_ref):
+        ii, jj = np.nonzero(np.tril(E, -1))
+        assert m.bonds.tolist() == np.stack([ii, jj, E[ii, jj]], 1).tolist()
+    # second batch of the same pocket: served from the cache; script body writes the SDF
+    n = gen.generate_to_sdf(str(pdb), tmp_path / 'out.sdf', n_samples=4, batch_size=2, num_nodes_lig=11, ref_ligand='A:900',
+                            timesteps=10)
+    assert n == 4 and gen.pockets.misses == 1 and gen.pockets.hits >= 2
+    back = output.read_sdf(tmp_path / 'out.sdf')
+    assert len(back) == 4 and all(1 <= m.GetNumAtoms() <= 11 for m in back)          # largest fragment of 11 atoms
+    with pytest.raises(NotImplementedError):
+        gen.generate_ligands(str(pdb), 2, ref_ligand='A:900', num_nodes_lig=torch.tensor([9, 9]), timesteps=2, sanitize=True)
+    with pytest.raises(ValueError):
+        LigandGenerator(gen.ddpm, info).generate_ligands(str(pdb), 2, ref_ligand='A:900', timesteps=2)
