@@ -72,6 +72,7 @@ class BondPerception:
                 mats.append(e_flat[off:off + k * k].view(k, k))
                 off += k * k
             out['E'] = mats
+            out['E_flat'], out['sizes'] = e_flat[:cap], sizes
         return out
 
     def keep_mask(self, stats: Mapping[str, torch.Tensor], sizes: torch.Tensor, min_fragment: float = 0.5,

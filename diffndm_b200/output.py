@@ -83,12 +83,13 @@ def build_molecules(x: torch.Tensor, atom_types: torch.Tensor, mol_mask: torch.T
     out = perception(x, atom_types, mol_mask, n_mols, return_matrices=True)
     xs = x.detach().cpu().numpy()
     ts = atom_types.detach().cpu().numpy()
-    sizes = torch.bincount(mol_mask.to(x.device), minlength=n_mols).cpu().tolist()
-    mats = [m.cpu().numpy() for m in out['E']]
-    mols, off = [], 0
-    for k, E in zip(sizes, mats):
+    e_flat = out['E_flat'].cpu().numpy()                       # one device-to-host copy for the whole batch
+    mols, off, eoff = [], 0, 0
+    for k in out['sizes'].cpu().tolist():
+        E = e_flat[eoff:eoff + k * k].reshape(k, k)
         mols.append(molecule_from_bond_matrix(xs[off:off + k, :3], ts[off:off + k], E, dataset_info['atom_decoder']))
         off += k
+        eoff += k * k
     return mols
 
 

@@ -7,11 +7,13 @@ Tolerances (BASELINE.json north_star): radius-graph edge sets bit-exact (set AND
 (< 1 over the polynomial_2 schedule), so eps_x is held to max(1e-3 A, 2e-3 relative) and the resulting
 per-step coordinates are checked against the 1e-3 A bar directly.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import load_npz_groups
+from conftest import GOLDEN, load_npz_groups
 from oracle import egnn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -724,3 +726,62 @@ def test_generate_ligands_pdb_to_sdf(dyn, dev, tmp_path):
         gen.generate_ligands(str(pdb), 2, ref_ligand='A:900', num_nodes_lig=torch.tensor([9, 9]), timesteps=2, sanitize=True)
     with pytest.raises(ValueError):
         LigandGenerator(gen.ddpm, info).generate_ligands(str(pdb), 2, ref_ligand='A:900', timesteps=2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (iv) full free-running trajectories: distribution-level comparison with the reference
+# ---------------------------------------------------------------------------------------------------------------
+def _ligand_stats(x_rel, types, sizes):
+    """Per-ligand, translation-free statistics of end-of-trajectory ligands given relative to the pocket COM."""
+    out = {'log_rg': [], 'log_com_dist': [], 'log_min_pair': []}
+    off = 0
+    for k in sizes:
+        x = x_rel[off:off + k].astype(np.float64)
+        off += k
+        c = x.mean(0)
+        out['log_rg'].append(np.log(np.sqrt(((x - c) ** 2).sum(1).mean())))
+        out['log_com_dist'].append(np.log(np.linalg.norm(c) + 1e-9))
+        d = np.sqrt(((x[:, None] - x[None]) ** 2).sum(-1))[np.triu_indices(k, 1)]
+        out['log_min_pair'].append(np.log(d.min() + 1e-9))
+    return {k: np.asarray(v) for k, v in out.items()}, np.bincount(types, minlength=10)
+
+
+def test_trajectory_distribution_vs_reference(dyn, dev):
+    """500-step free-running sampling, each side with its own Gaussian draws: the end-of-trajectory ligands of the CUDA
+    engine and of the reference (``tests/golden/distribution.npz``, 64 ligands drawn by the unmodified reference on the CPU)
+    must be statistically indistinguishable -- two-sample KS tests on per-ligand radius of gyration, distance to the pocket
+    and closest atom pair, chi-square on the atom-type histogram; each at p > 1e-3 (bar stated here; with four tests the
+    chance of a false alarm under equal distributions is < 0.4 %).  QED / SA need RDKit, which neither side has."""
+    from scipy import stats
+    from diffndm_b200.sampler import ConditionalSampler
+    z = np.load(os.path.join(GOLDEN, 'distribution.npz'))
+    sizes = z['sizes'].tolist()
+    ref_stats, ref_hist = [], np.zeros(10, np.int64)
+    for r in range(int(z['n_batches'])):
+        s, h = _ligand_stats(z['x_rel'][r], z['types'][r], sizes)
+        ref_stats.append(s)
+        ref_hist += h
+    ref = {k: np.concatenate([s[k] for s in ref_stats]) for k in ref_stats[0]}
+    px, pt = z['pocket_x'], z['pocket_t']
+    reps = 16                                                   # 16 x 16 = 256 ligands in one batch (samples are independent)
+    all_sizes = np.tile(z['sizes'], reps)
+    B, n_p = len(all_sizes), len(px)
+    onehot = np.eye(10, dtype=np.float32)[pt]
+    pocket = {'x': torch.from_numpy(np.tile(px, (B, 1))), 'one_hot': torch.from_numpy(np.tile(onehot, (B, 1))),
+              'size': torch.tensor([n_p] * B), 'mask': torch.arange(B).repeat_interleave(n_p)}
+    torch.manual_seed(77)
+    torch.cuda.manual_seed(77)
+    smp = ConditionalSampler(dyn, timesteps=500)
+    xh_l, xh_p, lm, pm = smp.sample_given_pocket(pocket, all_sizes, timesteps=500)
+    pcom = torch.zeros((B, 3), device=xh_p.device).index_add_(0, pm, xh_p[:, :3]) / n_p
+    x_rel = (xh_l[:, :3] - pcom[lm]).cpu().numpy()
+    ours, our_hist = _ligand_stats(x_rel, xh_l[:, 3:].argmax(1).cpu().numpy(), all_sizes.tolist())
+    report = {}
+    for k in ref:
+        assert np.isfinite(ours[k]).all()
+        report[k] = stats.ks_2samp(ref[k], ours[k]).pvalue
+    keep = (ref_hist + our_hist) > 0
+    report['atom_types'] = stats.chi2_contingency(np.stack([ref_hist[keep], our_hist[keep]]))[1]
+    print('distribution p-values:', {k: round(float(v), 4) for k, v in report.items()},
+          'medians ref/ours:', {k: (round(float(np.median(ref[k])), 3), round(float(np.median(ours[k])), 3)) for k in ref})
+    assert all(p > 1e-3 for p in report.values()), report
