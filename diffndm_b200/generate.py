@@ -85,19 +85,56 @@ class LigandGenerator:
         return self._finish(xh_lig, xh_pocket, lig_mask, pocket_mask, pocket_com_before, n_samples, sanitize,
                             largest_frag, relax_iter, return_tensors)
 
+    def prepare_substructure(self, ref_ligand: str, fix_atoms: Sequence[str], pdb_model):
+        """inpaint.py:47-62: the atoms to keep, as (coord [n,3] fp32, one_hot [n, atom_nf] int64).  ``fix_atoms`` is a list
+        of SDF files (all atoms of each file's first molecule) or of atom names inside the PDB residue ``ref_ligand``."""
+        enc = self.dataset_info['atom_encoder']
+        if str(fix_atoms[0]).endswith('.sdf'):
+            mols = [output.read_sdf(f)[0] for f in fix_atoms]
+            coord = torch.cat([torch.from_numpy(m.positions).float() for m in mols], dim=0)
+            types = torch.tensor([enc[a] for m in mols for a in m.symbols])
+        else:
+            chain, resi = ref_ligand.split(':')
+            hits = [r for r in pdb_model if r.chain == chain and r.id[1] == int(resi)]
+            assert len(hits) == 1
+            atoms = [a for a in hits[0].get_atoms() if a.name in set(fix_atoms)]
+            coord = torch.tensor([a.coord.tolist() for a in atoms], dtype=ingest.FLOAT_TYPE).reshape(-1, 3)
+            types = torch.tensor([enc[a.element.capitalize()] for a in atoms], dtype=torch.long)
+        return coord, torch.nn.functional.one_hot(types, num_classes=len(enc))
+
     @torch.no_grad()
-    def inpaint_ligands(self, pdb_file, n_samples: int, ligand: Mapping[str, torch.Tensor], lig_fixed: torch.Tensor,
-                        pocket_ids: Optional[Sequence[str]] = None, ref_ligand: Optional[str] = None,
-                        sanitize: bool = False, largest_frag: bool = False, relax_iter: int = 0,
-                        timesteps: Optional[int] = None, resamplings: int = 1, center: str = 'ligand',
-                        return_tensors: bool = False, **kwargs) -> List:
-        """The model call of ``inpaint.py:inpaint_ligand`` (inpaint.py:120-181): fixed atoms flagged in ``lig_fixed``,
-        ``ligand`` = dict x / one_hot / size / mask for ``n_samples`` copies."""
-        assert (pocket_ids is None) ^ (ref_ligand is None)
-        pocket = self.pockets.get(pdb_file, pocket_ids, ref_ligand, repeats=n_samples)
+    def inpaint_ligand(self, pdb_file, n_samples: int, ligand: str, fix_atoms: Sequence[str], add_n_nodes=None,
+                       svdd: int = 0, center: str = 'ligand', sanitize: bool = False, largest_frag: bool = False,
+                       relax_iter: int = 0, timesteps: Optional[int] = None, resamplings: int = 1,
+                       reward_fn: Optional[Callable] = None, return_tensors: bool = False, **kwargs) -> List:
+        """``inpaint.py:inpaint_ligand`` (inpaint.py:65-188) with the same arguments: ``ligand`` defines the pocket
+        (``<chain>:<resi>`` or an SDF path), ``fix_atoms`` the substructure to keep, ``add_n_nodes`` how many atoms to add
+        (drawn from the size prior, at least the fixed ones, if None).  ``save_traj`` (visualisation) is not offered."""
+        dev = self.device
+        pocket = self.pockets.get(pdb_file, None, ligand, repeats=n_samples)
+        x_fixed, one_hot_fixed = self.prepare_substructure(ligand, fix_atoms, ingest.parse_pdb(pdb_file))
+        n_fixed = len(x_fixed)
+        if add_n_nodes is None:
+            if self.size_distribution is None:
+                raise ValueError('add_n_nodes is None and no size histogram was given')
+            num_nodes_lig = torch.clamp(self.size_distribution.sample_conditional(n1=None, n2=pocket['size']), min=n_fixed)
+        else:
+            num_nodes_lig = torch.ones(n_samples, dtype=torch.long) * n_fixed + add_n_nodes
+        num_nodes_lig = num_nodes_lig.to(dev)
+        ligand_mask = ingest.num_nodes_to_batch_mask(len(num_nodes_lig), num_nodes_lig, dev)
+        # fixed atoms occupy the first n_fixed slots of every sample (inpaint.py:125-139)
+        starts = torch.cumsum(num_nodes_lig, 0) - num_nodes_lig
+        slot = torch.arange(len(ligand_mask), device=dev) - starts[ligand_mask]
+        is_fixed = slot < n_fixed
+        lig = {'x': torch.zeros((len(ligand_mask), self.x_dims), device=dev, dtype=ingest.FLOAT_TYPE),
+               'one_hot': torch.zeros((len(ligand_mask), self.atom_nf), device=dev, dtype=ingest.FLOAT_TYPE),
+               'size': num_nodes_lig, 'mask': ligand_mask}
+        lig['x'][is_fixed] = x_fixed.to(dev)[slot[is_fixed]]
+        lig['one_hot'][is_fixed] = one_hot_fixed.to(dev, ingest.FLOAT_TYPE)[slot[is_fixed]]
         pocket_com_before = self._com(pocket['x'], pocket['mask'], n_samples)
         xh_lig, xh_pocket, lig_mask, pocket_mask = self.ddpm.inpaint(
-            ligand, pocket, lig_fixed, resamplings=resamplings, timesteps=timesteps, center=center, **kwargs)
+            lig, pocket, is_fixed.long(), svdd=svdd, resamplings=resamplings, timesteps=timesteps, center=center,
+            reward_fn=reward_fn, **kwargs)
         return self._finish(xh_lig, xh_pocket, lig_mask, pocket_mask, pocket_com_before, n_samples, sanitize,
                             largest_frag, relax_iter, return_tensors)
 

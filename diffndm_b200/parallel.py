@@ -8,7 +8,7 @@ the CPU tests) is latency-bound and sufficient.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Iterator, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -17,6 +17,42 @@ import torch.distributed as dist
 def shard_pockets(n_pockets: int, rank: int, world: int) -> List[int]:
     """Static round-robin of pocket ids over ranks (work unit = one pocket's trajectory batch)."""
     return list(range(rank, n_pockets, world))
+
+
+class PocketQueue:
+    """Shared work queue over pocket ids for tail balance: pocket cost grows with its edge count
+    (~ atoms x degree), so a static round-robin leaves ranks idle at the end of a job.  Every rank pulls the next pocket
+    with an atomic add on the process group's key-value store -- host-side, a few bytes per pocket, no collective and
+    nothing on the denoising path.  With ``costs`` the queue hands out the most expensive pockets first (longest
+    processing time first), the order every rank derives identically from the same list.
+
+    ``store=None`` uses the default process group's store; without an initialised process group the queue is local."""
+
+    def __init__(self, n_pockets: int, costs: Optional[Sequence[float]] = None, store=None, key: str = 'dndm/pocket_queue'):
+        self.n = int(n_pockets)
+        if costs is not None:
+            assert len(costs) == self.n
+            self.order = sorted(range(self.n), key=lambda i: (-float(costs[i]), i))
+        else:
+            self.order = list(range(self.n))
+        if store is None and dist.is_available() and dist.is_initialized():
+            store = dist.distributed_c10d._get_default_store()
+        self.store = store
+        self.key = key
+        self._local = 0
+
+    def _next(self) -> int:
+        if self.store is None:
+            self._local += 1
+            return self._local - 1
+        return int(self.store.add(self.key, 1)) - 1
+
+    def __iter__(self) -> Iterator[int]:
+        while True:
+            i = self._next()
+            if i >= self.n:
+                return
+            yield self.order[i]
 
 
 def _all_gather_varlen(t: torch.Tensor, group=None) -> List[torch.Tensor]:

@@ -746,15 +746,18 @@ def _ligand_stats(x_rel, types, sizes):
     return {k: np.asarray(v) for k, v in out.items()}, np.bincount(types, minlength=10)
 
 
-def test_trajectory_distribution_vs_reference(dyn, dev):
+def test_trajectory_distribution_vs_reference(golden_weights, dev):
     """500-step free-running sampling, each side with its own Gaussian draws: the end-of-trajectory ligands of the CUDA
     engine and of the reference (``tests/golden/distribution.npz``, 64 ligands drawn by the unmodified reference on the CPU)
     must be statistically indistinguishable -- two-sample KS tests on per-ligand radius of gyration, distance to the pocket
     and closest atom pair, chi-square on the atom-type histogram; each at p > 1e-3 (bar stated here; with four tests the
     chance of a false alarm under equal distributions is < 0.4 %).  QED / SA need RDKit, which neither side has."""
     from scipy import stats
+    from diffndm_b200.engine import B200EGNNDynamics
     from diffndm_b200.sampler import ConditionalSampler
+    from diffndm_b200.weights import DynamicsConfig
     z = np.load(os.path.join(GOLDEN, 'distribution.npz'))
+    assert int(z['weight_seed']) == 0 and abs(float(z['coord_head_gain']) - 0.3) < 1e-9      # = the golden_weights fixture
     sizes = z['sizes'].tolist()
     ref_stats, ref_hist = [], np.zeros(10, np.int64)
     for r in range(int(z['n_batches'])):
@@ -771,7 +774,9 @@ def test_trajectory_distribution_vs_reference(dyn, dev):
               'size': torch.tensor([n_p] * B), 'mask': torch.arange(B).repeat_interleave(n_p)}
     torch.manual_seed(77)
     torch.cuda.manual_seed(77)
-    smp = ConditionalSampler(dyn, timesteps=500)
+    big = B200EGNNDynamics(DynamicsConfig(), golden_weights, max_nodes=B * (n_p + 16), max_edges=B * (n_p + 16) * 40,
+                           max_samples=B).eval()
+    smp = ConditionalSampler(big, timesteps=500)
     xh_l, xh_p, lm, pm = smp.sample_given_pocket(pocket, all_sizes, timesteps=500)
     pcom = torch.zeros((B, 3), device=xh_p.device).index_add_(0, pm, xh_p[:, :3]) / n_p
     x_rel = (xh_l[:, :3] - pcom[lm]).cpu().numpy()
@@ -785,3 +790,34 @@ def test_trajectory_distribution_vs_reference(dyn, dev):
     print('distribution p-values:', {k: round(float(v), 4) for k, v in report.items()},
           'medians ref/ours:', {k: (round(float(np.median(ref[k])), 3), round(float(np.median(ours[k])), 3)) for k in ref})
     assert all(p > 1e-3 for p in report.values()), report
+
+
+def test_inpaint_ligand_keeps_the_fixed_substructure(dyn, dev, tmp_path):
+    """``LigandGenerator.inpaint_ligand`` (inpaint.py:65-188 surface): the atoms named in ``fix_atoms`` keep their element
+    and their geometry (up to the p(x|z_0) head's noise), every sample gets n_fixed + add_n_nodes atoms, and the output is
+    moved back into the frame of the PDB file."""
+    from diffndm_b200 import synthetic
+    from diffndm_b200.datasets import crossdock_dataset_info
+    from diffndm_b200.generate import LigandGenerator
+    from diffndm_b200.sampler import ConditionalSampler
+    info = crossdock_dataset_info()
+    px, pt = synthetic.synthetic_pocket(6, 100)
+    px = (np.round(px, 3) + np.array([-8.0, 21.0, 3.5], np.float32)).astype(np.float32)
+    frag = px.mean(0, keepdims=True) + np.array([[0, 0, 0], [1.4, 0, 0], [2.1, 1.2, 0]], np.float32)
+    pdb = tmp_path / 'pocket.pdb'
+    _write_pdb(pdb, px, np.minimum(pt, 3), frag)
+    gen = LigandGenerator(ConditionalSampler(dyn, timesteps=500), info)
+    torch.manual_seed(11)
+    torch.cuda.manual_seed(11)
+    mols, (xh_lig, xh_pocket, lig_mask, pocket_mask) = gen.inpaint_ligand(
+        str(pdb), 3, 'A:900', ['C0', 'C2'], add_n_nodes=5, timesteps=25, resamplings=2, return_tensors=True)
+    assert len(mols) == 3 and torch.bincount(lig_mask).tolist() == [7, 7, 7]
+    d_ref = float(np.linalg.norm(frag[0] - frag[2]))
+    for b in range(3):
+        x = xh_lig[lig_mask == b][:, :3].cpu().numpy()
+        t = xh_lig[lig_mask == b][:, 3:].argmax(1).cpu().numpy()
+        assert t[0] == 0 and t[1] == 0                                          # both fixed atoms are carbons
+        assert abs(np.linalg.norm(x[0] - x[1]) - d_ref) < 0.3                   # fragment geometry kept
+        assert np.abs(x[:2] - frag[[0, 2]]).max() < 0.5                         # and it sits where the PDB file has it
+    with pytest.raises(ValueError):
+        gen.inpaint_ligand(str(pdb), 2, 'A:900', ['C0'], timesteps=5)            # no size prior, no add_n_nodes

@@ -36,9 +36,31 @@ def _worker(rank, world, port, ret):
         z3, m3, s3 = atp_select_distributed(scores_all[:0], z_all[:0], sizes_all[:0], top_k=2)
     ok = ok and s3.tolist() == [7, 5] and torch.equal(z3, exp[:12])
     ok = ok and shard_pockets(7, rank, world) == list(range(rank, 7, world))
+    # shared work queue: every pocket handed out exactly once over both ranks, most expensive first
+    from diffndm_b200.parallel import PocketQueue
+    costs = [3.0, 9.0, 1.0, 9.0, 5.0, 2.0, 7.0]
+    q = PocketQueue(7, costs=costs)
+    mine = []
+    for pid in q:
+        mine.append(pid)
+        if rank == 1:
+            import time
+            time.sleep(0.02)                     # a slow rank ends up with fewer pockets
+    got = [None, None]
+    dist.all_gather_object(got, mine)
+    ok = ok and sorted(got[0] + got[1]) == list(range(7)) and q.order == [1, 3, 6, 4, 0, 5, 2]
+    ok = ok and all(q.order.index(a) < q.order.index(b) for g in got for a, b in zip(g, g[1:]))
+    ok = ok and len(got[0]) >= len(got[1])
     ret[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_pocket_queue_local():
+    from diffndm_b200.parallel import PocketQueue
+    assert list(PocketQueue(4)) == [0, 1, 2, 3]
+    assert list(PocketQueue(3, costs=[1, 5, 5])) == [1, 2, 0]
+    assert list(PocketQueue(0)) == []
 
 
 def test_atp_selection_world2_gloo():
