@@ -65,6 +65,7 @@ def parse():
     return ap.parse_args()
 
 
+REFERENCE_BUDGET_S = 150.0     # wall-clock bound of the `--impl reference` arm
 POCKET_ATOMS = 330     # mean of the CrossDocked-shaped pocket-size distribution; same size on every rank so
                        # that the weak-scaling runs compare equal per-GPU work (geometry / ligand sizes differ per rank)
 
@@ -114,9 +115,16 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count()
-    sec, n_p = cpu_step_seconds(args.cpu_batch, args.steps, min(args.warmup, 2))
-    val = args.cpu_batch / (CALLS_PER_TRAJ * sec)
-    sample = (f'{args.steps} denoising steps (numpy oracle forward + p(z_s|z_t)) on {args.cpu_batch} ligands of the same '
+    # bounded sample: the whole --steps K --warmup W run has to end within a few minutes whatever K the caller passes, so
+    # the number of ligands per CPU step shrinks (down to 1) until K steps fit REFERENCE_BUDGET_S (cost is ~linear in it)
+    cpu_batch, warm = args.cpu_batch, min(args.warmup, 2)
+    probe, _ = cpu_step_seconds(cpu_batch, 1, 0)
+    total = probe * (args.steps + warm)
+    if total > REFERENCE_BUDGET_S:
+        cpu_batch = max(1, int(cpu_batch * REFERENCE_BUDGET_S / total))
+    sec, n_p = cpu_step_seconds(cpu_batch, args.steps, warm)
+    val = cpu_batch / (CALLS_PER_TRAJ * sec)
+    sample = (f'{args.steps} denoising steps (numpy oracle forward + p(z_s|z_t)) on {cpu_batch} ligands of the same '
               f'synthetic pocket ({n_p} atoms); per-step cost scaled to 501 calls per trajectory')
     line = {
         'impl': 'reference', 'metric': 'ligands/sec (500-step fullatom_cond sampling)', 'value': val, 'unit': 'ligands/s',
