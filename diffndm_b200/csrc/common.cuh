@@ -216,4 +216,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t 
 // Byte offset of element (row r, 16-byte unit u in [0,8)) inside a SW128 K-major tile whose rows are 128 B.
 DNDM_DEVICE uint32_t sw128_offset(uint32_t r, uint32_t u) { return r * 128u + ((u ^ (r & 7u)) << 4); }
 
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running: everything before pdl_wait() (barrier init, TMEM
+// allocation, the TMA load of the resident weights -- constant data only) overlaps the predecessor's tail; pdl_wait()
+// returns once the predecessor has completed and its writes are visible.  pdl_trigger() lets the successor be
+// scheduled as soon as SM resources free up.  Both are no-ops for a kernel launched without the attribute.
+DNDM_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DNDM_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace dndm

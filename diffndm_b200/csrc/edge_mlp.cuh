@@ -215,8 +215,7 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     const EdgeProblem& pr = second ? p1 : p0;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int E = *g.n_edges;
-    const int num_tiles = (E + EK_TILE - 1) / EK_TILE;
+    pdl_trigger();
 
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -228,6 +227,10 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         mbar_init(&tmem_empty[1], EK_EPI_WARPS * 32);
         mbar_init(a_full, EK_PROD_WARPS);
         fence_mbar_init();
+        // the resident second-layer weights are constant: their load runs under the predecessor's tail (before pdl_wait)
+        mbar_arrive_expect_tx(w_bar, EK_W2_BYTES);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     // bias step operands (K-major core matrices, no swizzle): A[r][0] = A[r][1] = 1 ; B[n][0] + B[n][1] = b2[n]
@@ -254,14 +257,15 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                  // everything below reads / writes what earlier kernels of the stream produce
+    const int E = *g.n_edges;
+    const int num_tiles = (E + EK_TILE - 1) / EK_TILE;
 
     if (warp == EK_EPI_WARPS + EK_PROD_WARPS) {
         // =========================== MMA issuer (one lane) ===========================
+        if (lane == 0 && (int)blockIdx.x >= num_tiles) mbar_wait(w_bar, 0);     // no tile: the weight load must land before exit
         if (lane == 0 && (int)blockIdx.x < num_tiles) {
             constexpr uint32_t idesc = make_idesc_bf16_f32(EK_TILE, EK_H);
-            mbar_arrive_expect_tx(w_bar, EK_W2_BYTES);
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW);
             const uint64_t ax = make_kmajor_noswz_desc(smem_u32(sAx), 128, 256), bx = make_kmajor_noswz_desc(smem_u32(sBx), 128, 256);
             int it = 0;
@@ -460,6 +464,7 @@ segment_reduce_kernel(const __nv_bfloat16* __restrict__ msg, const float* __rest
                       int n_nodes, __nv_bfloat16* __restrict__ hcat) {
     const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();                               // the node GEMM that follows may set up under this kernel's tail
     if (node >= n_nodes) return;
     const int e0 = row_ptr[node], e1 = row_ptr[node + 1];
     float acc[8];

@@ -27,6 +27,25 @@ static thread_local char g_err[512] = "";
 static int g_num_sms = 148;
 static long long g_launches = 0;   // kernels of this library launched (or captured) so far
 #define COUNT_LAUNCH(n) (g_launches += (n))
+// Programmatic dependent launch for the weight-resident kernels (edge MLP, node GEMMs): their prologue -- barrier
+// init, TMEM allocation, the 64-128 KiB TMA load of the resident weights -- runs under the tail of the previous kernel
+// of the stream (see pdl_wait / pdl_trigger in common.cuh).  DNDM_PDL=0 in the environment turns the attribute off.
+static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] == '0'); }();
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 static int set_err(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -496,7 +515,7 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
 // n_full column groups over M rows followed by n_tail groups over the first M_tail rows (see gemm_wres_kernel)
 template <int kK = 256, int kBN = 256>
 static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to16, int M,
-                       int n_full, int g0, int a_col0, const WresEpilogue& ep, int n_tail = 0, int M_tail = 0) {
+                       int n_full, int g0, int a_col0, const WresEpilogue& ep, int n_tail = 0, int M_tail = 0, bool pdl = false) {
     if (M <= 0) return DNDM_OK;
     if (M_tail <= 0) n_tail = 0;
     const int m_tiles = (M + WR_BM - 1) / WR_BM, t_tiles = (M_tail + WR_BM - 1) / WR_BM;
@@ -511,8 +530,8 @@ static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
     if (ctas_full < 1) ctas_full = 1;
     if (ctas_full > m_tiles) ctas_full = m_tiles;
     const int grid = n_full * ctas_full + n_tail * ctas_tail;
-    gemm_wres_kernel<kK, kBN><<<grid, WR_THREADS, WresShape<kK, kBN>::smem_bytes, st>>>(ta, tw, to16, M, M_tail, a_col0, g0, n_full, ctas_full,
-                                                              ctas_tail > 0 ? ctas_tail : 1, ep);
+    CU_CHECK(launch_pdl(pdl, gemm_wres_kernel<kK, kBN>, dim3(grid), dim3(WR_THREADS), WresShape<kK, kBN>::smem_bytes, st, ta, tw, to16,
+                        M, M_tail, a_col0, g0, n_full, ctas_full, ctas_tail > 0 ? ctas_tail : 1, ep));
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
@@ -610,6 +629,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     //      side stream (also under CUDA-graph capture: the fork/join events become graph edges); with per-section
     //      profiling on it stays on the main stream so that the categories time what they name. ----
     const bool fork = !e->profile;
+    const bool pdl = !e->profile;                               // per-section timing wants kernels that do not overlap
     cudaStream_t gs = fork ? e->side : st;
     if (fork) {
         CU_CHECK(cudaEventRecord(e->ev_fork, st));              // after prepare_batch (sample pointers)
@@ -656,8 +676,9 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
-            edge_mlp_kernel<true><<<dim3(e->num_sms, 1), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e, L.c_e,
-                                                                                          g, pe, pe);
+            // PDL: preceded by the merged projection GEMM (block 0) / coord_update (later blocks) on this stream
+            CU_CHECK(launch_pdl(pdl, edge_mlp_kernel<true>, dim3(e->num_sms, 1), dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_e,
+                                L.tm_w2_e, e->to_msg, L.c_e, L.c_e, g, pe, pe));
         }
         {
             ProfScope ps(e, PROF_NODE, st);
@@ -668,9 +689,9 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         {
             ProfScope ps(e, PROF_GEMM, st);
             WresEpilogue ep1{L.b3, nullptr, 0, nullptr, 0, 0, 1, 0, 1};          // hid = SiLU(W3 [h | agg] + b3), K = 512
-            RET_IF((launch_wres<512, 128>(st, e->tm_hcat, L.tm_w3, e->to_hid32, N, 2, 0, 0, ep1)));
+            RET_IF((launch_wres<512, 128>(st, e->tm_hcat, L.tm_w3, e->to_hid32, N, 2, 0, 0, ep1, 0, 0, pdl)));
             WresEpilogue ep2{L.b4, e->h, 256, e->h, 256, 0, 1, 0};       // h += W4 hid + b4 ; bf16 copy -> hcat[:, :256]
-            RET_IF((launch_wres<256, 128>(st, e->tm_hid, L.tm_w4, e->to_hcat32, N, 2, 0, 0, ep2)));
+            RET_IF((launch_wres<256, 128>(st, e->tm_hid, L.tm_w4, e->to_hcat32, N, 2, 0, 0, ep2, 0, 0, pdl)));
         }
         // ---- node projections: this block's coordinate heads (sender parts for every node, receiver parts for the
         //      ligand rows) and the next block's edge model, one weight-resident GEMM over the new h ----
@@ -679,7 +700,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             const bool has_next = l + 1 < e->cfg.n_layers;
             WresEpilogue epm{L.bias_m, nullptr, 0, nullptr, 0, 0, 1, 0};
             // column groups 0-3 over all nodes (0,1 only when a next block exists), groups 4,5 over the ligand rows only
-            RET_IF(launch_wres(st, e->tm_hcat, L.tm_wm, e->to_pq32, N, has_next ? 4 : 2, has_next ? 0 : 2, 0, epm, 2, n_lig));
+            RET_IF(launch_wres(st, e->tm_hcat, L.tm_wm, e->to_pq32, N, has_next ? 4 : 2, has_next ? 0 : 2, 0, epm, 2, n_lig, pdl));
         }
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
         {
@@ -689,8 +710,8 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
             {
                 ProfScope ps(e, PROF_HEAD, st);
-                edge_mlp_kernel<false><<<dim3(gx, 2), EK_THREADS, EK_SMEM_BYTES, st>>>(L.tm_w2_c, L.tm_w2_x, e->to_msg, L.c_c, L.c_x, gh,
-                                                                                       pc, px);
+                CU_CHECK(launch_pdl(pdl, edge_mlp_kernel<false>, dim3(gx, 2), dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_c, L.tm_w2_x,
+                                    e->to_msg, L.c_c, L.c_x, gh, pc, px));
             }
             ProfScope ps2(e, PROF_NODE, st);
             coord_update_kernel<<<(n_lig * 32 + 255) / 256, 256, 0, st>>>(x_cur, x_next, e->row_ptr, e->ecol, e->phi, e->psi,

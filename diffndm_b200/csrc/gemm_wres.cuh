@@ -100,6 +100,8 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         M = M_tail;
     }
     const int m_tiles = (M + WR_BM - 1) / WR_BM;
+    const bool has_work = cta_rank < m_tiles;
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -115,19 +117,21 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         mbar_init(w_bar, 1);
         fence_mbar_init();
+        if (has_work) {          // constant weights: loaded under the predecessor's tail (before pdl_wait)
+            mbar_arrive_expect_tx(w_bar, kK * kBN * 2);
+#pragma unroll
+            for (int kc = 0; kc < KB; ++kc) tma_load_2d(sW + kc * (WR_BN * 128), &tmap_w, w_bar, kc * 64, grp * WR_BN);
+        }
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const bool has_work = cta_rank < m_tiles;
+    pdl_wait();                  // A, the residual and every output buffer belong to earlier kernels of the stream
 
     if (warp == 0) {
         if (elect_one() && has_work) {
-            mbar_arrive_expect_tx(w_bar, kK * kBN * 2);
-#pragma unroll
-            for (int kc = 0; kc < KB; ++kc) tma_load_2d(sW + kc * (WR_BN * 128), &tmap_w, w_bar, kc * 64, grp * WR_BN);
             int kq = 0, itp = 0;
             for (int m_blk = cta_rank; m_blk < m_tiles; m_blk += cta_stride, ++itp) {
                 WR_STAMP(itp, 0);

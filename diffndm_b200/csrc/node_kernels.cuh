@@ -110,6 +110,7 @@ coord_update_kernel(const float* __restrict__ x_cur, float* __restrict__ x_next,
                     const float* __restrict__ pocket_sum, int n_lig, float norm_constant, float inv_norm) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();                               // the next block's edge kernel sets up under this kernel
     if (i >= n_lig) return;
     const int b = node_sample[i];
     // per-sample mean over ligand + pocket atoms of the CURRENT coordinates (coord2cross)
