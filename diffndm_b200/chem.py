@@ -81,3 +81,46 @@ class BondPerception:
         ``min_fragment`` of the atoms and with at most ``max_violations`` over-valent atoms."""
         frac = stats['largest_component'].float() / sizes.to(stats['largest_component'].device).clamp(min=1).float()
         return (frac >= min_fragment) & (stats['valence_violations'] <= max_violations)
+
+
+class PrefilteredReward:
+    """``reward_fn`` wrapper for the guided samplers: one ``dndm_bond_orders`` launch over all
+    candidates of an SPSA / ATP round, and only the molecules that pass ``BondPerception.keep_mask`` are handed to the
+    (expensive, host-side: OpenBabel + RDKit) scorer -- the rest get ``rejected_score``, the value the reference's
+    ``my_reward_function`` assigns to molecules it cannot build (0).  Opt-in: it changes the result only if the scorer
+    would have given a rejected molecule something else than ``rejected_score``.
+
+    ``reward_fn(x_lig [n,3], atom_types [n], lig_mask [n]) -> list[float]`` as everywhere in ``sampler.py``."""
+
+    def __init__(self, reward_fn, perception: BondPerception, rejected_score: float = 0.0, min_fragment: float = 0.5,
+                 max_violations: int = 0):
+        self.reward_fn = reward_fn
+        self.perception = perception
+        self.rejected_score = float(rejected_score)
+        self.min_fragment = min_fragment
+        self.max_violations = max_violations
+        self.scored = 0
+        self.rejected = 0
+
+    @torch.no_grad()
+    def __call__(self, x_lig: torch.Tensor, atom_types: torch.Tensor, lig_mask: torch.Tensor):
+        n = int(lig_mask.max().item()) + 1 if lig_mask.numel() else 0
+        if n == 0:
+            return []
+        x = x_lig[:, :3].contiguous().float()
+        stats = self.perception(x, atom_types, lig_mask, n, return_matrices=False)
+        sizes = torch.bincount(lig_mask, minlength=n)
+        keep = self.perception.keep_mask(stats, sizes, self.min_fragment, self.max_violations)
+        n_keep = int(keep.sum().item())
+        self.scored += n_keep
+        self.rejected += n - n_keep
+        if n_keep == n:
+            return list(self.reward_fn(x_lig, atom_types, lig_mask))
+        out = [self.rejected_score] * n
+        if n_keep:
+            atom_keep = keep[lig_mask]
+            new_id = torch.cumsum(keep.long(), 0) - 1
+            scores = self.reward_fn(x_lig[atom_keep], atom_types[atom_keep], new_id[lig_mask][atom_keep])
+            for i, s in zip(torch.nonzero(keep).flatten().tolist(), scores):
+                out[i] = float(s)
+        return out

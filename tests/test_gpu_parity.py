@@ -821,3 +821,30 @@ def test_inpaint_ligand_keeps_the_fixed_substructure(dyn, dev, tmp_path):
         assert np.abs(x[:2] - frag[[0, 2]]).max() < 0.5                         # and it sits where the PDB file has it
     with pytest.raises(ValueError):
         gen.inpaint_ligand(str(pdb), 2, 'A:900', ['C0'], timesteps=5)            # no size prior, no add_n_nodes
+
+
+def test_prefiltered_reward_scores_only_plausible_candidates(dyn, dev):
+    """``chem.PrefilteredReward``: candidates without a bonded majority fragment never reach the host scorer and get the
+    rejected score; the others are scored in their original order."""
+    from diffndm_b200.chem import BondPerception, PrefilteredReward
+    from diffndm_b200.datasets import crossdock_dataset_info
+    info = crossdock_dataset_info()
+    chain = np.array([[0, 0, 0], [1.5, 0, 0], [2.2, 1.3, 0], [3.7, 1.3, 0]], np.float32)         # C-C-C-C, all bonded
+    gas = np.array([[0, 0, 0], [6, 0, 0], [0, 6, 0], [0, 0, 6]], np.float32)                       # four lone atoms
+    x = torch.from_numpy(np.concatenate([gas, chain, gas + 1.0, chain + 2.0])).to(dev)
+    types = torch.zeros(16, dtype=torch.long, device=dev)
+    mask = torch.arange(4, device=dev).repeat_interleave(4)
+    seen = []
+
+    def scorer(xs, ts, ms):
+        seen.append((xs.cpu().numpy().copy(), ms.cpu().numpy().copy()))
+        return [10.0 + float(xs[ms == i][:, 0].mean()) for i in range(int(ms.max()) + 1)]
+
+    pre = PrefilteredReward(scorer, BondPerception(dyn.engine, info), rejected_score=-1.0)
+    out = pre(x, types, mask)
+    assert out[0] == -1.0 and out[2] == -1.0 and pre.rejected == 2 and pre.scored == 2
+    assert abs(out[1] - (10.0 + chain[:, 0].mean())) < 1e-5 and abs(out[3] - (12.0 + chain[:, 0].mean())) < 1e-5
+    assert len(seen) == 1 and seen[0][1].tolist() == [0] * 4 + [1] * 4                               # compacted ids
+    assert np.allclose(seen[0][0], np.concatenate([chain, chain + 2.0]))
+    again = pre(x[4:8], types[4:8], mask[:4])                                                        # nothing rejected: pass-through
+    assert len(again) == 1 and abs(again[0] - (10.0 + float(chain[:, 0].mean()))) < 1e-5 and len(seen) == 2
