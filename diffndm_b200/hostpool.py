@@ -30,6 +30,7 @@ class PooledReward:
         self.workers = int(workers)
         self.chunk = int(chunk)
         self._pool: Optional[ProcessPoolExecutor] = None
+        self._copy_stream = None
         if self.workers > 0:
             self._pool = ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context(start_method))
 
@@ -51,21 +52,56 @@ class PooledReward:
         bounds = np.searchsorted(mask, np.arange(n + 1))
         return [(x[bounds[i]:bounds[i + 1]], types[bounds[i]:bounds[i + 1]]) for i in range(n)]
 
-    def __call__(self, x_lig: torch.Tensor, atom_types: torch.Tensor, lig_mask: torch.Tensor) -> List[float]:
-        # one device->host transfer for the whole candidate set (coordinates, types and mask packed side by side)
-        packed = torch.cat([x_lig[:, :3].float(), atom_types.reshape(-1, 1).float(), lig_mask.reshape(-1, 1).float()], dim=1)
-        host = packed.detach().to('cpu', non_blocking=False).numpy()
+    def _to_host(self, x_lig: torch.Tensor, atom_types: torch.Tensor, lig_mask: torch.Tensor, after=None):
+        """One device->host transfer for the whole candidate set (coordinates, types and mask packed side by side).
+        ``after``: a CUDA event; the copy then runs on this pool's side stream as soon as that event has fired, without
+        waiting for work queued behind it on the producing stream."""
+        if x_lig.is_cuda and after is not None:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=x_lig.device)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(after)
+                packed = torch.cat([x_lig[:, :3].float(), atom_types.reshape(-1, 1).float(), lig_mask.reshape(-1, 1).float()],
+                                   dim=1)
+                host = torch.empty(packed.shape, dtype=packed.dtype, pin_memory=True)
+                host.copy_(packed, non_blocking=True)
+                for t in (x_lig, atom_types, lig_mask, packed):
+                    t.record_stream(self._copy_stream)
+            self._copy_stream.synchronize()
+            host = host.numpy()
+        else:
+            packed = torch.cat([x_lig[:, :3].float(), atom_types.reshape(-1, 1).float(), lig_mask.reshape(-1, 1).float()], dim=1)
+            host = packed.detach().to('cpu', non_blocking=False).numpy()
         x = np.ascontiguousarray(host[:, :3], dtype=np.float32)
         types = host[:, 3].astype(np.int64)
         mask = host[:, 4].astype(np.int64)
-        mols = self.split(x, types, mask)
+        return self.split(x, types, mask)
+
+    def submit(self, x_lig: torch.Tensor, atom_types: torch.Tensor, lig_mask: torch.Tensor, after=None) -> 'PendingScores':
+        """Non-blocking variant of ``__call__``: copies the candidates to the host (after the CUDA event ``after`` if given)
+        and hands them to the workers; ``.result()`` of the returned handle gives the scores in candidate order.  The
+        samplers use it to score one half of an SPSA round while the GPU denoises the other half."""
+        mols = self._to_host(x_lig, atom_types, lig_mask, after)
         if self._pool is None:
-            return _score_chunk((self.score_one, mols))
+            return PendingScores(None, _score_chunk((self.score_one, mols)))
         chunks = [mols[i:i + self.chunk] for i in range(0, len(mols), self.chunk)]
-        out: List[float] = []
-        for part in self._pool.map(_score_chunk, [(self.score_one, c) for c in chunks]):
-            out.extend(part)
-        return out
+        return PendingScores([self._pool.submit(_score_chunk, (self.score_one, c)) for c in chunks], None)
+
+    def __call__(self, x_lig: torch.Tensor, atom_types: torch.Tensor, lig_mask: torch.Tensor) -> List[float]:
+        return self.submit(x_lig, atom_types, lig_mask).result()
+
+
+class PendingScores:
+    def __init__(self, futures, ready):
+        self._futures, self._ready = futures, ready
+
+    def result(self) -> List[float]:
+        if self._ready is None:
+            out: List[float] = []
+            for f in self._futures:
+                out.extend(f.result())
+            self._ready = out
+        return self._ready
 
 
 def radius_of_gyration_score(x: np.ndarray, types: np.ndarray) -> float:

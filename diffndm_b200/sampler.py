@@ -105,6 +105,7 @@ class ConditionalSampler:
         self.norm_values = norm_values
         self.norm_biases = norm_biases
         self.check_every_step = check_every_step
+        self.overlap_scoring = True                # SPSA: score one half of a round on the host while the GPU denoises the other
         self._graph_cache = {}                     # (weights version, B, N_l, N_p) -> _GraphedReverseStep
         assert noise_schedule.startswith('polynomial_')
         self.gamma = polynomial_gamma(timesteps, noise_precision, float(noise_schedule.split('_')[1]))   # CPU fp32
@@ -232,10 +233,30 @@ class ConditionalSampler:
         big_pocket = xh_pocket.unsqueeze(0).repeat(reps, 1, 1).reshape(reps * n_p, -1)
         big_t = t_array.to(self.device).reshape(1, B, 1).repeat(reps, 1, 1).reshape(reps * B, 1)
         nz = None if x0_noise is None else x0_noise.reshape(reps * n_l, -1)
-        x_l, h_l, _, _ = self.my_to_x0(big_t, z_rep.reshape(reps * n_l, -1), big_pocket, big_lig_mask, big_pocket_mask,
-                                       reps * B, noise=nz)
-        rewards = torch.as_tensor(reward_fn(x_l, h_l.argmax(1), big_lig_mask), dtype=torch.float32,
-                                  device=self.device).reshape(reps, B)
+        if hasattr(reward_fn, 'submit') and self.overlap_scoring:
+            # host scoring overlapped with GPU denoising: the +U copies are denoised first and go to the scorer's worker
+            # processes (device->host copy on its side stream, gated by an event) while the GPU denoises the -U copies
+            z_flat = z_rep.reshape(reps * n_l, -1)
+            pending = []
+            for half in range(2):
+                a_l, b_l = half * k * n_l, (half + 1) * k * n_l
+                a_p, b_p = half * k * n_p, (half + 1) * k * n_p
+                a_b, b_b = half * k * B, (half + 1) * k * B
+                x_h, h_h, _, _ = self.my_to_x0(big_t[a_b:b_b], z_flat[a_l:b_l], big_pocket[a_p:b_p],
+                                               big_lig_mask[a_l:b_l] - a_b, big_pocket_mask[a_p:b_p] - a_b, k * B,
+                                               noise=None if nz is None else nz[a_l:b_l])
+                done = torch.cuda.Event()
+                done.record()
+                pending.append((x_h, h_h.argmax(1), big_lig_mask[a_l:b_l] - a_b, done))
+                if half == 1:                      # both halves are queued: hand them over in order
+                    handles = [reward_fn.submit(x, t, m, after=ev) for x, t, m, ev in pending]
+            rewards = torch.as_tensor(handles[0].result() + handles[1].result(), dtype=torch.float32,
+                                      device=self.device).reshape(reps, B)
+        else:
+            x_l, h_l, _, _ = self.my_to_x0(big_t, z_rep.reshape(reps * n_l, -1), big_pocket, big_lig_mask, big_pocket_mask,
+                                           reps * B, noise=nz)
+            rewards = torch.as_tensor(reward_fn(x_l, h_l.argmax(1), big_lig_mask), dtype=torch.float32,
+                                      device=self.device).reshape(reps, B)
         f_plus, f_minus = rewards[:k], rewards[k:]
         dd = (f_plus - f_minus) / (2 * 1e-4)                                         # hard-coded divisor, :799
         grad = (dd[:, lig_mask, None] * U).mean(0)                                   # :749-758, :801

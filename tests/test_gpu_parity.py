@@ -848,3 +848,33 @@ def test_prefiltered_reward_scores_only_plausible_candidates(dyn, dev):
     assert np.allclose(seen[0][0], np.concatenate([chain, chain + 2.0]))
     again = pre(x[4:8], types[4:8], mask[:4])                                                        # nothing rejected: pass-through
     assert len(again) == 1 and abs(again[0] - (10.0 + float(chain[:, 0].mean()))) < 1e-5 and len(seen) == 2
+
+
+def test_spsa_overlapped_scoring_matches_plain(dyn, dev):
+    """With a scorer that offers ``submit`` (hostpool.PooledReward) an SPSA round is split into its +U and -U halves: the
+    first half is scored by the worker processes while the GPU denoises the second.  Same perturbations and noise in,
+    same update out (the halves see the denoiser at another batch composition: tolerance, not bit equality)."""
+    from diffndm_b200 import synthetic
+    from diffndm_b200.hostpool import PooledReward, radius_of_gyration_score
+    from diffndm_b200.sampler import ConditionalSampler
+    px, pt = synthetic.synthetic_pocket(8, 70)
+    sizes = np.array([6, 11, 8, 9])
+    b = synthetic.make_batch(px, pt, sizes, 8)
+    k, B = 4, 4
+    rng = np.random.default_rng(3)
+    U = torch.from_numpy((1e-3 * rng.standard_normal((k, len(b['lig_mask']), 3))).astype(np.float32))
+    x0_noise = torch.from_numpy(rng.standard_normal((2 * k, len(b['lig_mask']), 13)).astype(np.float32)).to(dev)
+    smp = ConditionalSampler(dyn, timesteps=500)
+    t_arr = torch.full((B, 1), 16 / 500)
+    args = (_t(b['xh_lig'], dev), _t(b['xh_pocket'], dev), _t(b['lig_mask'], dev), _t(b['pocket_mask'], dev), t_arr, B, 1e-3)
+    with PooledReward(radius_of_gyration_score, workers=2, chunk=3) as pool:
+        submits = []
+        orig = pool.submit
+        pool.submit = lambda *a, **kw: (submits.append(kw.get('after') is not None), orig(*a, **kw))[1]
+        z1, p1 = smp.my_update_z_lig(*args, pool, guidance_scale=1e-3, k=k, perturbations=U, x0_noise=x0_noise)
+        assert submits == [True, True]                                       # two halves, each gated by its CUDA event
+        smp.overlap_scoring = False
+        z2, p2 = smp.my_update_z_lig(*args, pool, guidance_scale=1e-3, k=k, perturbations=U, x0_noise=x0_noise)
+        assert len(submits) == 3 and submits[2] is False                     # plain path: one blocking call
+    scale = max(1.0, float(z2.abs().max()))
+    assert float((z1 - z2).abs().max()) < 2e-4 * scale and float((p1 - p2).abs().max()) < 2e-4 * scale

@@ -30,3 +30,15 @@ def test_split_handles_single_molecule():
     x = np.zeros((4, 3), np.float32)
     mols = PooledReward.split(x, np.arange(4), np.zeros(4, np.int64))
     assert len(mols) == 1 and mols[0][0].shape == (4, 3)
+
+
+def test_submit_is_non_blocking_and_ordered():
+    import time
+    x, types, mask, sizes = _batch(1)
+    with PooledReward(radius_of_gyration_score, workers=2, chunk=4) as pool:
+        h1 = pool.submit(x, types, mask)
+        h2 = pool.submit(x, types, mask)
+        assert h1.result() == h2.result() == pool(x, types, mask)
+        assert h1.result() is h1.result()                                   # cached
+    serial = PooledReward(radius_of_gyration_score, workers=0)
+    assert serial.submit(x, types, mask).result() == serial(x, types, mask)
