@@ -24,11 +24,13 @@ def _score_chunk(args):
 
 
 class PooledReward:
-    def __init__(self, score_one: Callable[[np.ndarray, np.ndarray], float], workers: int = 8, chunk: int = 8,
+    def __init__(self, score_one: Callable[[np.ndarray, np.ndarray], float], workers: int = 8, chunk: Optional[int] = None,
                  start_method: str = 'spawn'):
+        """``chunk``: molecules per worker task; None = ceil(n / (2 * workers)) per call, i.e. two equal rounds over the
+        workers (a fixed chunk size leaves workers idle in the last round: 17 tasks on 8 workers take 3 rounds)."""
         self.score_one = score_one
         self.workers = int(workers)
-        self.chunk = int(chunk)
+        self.chunk = None if chunk is None else int(chunk)
         self._pool: Optional[ProcessPoolExecutor] = None
         self._copy_stream = None
         if self.workers > 0:
@@ -84,7 +86,8 @@ class PooledReward:
         mols = self._to_host(x_lig, atom_types, lig_mask, after)
         if self._pool is None:
             return PendingScores(None, _score_chunk((self.score_one, mols)))
-        chunks = [mols[i:i + self.chunk] for i in range(0, len(mols), self.chunk)]
+        step = self.chunk or max(1, -(-len(mols) // (2 * self.workers)))
+        chunks = [mols[i:i + step] for i in range(0, len(mols), step)]
         return PendingScores([self._pool.submit(_score_chunk, (self.score_one, c)) for c in chunks], None)
 
     def __call__(self, x_lig: torch.Tensor, atom_types: torch.Tensor, lig_mask: torch.Tensor) -> List[float]:

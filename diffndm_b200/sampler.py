@@ -121,6 +121,21 @@ class ConditionalSampler:
         self.alpha_tab = alp(g)
         self.gamma_dev = g.to(self.device)
 
+    def _h2d(self, t: torch.Tensor) -> torch.Tensor:
+        """Host -> device without blocking the host: a blocking ``.to(device)`` synchronises the stream, i.e. waits for every
+        kernel queued so far, which serialises the host with the GPU (and with it the overlapped host scoring).  The pinned
+        staging block is recycled by torch's host allocator only after the copy has run."""
+        if t.is_cuda:
+            return t.to(self.device)
+        return t.contiguous().pin_memory().to(self.device, non_blocking=True)
+
+    def _const_rows(self, row, n: int) -> torch.Tensor:
+        """[n, len(row)] device tensor with every row = ``row``, built by fill kernels (no host copy, no sync)."""
+        out = torch.empty((n, len(row)), device=self.device)
+        for j, v in enumerate(row):
+            out[:, j] = float(v)
+        return out
+
     def lookup(self, t: torch.Tensor) -> torch.Tensor:
         """gamma(t) with t in [0,1] -- PredefinedNoiseSchedule.forward, en_diffusion.py:1193-1195 (CPU table)."""
         return self.gamma[torch.round(t.detach().cpu().float() * self.T).long().reshape(-1)]
@@ -154,8 +169,8 @@ class ConditionalSampler:
     def sample_p_zs_given_zt(self, s, t, zt_lig, xh0_pocket, ligand_mask, pocket_mask, noise=None, n_samples=None):
         """conditional_model.py:483-540 (optimize=0; AdjustNet is training-only and off the sampling path)."""
         B = int(n_samples if n_samples is not None else t.numel())
-        coef = self.step_coefficients(self.lookup(s), self.lookup(t)).to(self.device)
-        eps = self._eps(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, B)
+        coef = self._h2d(self.step_coefficients(self.lookup(s), self.lookup(t)))
+        eps = self._eps(zt_lig, xh0_pocket, self._h2d(t), ligand_mask, pocket_mask, B)
         zs, xp = self.engine.sampler_step(zt_lig, eps, self._noise(len(ligand_mask), noise), xh0_pocket, coef,
                                           ligand_mask, pocket_mask, B, check_com=True)     # assert on z_t, :535
         if self.check_every_step:
@@ -165,12 +180,12 @@ class ConditionalSampler:
     def sample_p_xh_given_z0(self, z0_lig, xh0_pocket, lig_mask, pocket_mask, batch_size, noise=None):
         """conditional_model.py:136-160.  Returns x_lig, one-hot h_lig (int64), x_pocket, h_pocket."""
         B = int(batch_size)
+        g0 = self.lookup(torch.zeros((B, 1)))                           # CPU table: no device round trip, no host sync
         t0 = torch.zeros((B, 1), device=self.device)
-        g0 = self.lookup(t0)
         eps0 = self._eps(z0_lig, xh0_pocket, t0, lig_mask, pocket_mask, B)
         sigma_x = torch.exp(0.5 * g0)                                   # SNR(-0.5 gamma_0)
         sigma0, alpha0 = torch.sqrt(torch.sigmoid(g0)), torch.sqrt(torch.sigmoid(-g0))
-        coef = torch.stack([1.0 / alpha0, sigma0 / alpha0, sigma_x], dim=1).to(self.device)   # compute_x_pred
+        coef = self._h2d(torch.stack([1.0 / alpha0, sigma0 / alpha0, sigma_x], dim=1))        # compute_x_pred
         xh, xp = self.engine.sampler_step(z0_lig, eps0, self._noise(len(lig_mask), noise), xh0_pocket, coef, lig_mask,
                                           pocket_mask, B)
         x_lig = xh[:, :3] * self.norm_values[0]
@@ -183,10 +198,10 @@ class ConditionalSampler:
     def my_to_x0(self, t, zt_lig, xh0_pocket, ligand_mask, pocket_mask, n_samples, noise=None):
         """conditional_model.py:457-468: x0 look-ahead (two denoiser calls)."""
         B = int(n_samples)
-        eps_t = self._eps(zt_lig, xh0_pocket, t.to(self.device), ligand_mask, pocket_mask, B)
+        eps_t = self._eps(zt_lig, xh0_pocket, self._h2d(t), ligand_mask, pocket_mask, B)
         gt = self.lookup(t)
-        alpha_t = torch.exp(0.5 * F.logsigmoid(-gt)).to(self.device)
-        sigma_t = torch.sqrt(torch.sigmoid(gt)).to(self.device)
+        alpha_t = self._h2d(torch.exp(0.5 * F.logsigmoid(-gt)))
+        sigma_t = self._h2d(torch.sqrt(torch.sigmoid(gt)))
         z0 = (zt_lig - sigma_t[ligand_mask][:, None] * eps_t) / alpha_t[ligand_mask][:, None]
         return self.sample_p_xh_given_z0(z0, xh0_pocket, ligand_mask, pocket_mask, B, noise=noise)
 
@@ -197,7 +212,7 @@ class ConditionalSampler:
         z[:, :3] = x_lig
         p = torch.zeros((x_pocket.shape[0], 3 + self.atom_nf), device=self.device)
         p[:, :3] = x_pocket
-        coef = torch.tensor([[1.0, 0.0, 0.0]], device=self.device).repeat(B, 1)
+        coef = self._const_rows((1.0, 0.0, 0.0), B)
         zo, po = self.engine.sampler_step(z, None, z, p, coef, lig_mask, pocket_mask, B)
         return zo[:, :3], po[:, :3]
 
@@ -222,7 +237,7 @@ class ConditionalSampler:
             noise = torch.randn((k, n_l, 3), device=self.device)
             mean = torch.zeros((k, B, 3), device=self.device).index_add_(1, lig_mask, noise) / sizes[None, :, None]
             perturbations = zeta * (noise - mean[:, lig_mask])
-        U = perturbations.to(self.device)
+        U = self._h2d(perturbations)
         reps = 2 * k
         z_rep = z_lig.unsqueeze(0).repeat(reps, 1, 1)
         z_rep[:k, :, :3] += U
@@ -231,7 +246,9 @@ class ConditionalSampler:
         big_lig_mask = (lig_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
         big_pocket_mask = (pocket_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
         big_pocket = xh_pocket.unsqueeze(0).repeat(reps, 1, 1).reshape(reps * n_p, -1)
-        big_t = t_array.to(self.device).reshape(1, B, 1).repeat(reps, 1, 1).reshape(reps * B, 1)
+        # kept on the host: my_to_x0 looks the schedule up in the CPU table, and a device tensor there would cost a
+        # device->host copy that blocks the host until everything queued so far has run
+        big_t = t_array.detach().cpu().reshape(1, B, 1).repeat(reps, 1, 1).reshape(reps * B, 1)
         nz = None if x0_noise is None else x0_noise.reshape(reps * n_l, -1)
         if hasattr(reward_fn, 'submit') and self.overlap_scoring:
             # host scoring overlapped with GPU denoising: the +U copies are denoised first and go to the scorer's worker
@@ -245,9 +262,10 @@ class ConditionalSampler:
                 x_h, h_h, _, _ = self.my_to_x0(big_t[a_b:b_b], z_flat[a_l:b_l], big_pocket[a_p:b_p],
                                                big_lig_mask[a_l:b_l] - a_b, big_pocket_mask[a_p:b_p] - a_b, k * B,
                                                noise=None if nz is None else nz[a_l:b_l])
-                done = torch.cuda.Event()
+                types_h, mask_h = h_h.argmax(1), big_lig_mask[a_l:b_l] - a_b
+                done = torch.cuda.Event()          # recorded after EVERYTHING the scorer's copy stream will read
                 done.record()
-                pending.append((x_h, h_h.argmax(1), big_lig_mask[a_l:b_l] - a_b, done))
+                pending.append((x_h, types_h, mask_h, done))
                 if half == 1:                      # both halves are queued: hand them over in order
                     handles = [reward_fn.submit(x, t, m, after=ev) for x, t, m, ev in pending]
             rewards = torch.as_tensor(handles[0].result() + handles[1].result(), dtype=torch.float32,
@@ -261,7 +279,7 @@ class ConditionalSampler:
         dd = (f_plus - f_minus) / (2 * 1e-4)                                         # hard-coded divisor, :799
         grad = (dd[:, lig_mask, None] * U).mean(0)                                   # :749-758, :801
         # x += guidance_scale * grad ; COM removal for ligand and pocket  (:803-812)
-        coef = torch.tensor([[1.0, 0.0, 0.0]], device=self.device).repeat(B, 1)
+        coef = self._const_rows((1.0, 0.0, 0.0), B)
         return self.engine.sampler_step(z_lig, None, z_lig, xh_pocket, coef, lig_mask, pocket_mask, B, grad=grad,
                                         lam=float(guidance_scale))
 

@@ -45,7 +45,7 @@ def main():
     tl = lambda a: torch.from_numpy(a).to(dev)
     args = (tl(b['xh_lig']), tl(b['xh_pocket']), tl(b['lig_mask']), tl(b['pocket_mask']), torch.full((B, 1), 20 / 500), B, 1e-3)
     out = {'batch': B, 'pocket_atoms': n_p, 'k': k, 'molecules_per_event': 2 * k * B, 'ms_per_molecule': MS, 'workers': workers}
-    with PooledReward(slow_score, workers=workers, chunk=max(1, 2 * k * B // (4 * workers))) as pool:
+    with PooledReward(slow_score, workers=workers) as pool:
         for name, overlap in (('plain', False), ('overlapped', True), ('plain_again', False)):
             smp.overlap_scoring = overlap
             times = []
