@@ -514,9 +514,18 @@ class ConditionalSampler:
         if n_here > 0:
             big_z = torch.cat(parts_z, dim=0)
             big_p = torch.cat(parts_p, dim=0)
+            pending_r = None
+            if hasattr(reward_fn, 'submit') and self.overlap_scoring:
+                # the current candidates are scored by the worker processes while the GPU runs their x0 look-ahead
+                cand_x, cand_t = big_z[:, :3].contiguous(), big_z[:, 3:].argmax(1)
+                ready = torch.cuda.Event()
+                ready.record()
             x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(n_here, 1), big_z, big_p, big_lig_mask, big_pocket_mask, n_here * B)
+            if hasattr(reward_fn, 'submit') and self.overlap_scoring:
+                pending_r = reward_fn.submit(cand_x, cand_t, big_lig_mask, after=ready)
             r0 = torch.as_tensor(reward_fn(x0_l, h0_l.argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
-            r = torch.as_tensor(reward_fn(big_z[:, :3], big_z[:, 3:].argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
+            r = torch.as_tensor(pending_r.result() if pending_r is not None else
+                                reward_fn(big_z[:, :3], big_z[:, 3:].argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
             mixed = r0 * (s / 250) + r * (250 - s / 250)                              # [sic] :1203
         else:
             big_z = z_lig[:0]

@@ -878,3 +878,31 @@ def test_spsa_overlapped_scoring_matches_plain(dyn, dev):
         assert len(submits) == 3 and submits[2] is False                     # plain path: one blocking call
     scale = max(1.0, float(z2.abs().max()))
     assert float((z1 - z2).abs().max()) < 2e-4 * scale and float((p1 - p2).abs().max()) < 2e-4 * scale
+
+
+def test_atp_overlapped_scoring_matches_plain(dyn, dev):
+    """ATP event with a scorer that offers ``submit``: the current candidates are scored by the worker processes while
+    the GPU runs their x0 look-ahead.  Same random draws in, same winners out."""
+    from diffndm_b200 import synthetic
+    from diffndm_b200.hostpool import PooledReward, radius_of_gyration_score
+    from diffndm_b200.sampler import ConditionalSampler
+    px, pt = synthetic.synthetic_pocket(8, 50)
+    sizes = np.array([6, 9, 5, 7])
+    b = synthetic.make_batch(px, pt, sizes, 8)
+    B, G, s = 4, 3, 20
+    smp = ConditionalSampler(dyn, timesteps=500)
+    s_arr, t_arr = torch.full((B, 1), s / 500), torch.full((B, 1), (s + 1) / 500)
+    args = (s, s_arr, t_arr, _t(b['xh_lig'], dev), _t(b['xh_pocket'], dev), _t(b['lig_mask'], dev), _t(b['pocket_mask'], dev), B)
+    outs = []
+    with PooledReward(radius_of_gyration_score, workers=2) as pool:
+        gated = []
+        orig = pool.submit
+        pool.submit = lambda *a, **kw: (gated.append(kw.get('after') is not None), orig(*a, **kw))[1]
+        for overlap in (True, False):
+            smp.overlap_scoring = overlap
+            torch.manual_seed(3)
+            torch.cuda.manual_seed(3)
+            outs.append(smp._atp_event(*args, pool, G))
+    assert gated.count(True) == 1                                            # one event-gated submit in the overlapped run
+    (z1, p1, m1), (z2, p2, m2) = outs
+    assert torch.equal(m1, m2) and torch.equal(z1, z2) and torch.equal(p1, p2)
