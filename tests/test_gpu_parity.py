@@ -906,3 +906,23 @@ def test_atp_overlapped_scoring_matches_plain(dyn, dev):
     assert gated.count(True) == 1                                            # one event-gated submit in the overlapped run
     (z1, p1, m1), (z2, p2, m2) = outs
     assert torch.equal(m1, m2) and torch.equal(z1, z2) and torch.equal(p1, p2)
+
+
+def test_generate_ligands_script(dev, tmp_path):
+    """scripts/generate_ligands.py: the reference script's flags on the B200 engine (random weights: no checkpoint here)."""
+    import importlib.util
+    from diffndm_b200 import output, synthetic
+    spec = importlib.util.spec_from_file_location('b200_generate_ligands',
+                                                  os.path.join(os.path.dirname(GOLDEN), '..', 'scripts', 'generate_ligands.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    px, pt = synthetic.synthetic_pocket(12, 90)
+    px = np.round(px, 3).astype(np.float32)
+    pdb, sdf = tmp_path / 'p.pdb', tmp_path / 'o.sdf'
+    _write_pdb(pdb, px, np.minimum(pt, 3), px.mean(0, keepdims=True) + np.array([[0, 0, 0], [1.4, 0, 0]], np.float32))
+    n = mod.main(['--random_init', '0', '--pdbfile', str(pdb), '--ref_ligand', 'A:900', '--outfile', str(sdf), '--n_samples', '4',
+                  '--batch_size', '2', '--num_nodes_lig', '10', '--timesteps', '8', '--seed', '1', '--all_frags'])
+    mols = output.read_sdf(sdf)
+    assert n == 4 and len(mols) == 4 and all(m.GetNumAtoms() == 10 for m in mols)
+    with pytest.raises(SystemExit):
+        mod.main(['--random_init', '0', '--pdbfile', str(pdb), '--ref_ligand', 'A:900', '--outfile', str(sdf), '--SPSA', '1'])
