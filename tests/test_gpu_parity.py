@@ -926,3 +926,25 @@ def test_generate_ligands_script(dev, tmp_path):
     assert n == 4 and len(mols) == 4 and all(m.GetNumAtoms() == 10 for m in mols)
     with pytest.raises(SystemExit):
         mod.main(['--random_init', '0', '--pdbfile', str(pdb), '--ref_ligand', 'A:900', '--outfile', str(sdf), '--SPSA', '1'])
+
+
+def test_inpaint_script(dev, tmp_path):
+    """scripts/inpaint.py: the reference script's flags; the fixed fragment comes from an SDF file here."""
+    import importlib.util
+    from diffndm_b200 import output, synthetic
+    spec = importlib.util.spec_from_file_location('b200_inpaint', os.path.join(os.path.dirname(GOLDEN), '..', 'scripts', 'inpaint.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    px, pt = synthetic.synthetic_pocket(13, 90)
+    px = np.round(px, 3).astype(np.float32)
+    frag = px.mean(0, keepdims=True) + np.array([[0, 0, 0], [1.4, 0, 0], [2.1, 1.2, 0]], np.float32)
+    pdb, frag_sdf, sdf = tmp_path / 'p.pdb', tmp_path / 'frag.sdf', tmp_path / 'o.sdf'
+    _write_pdb(pdb, px, np.minimum(pt, 3), frag)
+    output.write_sdf_file(frag_sdf, [output.Molecule(['C', 'N'], frag[:2], np.array([[1, 0, 1]]))])
+    n = mod.main(['--random_init', '0', '--pdbfile', str(pdb), '--ref_ligand', 'A:900', '--fix_atoms', str(frag_sdf), '--outfile',
+                  str(sdf), '--n_samples', '3', '--add_n_nodes', '4', '--timesteps', '12', '--resamplings', '2', '--seed', '2'])
+    mols = output.read_sdf(sdf)
+    assert n == 3 and len(mols) == 3
+    for m in mols:
+        assert m.GetNumAtoms() == 6 and m.symbols[:2] == ['C', 'N']
+        assert np.abs(m.positions[:2] - frag[:2]).max() < 0.5
