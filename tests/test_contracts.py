@@ -34,3 +34,12 @@ def test_reference_arm_json_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'ligands/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config'] and d['vs_baseline'] is None
+
+
+def test_scripts_reject_guidance_without_a_host_reward(tmp_path):
+    """The reference-flag scripts stop at argument parsing (before any CUDA work) when guidance has no host reward."""
+    for script, extra in (('generate_ligands.py', ['--SPSA', '1']), ('inpaint.py', ['--fix_atoms', 'C1', '--svdd', '1'])):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', script), '--random_init', '0', '--pdbfile', 'x.pdb',
+                            '--ref_ligand', 'A:1', '--outfile', str(tmp_path / 'o.sdf')] + extra,
+                           capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert r.returncode == 2 and 'need' in r.stderr and '--reward' in r.stderr, r.stderr[-500:]
