@@ -81,6 +81,8 @@ def build_molecules(x: torch.Tensor, atom_types: torch.Tensor, mol_mask: torch.T
     """Batch version of ``build_molecule(*mol_pc, dataset_info, add_coords=True, use_openbabel=False)``
     (lightning_modules.py:937-941).  x [N,3] fp32 CUDA, atom_types [N] int64, mol_mask [N] sorted int64."""
     out = perception(x, atom_types, mol_mask, n_mols, return_matrices=True)
+    if n_mols and int(out['sizes'].max()) > 256:                # BOND_MAX_ATOMS of the kernel: such a block is left unwritten
+        raise ValueError('build_molecules: a molecule has more than 256 atoms')
     xs = x.detach().cpu().numpy()
     ts = atom_types.detach().cpu().numpy()
     e_flat = out['E_flat'].cpu().numpy()                       # one device-to-host copy for the whole batch
