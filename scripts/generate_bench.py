@@ -19,7 +19,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from diffndm_b200 import engine as E, ingest, output, synthetic          # noqa: E402
+from diffndm_b200 import engine as E, output, synthetic                  # noqa: E402
 from diffndm_b200.datasets import crossdock_dataset_info                  # noqa: E402
 from diffndm_b200.generate import LigandGenerator                         # noqa: E402
 from diffndm_b200.sampler import ConditionalSampler                       # noqa: E402

@@ -33,7 +33,6 @@ def test_split_handles_single_molecule():
 
 
 def test_submit_is_non_blocking_and_ordered():
-    import time
     x, types, mask, sizes = _batch(1)
     with PooledReward(radius_of_gyration_score, workers=2, chunk=4) as pool:
         h1 = pool.submit(x, types, mask)
