@@ -68,16 +68,58 @@ def parse():
     return args
 
 
+MIN_LIG_RECV_SHARE = 0.11      # ligand-receiver edges / edges below this: the ligands have left the pocket
+MIN_LAST_BLOCK_SHARE = 0.27    # last-block edges / edges
 REFERENCE_BUDGET_S = 150.0     # wall-clock bound of the `--impl reference` arm
 POCKET_ATOMS = 330     # mean of the CrossDocked-shaped pocket-size distribution; same size on every rank so
                        # that the weak-scaling runs compare equal per-GPU work (geometry / ligand sizes differ per rank)
 
 
 def make_inputs(rank, batch):
+    """Pocket, ligand sizes, the z_T batch (make_batch) and the synthetic data point x_0 in the batch's frame.
+
+    Random-init weights cannot denoise: with them alone a reverse trajectory inflates by 1/alpha_T ~ 45x and the ligands
+    leave the pocket within ~25 steps (no ligand-pocket edges left -- a degenerate, too cheap workload).  The bench therefore
+    adds the exact score of a point-mass data distribution to the network output, eps = eps_net + (z_t - alpha_t x_0) /
+    sigma_t, with x_0 a ligand-shaped point cloud in the pocket cavity (synthetic.synthetic_ligand_pose): every step is
+    then a real p(z_s | z_t) move of a trajectory that converges to x_0 like a trained model's does to a molecule, the
+    ligands stay in the pocket from z_T to z_0, and the edge counts are stationary (emitted and asserted below)."""
     from diffndm_b200 import synthetic
     px, pt = synthetic.synthetic_pocket(rank, POCKET_ATOMS)
     sizes = synthetic.synthetic_ligand_sizes(rank, batch)
-    return px, pt, sizes, synthetic.make_batch(px, pt, sizes, rank)
+    b = synthetic.make_batch(px, pt, sizes, rank)
+    n_p = len(px)
+    com = px.mean(axis=0, dtype=np.float64)
+    pose = synthetic.synthetic_ligand_pose(rank, sizes, com)
+    # make_batch moved every sample into its ligand-COM-free frame: apply the same per-sample translation to x_0
+    shift = b['xh_pocket'][::n_p, :3] - px[0][None, :]                    # [B,3]
+    pose[:, :3] += shift[b['lig_mask']]
+    b['x0_target'] = pose
+    return px, pt, sizes, b
+
+
+class SyntheticScore:
+    """eps += (z - alpha_t * x_0(frame)) / sigma_t, where x_0 follows the pocket's accumulated translation (the pocket is
+    rigid: its first atom gives the translation).  Six small torch kernels on [N_l, 13] rows inside the timed region -- work
+    the real path does not have, so the measured step is slightly pessimistic."""
+
+    def __init__(self, x0_target, xh_pocket0, lig_mask, n_p, B, dev):
+        import torch
+        self.x0 = x0_target
+        self.first = torch.arange(B, device=dev) * n_p
+        self.p0 = xh_pocket0[self.first].clone()
+        self.lig_mask = lig_mask
+        self.isig = torch.zeros(1, 1, device=dev)          # 1 / sigma_t
+        self.nais = torch.zeros(1, 1, device=dev)          # -alpha_t / sigma_t
+
+    def set_step(self, isig_t, nais_t):
+        self.isig.copy_(isig_t)
+        self.nais.copy_(nais_t)
+
+    def apply(self, eps, z, xp):
+        tgt = self.x0 + (xp[self.first] - self.p0)[self.lig_mask]
+        eps.addcmul_(z, self.isig)
+        eps.addcmul_(tgt, self.nais)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -112,18 +154,28 @@ def cpu_step_seconds(batch, n_steps, warmup, rank=0):
         sl = (b['lig_mask'] >= lo) & (b['lig_mask'] < hi)
         sp = (b['pocket_mask'] >= lo) & (b['pocket_mask'] < hi)
         parts.append({'z': b['xh_lig'][sl], 'xp': b['xh_pocket'][sp], 'lm': b['lig_mask'][sl] - lo, 'pm': b['pocket_mask'][sp] - lo,
-                      'n': int(hi - lo), 'seed': gi})
+                      'n': int(hi - lo), 'seed': gi, 'x0': b['x0_target'][sl],
+                      'first': np.arange(int(hi - lo)) * b['n_pocket'], 'p0': b['xh_pocket'][sp][::b['n_pocket']].copy()})
+    alpha_tab, sigma_tab = np.sqrt(O.sigmoid(-g)), np.sqrt(O.sigmoid(g))
+    # start where the GPU arm's timed window sits: the middle of the trajectory, z_t ~ q(z_t | x_0)
+    s_start = T_STEPS // 2
+    for part in parts:
+        nz = np.random.default_rng(77 + part['seed']).standard_normal(part['z'].shape).astype(np.float32)
+        part['z'], part['xp'] = O.noised_representation(part['x0'], part['xp'], nz, np.full(part['n'], g[s_start + 1]),
+                                                        part['lm'], part['pm'])
 
     def one(part, s):
         n = part['n']
         tt = np.full((n, 1), (s + 1) / T_STEPS, np.float32)
         eps, _ = O.dynamics_forward(W, part['z'], part['xp'], tt, part['lm'], part['pm'], cfg)
+        tgt = part['x0'] + (part['xp'][part['first']] - part['p0'])[part['lm']]   # synthetic score, as in the GPU arm (make_inputs)
+        eps = (eps + (part['z'] - alpha_tab[s + 1] * tgt) / sigma_tab[s + 1]).astype(np.float32)
         noise = np.random.default_rng(1000 * s + part['seed']).standard_normal(part['z'].shape).astype(np.float32)
         part['z'], part['xp'] = O.sample_p_zs_given_zt(part['z'], part['xp'], eps, noise, np.full(n, g[s]), np.full(n, g[s + 1]),
                                                        part['lm'], part['pm'])
 
     times = []
-    s = T_STEPS - 1
+    s = s_start
     with ThreadPoolExecutor(max_workers=groups) as pool:
         for i in range(warmup + n_steps):
             t0 = time.perf_counter()
@@ -302,15 +354,21 @@ def run_b200(args):
     coef_buf = torch.zeros(B, 3, device=dev)
     eps = torch.zeros_like(z)
     noise = torch.zeros_like(z)
+    # synthetic score (see make_inputs): 1/sigma_t and -alpha_t/sigma_t of step s -> s+1's t
+    isig_tab = (1.0 / smp.sigma_tab[1:]).to(dev)
+    nais_tab = (-smp.alpha_tab[1:] / smp.sigma_tab[1:]).to(dev)
+    score = SyntheticScore(torch.from_numpy(b['x0_target']).to(dev), p0, lig_mask, n_p // B, B, dev)
 
     def body():
         noise.normal_()
         eng.forward(z, xp, t_buf, lig_mask, pocket_mask, B, out_lig=eps, want_pocket=False)
+        score.apply(eps, z, xp)
         eng.sampler_step(z, eps, noise, xp, coef_buf, lig_mask, pocket_mask, B, z_out=z, pocket_out=xp, check_com=True)
 
     def set_step(s):
         t_buf.copy_(t_tab[s].expand(B, 1))
         coef_buf.copy_(coef_tab[s].expand(B, 3))
+        score.set_step(isig_tab[s], nais_tab[s])
 
     graph = None
     l0 = E.launch_count()
@@ -324,7 +382,8 @@ def run_b200(args):
         with torch.cuda.stream(side):
             body()
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
+        eng.set_static_masks(True)          # cache reset: the captured step derives the per-sample offsets itself, exactly
+        graph = torch.cuda.CUDAGraph()      # like the sampler's graphed reverse step (sampler._GraphedReverseStep)
         with torch.cuda.graph(graph):
             body()
 
@@ -344,12 +403,20 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up, then EXACTLY K timed steps of a real trajectory (s = T-1, T-2, ...) ----
+    # ---- the timed window is centred on the trajectory's midpoint: the reverse steps from z_T down to its upper end run
+    #      untimed (real steps, same graph), then W warm-up steps, then EXACTLY K timed steps s_hi, s_hi - 1, ...  With
+    #      K >= T the whole trajectory is timed from z_T. ----
     reset()
+    n_warm = max(args.warmup, 3)
     s = T_STEPS - 1
-    for _ in range(max(args.warmup, 3)):
+    s_hi = min(T_STEPS - 1, T_STEPS // 2 + args.steps // 2)
+    while s > s_hi + n_warm:
+        step(s)
+        s -= 1
+    for _ in range(n_warm):
         step(s)
         s = max(s - 1, 0)
+    window = [int(s), int(max(s - args.steps + 1, 0))]
     barrier()
     clocks = ClockSampler(local)
     time.sleep(0.25)
@@ -369,11 +436,18 @@ def run_b200(args):
     if flags & (E.FLAG_EDGE_OVERFLOW | E.FLAG_NAN):
         raise RuntimeError(f'engine flags {flags} during the timed region')
     E_edges, E_lig, E_last = eng.graph_stats_full()
+    # the workload is only valid while the ligands sit in the pocket: ligand-receiver edges (ligand-ligand + ligand<-pocket)
+    # and the last block's edge list (ligand receivers + their pocket senders) as shares of all edges.  The real 3rfm
+    # complex (286 pocket atoms, 23-atom ligands) has 0.13 / ~0.2-0.3; ligands that left the pocket give 0.09 / 0.10.
+    if E_lig < MIN_LIG_RECV_SHARE * E_edges or E_last < MIN_LAST_BLOCK_SHARE * E_edges:
+        raise RuntimeError(f'degenerate bench state: ligand-receiver edges {E_lig}/{E_edges}, last-block edges {E_last}/{E_edges}')
     tmax = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_per_step = tmax.item() / args.steps
     value = world * B / (CALLS_PER_TRAJ * ms_per_step * 1e-3)
+
+    s_after, z_after, xp_after = int(s), z.clone(), xp.clone()      # where the e2e loop continues the trajectory
 
     # ---- roofline: the dominant kernel, CUDA events around every launch, eager pass over the same state ----
     roof = None
@@ -394,8 +468,10 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        peak = peaks.get('bf16_tflops_sustained')
-        peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+        # each launch is timed on its own by CUDA events in a ~50 ms eager pass (no power-cap samples at full clocks): the
+        # burst figure is the applicable denominator (the sustained one belongs to seconds-long loops)
+        peak = peaks.get('bf16_tflops')
+        peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed per launch)'
         if peak is None:
             peak, peak_src = 1590.0, 'fallback (B200_PROFILING.md)'
         # six launches per forward: five over all E edges, the last over the E_last edges that still matter (exact
@@ -404,12 +480,20 @@ def run_b200(args):
         edges_timed = (g_n // n_layers) * ((n_layers - 1) * E_edges + E_last)
         t_launch = g_ms / max(g_n, 1) * 1e-3
         achieved = edges_timed * EXEC_FLOP_PER_EDGE_GCL / (g_ms * 1e-3) / 1e12
-        # DRAM traffic of the kernel from the committed `ncu --set full` capture of this exact workload
-        # (profiles/r1_edge_kernel_ncu_raw.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch); other batch sizes: null
-        traffic = (47.59e6 + 289.15e6) * (edges_timed / max(g_n, 1)) / 613e3 if (B == 100 and POCKET_ATOMS == 330) else None
+        # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of this
+        # kernel in this build, stored per edge by scripts/ncu_summary.py next to the raw pages under profiles/; a capture of
+        # another build (other kernel name / version tag) is not used
+        traffic, traffic_src = None, None
+        try:
+            cap = json.load(open(os.path.join(ROOT, 'profiles', 'gcl_traffic.json')))
+            if cap.get('kernel_version') == E.load_library().dndm_version().decode():
+                traffic = cap['dram_bytes_per_edge'] * (edges_timed / max(g_n, 1))
+                traffic_src = cap.get('source')
+        except Exception:
+            pass
         roof = {'bound': 'tensor', 'kernel': 'edge_mlp_kernel<GCL>', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': 'profiles/r1_edge_kernel_ncu_raw.txt (336.7 MB at 613k edges, scaled to the mean edges per launch)',
-                'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+                'peak_source': peak_src, 'limiter': 'XU (MUFU.TANH, two SiLU per edge and channel): see DESIGN.md section 5',
                 'us_per_launch': t_launch * 1e6, 'edges_per_launch': edges_timed / max(g_n, 1), 'edges': E_edges,
                 'edges_last_block': E_last,
                 'flop_per_edge_executed': EXEC_FLOP_PER_EDGE_GCL,
@@ -433,17 +517,21 @@ def run_b200(args):
                 off += nbytes
             return block, views
         in_spec = [(tuple(z0.shape), torch.float32), (tuple(p0.shape), torch.float32), ((B, 1), torch.float32),
-                   ((B, 3), torch.float32), ((n_l,), torch.int64), ((n_p,), torch.int64)]
+                   ((B, 3), torch.float32), ((n_l,), torch.int64), ((n_p,), torch.int64), ((1, 2), torch.float32)]
         out_spec = [(tuple(z0.shape), torch.float32), (tuple(p0.shape), torch.float32)]
         # two identical pinned input blocks used in turn: the outputs of a step (new state, translated pocket) land in the
         # leading region of the OTHER block, which is the next step's input -- the trajectory goes through host memory
         # every step without a host-side memcpy
         hb = [carve(in_spec, 'cpu', True) for _ in range(2)]
-        d_in, (dz, dp, dt_, dc, dml, dmp) = carve(in_spec, dev, False)
+        d_in, (dz, dp, dt_, dc, dml, dmp, dsc) = carve(in_spec, dev, False)
         d_out, (dzo, dpo) = carve(out_spec, dev, False)
-        for blk, (hz, hp, ht, hc, hm_l, hm_p) in hb:
-            hz.copy_(z0.cpu()); hp.copy_(p0.cpu()); hm_l.copy_(lig_mask.cpu()); hm_p.copy_(pocket_mask.cpu())
+        z_h, xp_h = z_after.cpu(), xp_after.cpu()
+        for blk, (hz, hp, ht, hc, hm_l, hm_p, hsc) in hb:
+            hz.copy_(z_h); hp.copy_(xp_h); hm_l.copy_(lig_mask.cpu()); hm_p.copy_(pocket_mask.cpu())
         coef_cpu, t_cpu = coef_tab.cpu(), t_tab.cpu()
+        sc_cpu = torch.stack([isig_tab.cpu(), nais_tab.cpu()], dim=1)              # [T,2]: 1/sigma_t, -alpha_t/sigma_t
+        score2 = SyntheticScore(score.x0, p0, dml, n_p // B, B, dev)
+        score2.isig, score2.nais = dsc[:, 0:1], dsc[:, 1:2]                        # arrive with the step's inputs
         n_e2e = min(args.steps, 50)
 
         # One step through the public API with HOST buffers: H2D of every input of the call, denoiser forward, noise draw,
@@ -453,6 +541,7 @@ def run_b200(args):
         def e2e_body(i):
             d_in.copy_(hb[i][0], non_blocking=True)
             e_, _ = dyn(dz, dp, dt_, dml, dmp, n_samples=B)
+            score2.apply(e_, dz, dp)
             nz = torch.randn_like(dz)
             eng.sampler_step(dz, e_, nz, dp, dc, dml, dmp, B, z_out=dzo, pocket_out=dpo, check_com=True)
             hb[1 - i][0][:d_out.numel()].copy_(d_out, non_blocking=True)
@@ -460,9 +549,10 @@ def run_b200(args):
         e2e_graphs = None
         eng.set_static_masks(False)                 # the masks arrive from the host on every call
         if not args.no_graph:
-            for blk, (hz, hp, ht, hc, hm_l, hm_p) in hb:
-                ht.copy_(t_cpu[T_STEPS - 1].expand(B, 1))
-                hc.copy_(coef_cpu[T_STEPS - 1].expand(B, 3))
+            for blk, (hz, hp, ht, hc, hm_l, hm_p, hsc) in hb:
+                ht.copy_(t_cpu[s_after].expand(B, 1))
+                hc.copy_(coef_cpu[s_after].expand(B, 3))
+                hsc.copy_(sc_cpu[s_after].reshape(1, 2))
             side2 = torch.cuda.Stream()
             side2.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side2):
@@ -476,14 +566,15 @@ def run_b200(args):
                     e2e_body(i)
                 e2e_graphs.append(g)
             torch.cuda.synchronize()
-            for blk, (hz, hp, ht, hc, hm_l, hm_p) in hb:      # the dry runs advanced the state: start again from z0
-                hz.copy_(z0.cpu()); hp.copy_(p0.cpu())
+            for blk, (hz, hp, ht, hc, hm_l, hm_p, hsc) in hb:      # the dry runs advanced the state: start again
+                hz.copy_(z_h); hp.copy_(xp_h)
         turn = [0]
 
         def e2e_step(s):
             i = turn[0]
             hb[i][1][2].copy_(t_cpu[s].expand(B, 1))
             hb[i][1][3].copy_(coef_cpu[s].expand(B, 3))
+            hb[i][1][6].copy_(sc_cpu[s].reshape(1, 2))
             if e2e_graphs is not None:
                 e2e_graphs[i].replay()
             else:
@@ -491,10 +582,10 @@ def run_b200(args):
             torch.cuda.synchronize()
             turn[0] = 1 - i
 
-        s3 = T_STEPS - 1
+        s3 = s_after
         for _ in range(3):
             e2e_step(s3)
-            s3 -= 1
+            s3 = max(s3 - 1, 0)
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
@@ -524,7 +615,11 @@ def run_b200(args):
     if rank == 0:
         cfgd = workload_config(B)
         cfgd.update({'pocket_atoms_rank0': n_p // B, 'ligand_atoms_rank0': n_l, 'nodes': N, 'edges': E_edges,
-                     'ligand_receiver_edges': E_lig, 'cuda_graph': graph is not None})
+                     'ligand_receiver_edges': E_lig, 'edges_last_block': E_last,
+                     'ligand_receiver_share': E_lig / E_edges, 'last_block_share': E_last / E_edges,
+                     'trajectory_window_s': window, 'cuda_graph': graph is not None,
+                     'score': 'eps_net + (z_t - alpha_t x_0)/sigma_t, x_0 = synthetic ligand pose in the pocket (random-init '
+                              'weights cannot denoise; see make_inputs)'})
         line = {
             'metric': 'ligands/sec (500-step fullatom_cond sampling)', 'value': value, 'unit': 'ligands/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,

@@ -105,6 +105,18 @@ DNDM_DEVICE uint32_t bf2_tanh(uint32_t a) {
     return d;
 }
 DNDM_DEVICE uint32_t bf2_silu_half(uint32_t h) { return bf2_fma(h, bf2_tanh(h), h); }
+// Packed fp32 pair arithmetic (FFMA2 on sm_100a): one instruction for two channels at full fp32 precision.
+DNDM_DEVICE uint64_t f2_pack(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+DNDM_DEVICE void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+DNDM_DEVICE uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 DNDM_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 // mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of burning issue slots
@@ -190,7 +202,11 @@ constexpr int EK_EPI_WARPS = 8;                     // warps 0-7: epilogue, colu
 constexpr int EK_PROD_WARPS = 16;                   // warps 8-23: producers, 8 edges of every tile each
 constexpr int EK_PROD_THREADS = EK_PROD_WARPS * 32;
 
-template <bool kGCL>
+// kBf16Radial (GCL only): assemble the whole first-layer pre-activation in bf16x2 (the round-1 producers; r^2 and r0 are
+// then ROUNDED to bf16 before they meet their weights, which costs accuracy when r^2 is large -- fully connected
+// ligand-ligand edges early in a trajectory -- or the trained radial weights are).  Default (false): P + Q in bf16x2,
+// the two radial FMAs, SiLU and the single rounding to bf16 in fp32 (FFMA2).  DNDM_GCL_BF16_RADIAL=1 selects the old path.
+template <bool kGCL, bool kBf16Radial = false>
 __global__ void __launch_bounds__(EK_THREADS, 1)
 edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
                 const __grid_constant__ CUtensorMap tmap_msg, const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,
@@ -304,13 +320,18 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
             wr[0] = a.x; wr[1] = a.y; wr[2] = a.z; wr[3] = a.w; wr[4] = b.x; wr[5] = b.y; wr[6] = b.z; wr[7] = b.w;
             w0[0] = c.x; w0[1] = c.y; w0[2] = c.z; w0[3] = c.w; w0[4] = d.x; w0[5] = d.y; w0[6] = d.z; w0[7] = d.w;
         }
-        uint32_t wr2[4], w02[4];                     // the same weights as bf16x2 pairs (GCL producers)
+        uint32_t wr2[4], w02[4];                     // the same weights as bf16x2 pairs (kBf16Radial producers)
+        uint64_t wrf[4], w0f[4];                     // ... and as fp32 pairs (FFMA2)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             wr2[i] = pack_bf16x2(wr[2 * i], wr[2 * i + 1]);
             w02[i] = pack_bf16x2(w0[2 * i], w0[2 * i + 1]);
+            wrf[i] = f2_pack(wr[2 * i], wr[2 * i + 1]);
+            w0f[i] = f2_pack(w0[2 * i], w0[2 * i + 1]);
         }
-        constexpr bool kPacked = kGCL;               // bf16x2 producer arithmetic; the coordinate heads stay fp32 (measured: packed doubles the x error)
+        constexpr bool kPacked = kGCL && kBf16Radial; // all-bf16x2 producer arithmetic
+        constexpr bool kMixed = kGCL && !kBf16Radial; // bf16x2 P + Q, fp32 radial terms and activation; the coordinate heads stay
+                                                      // fp32 throughout (measured: packed doubles the x error)
         const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
         const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
         const uint32_t ld4 = (uint32_t)g.ldpq / 8;
@@ -363,6 +384,20 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         ow[i] = bf2_silu_half(bf2_fma(w02[i], r02, bf2_fma(wr2[i], rad2, bf2_add(pw_[i], qw_[i]))));
+                    o[jj] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                } else if (kMixed) {
+                    const float rad = __int_as_float(md[jj].z), r0v = __int_as_float(md[jj].w);
+                    const uint64_t rad2 = f2_pack(rad, rad), r02 = f2_pack(r0v, r0v);
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t s2 = bf2_add(pw_[i], qw_[i]);
+                        const uint64_t pre = f2_fma(w0f[i], r02, f2_fma(wrf[i], rad2,
+                                                    f2_pack(__uint_as_float(s2 << 16), __uint_as_float(s2 & 0xffff0000u))));
+                        float lo, hi;
+                        f2_unpack(pre, lo, hi);
+                        ow[i] = pack_bf16x2(silu_half(lo), silu_half(hi));
+                    }
                     o[jj] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 } else {
                     const float rad = __int_as_float(md[jj].z), r0v = __int_as_float(md[jj].w);

@@ -31,6 +31,8 @@ static long long g_launches = 0;   // kernels of this library launched (or captu
 // init, TMEM allocation, the 64-128 KiB TMA load of the resident weights -- runs under the tail of the previous kernel
 // of the stream (see pdl_wait / pdl_trigger in common.cuh).  DNDM_PDL=0 in the environment turns the attribute off.
 static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] == '0'); }();
+// DNDM_GCL_BF16_RADIAL=1: the round-1 all-bf16x2 GCL producers (A/B measurements only; see edge_mlp.cuh)
+static bool g_bf16_radial = [] { const char* v = getenv("DNDM_GCL_BF16_RADIAL"); return v && v[0] == '1'; }();
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
@@ -261,6 +263,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     *out = e;
     return DNDM_OK;
@@ -677,8 +680,8 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         {
             ProfScope ps(e, PROF_GCL, st);
             // PDL: preceded by the merged projection GEMM (block 0) / coord_update (later blocks) on this stream
-            CU_CHECK(launch_pdl(pdl, edge_mlp_kernel<true>, dim3(e->num_sms, 1), dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_e,
-                                L.tm_w2_e, e->to_msg, L.c_e, L.c_e, g, pe, pe));
+            CU_CHECK(launch_pdl(pdl, g_bf16_radial ? edge_mlp_kernel<true, true> : edge_mlp_kernel<true, false>, dim3(e->num_sms, 1),
+                                dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e, L.c_e, g, pe, pe));
         }
         {
             ProfScope ps(e, PROF_NODE, st);

@@ -241,8 +241,11 @@ decode_kernel(const float* __restrict__ h, const float* __restrict__ x_final, co
 //   An optional guidance term  + lambda * grad  (SPSA, :801-806) is applied to the coordinates before the
 //   projection.  One CTA per sample; fixed-order reductions.  For a true reverse step (eps given) a |COM| drift of the
 //   INPUT z_t above 1e-2 of its largest coordinate raises flag bit 1 (assert_mean_zero_with_mask on zt_lig,
-//   conditional_model.py:535, en_diffusion.py:1829-1833); the prior / forward-noising / projection uses (eps == null)
-//   take inputs that are not COM-free by construction and are not checked.
+//   conditional_model.py:535 -> EnVariationalDiffusion.assert_mean_zero_with_mask, en_diffusion.py:930-935, which
+//   ConditionalDDPM inherits; only SimpleConditionalDDPM turns it off, conditional_model.py:1828-1830).  The reference divides
+//   the largest per-sample |sum| by the largest |x| of the whole batch; here every sample is tested against its OWN largest
+//   coordinate, which flags every batch the reference flags (and possibly more).  The prior / forward-noising /
+//   projection uses (eps == null) take inputs that are not COM-free by construction and are not checked.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 sampler_step_kernel(const float* z_t, const float* eps, const float* noise, const float* xh_pok_in,

@@ -218,10 +218,17 @@ class Engine:
         _check(self.lib, rc, 'dndm_sampler_step')
         return z_out, pocket_out
 
-    def read_flags(self) -> int:
+    _pending_flags = 0
+
+    def read_flags(self, consume: int = 0xFFFFFFFF) -> int:
+        """Sticky device flag word (NaN / COM drift / edge overflow / molecule too large), read and cleared on the device.
+        ``consume``: the bits the caller handles; the others stay pending on the host and are returned again by the next
+        call, so that a caller that only looks at NaN does not swallow a COM-drift bit meant for the sampler."""
         f = ctypes.c_uint32(0)
         _check(self.lib, self.lib.dndm_read_flags(self._h, ctypes.byref(f), _stream()), 'dndm_read_flags')
-        return int(f.value)
+        flags = int(f.value) | self._pending_flags
+        self._pending_flags = flags & ~consume & 0xFFFFFFFF
+        return flags
 
     # -- introspection (tests / bench) ---------------------------------------------------------------
     def set_trace(self, max_nodes: int):
@@ -324,7 +331,7 @@ class B200EGNNDynamics(torch.nn.Module):
         out_l, out_p = self.engine.forward(xh_atoms, xh_residues, t, mask_atoms, mask_residues, n_samples,
                                            want_pocket=self.compute_pocket_output)
         if self.check_nan:
-            flags = self.engine.read_flags()
+            flags = self.engine.read_flags(consume=FLAG_NAN | FLAG_EDGE_OVERFLOW)
             if flags & FLAG_EDGE_OVERFLOW:
                 raise RuntimeError('diffndm_b200: edge capacity exceeded (raise max_edges)')
             if flags & FLAG_NAN:

@@ -96,3 +96,54 @@ def atp_select_distributed(scores: torch.Tensor, z_lig: torch.Tensor, lig_sizes:
         all_pc = torch.cat(_all_gather_varlen(per_candidate.float(), group))
         return torch.cat(zs), torch.cat(ms), all_sizes[order], all_pc[order]
     return torch.cat(zs), torch.cat(ms), all_sizes[order]
+
+
+def atp_select_packed(mixed: torch.Tensor, big_z: torch.Tensor, big_p: torch.Tensor, lig_mask: torch.Tensor,
+                      pocket_mask: torch.Tensor, xh_pocket: torch.Tensor, B: int, G: int, group=None):
+    """ATP selection when the candidate groups of one pocket are split over the ranks of ``group`` (group g lives on rank
+    g % world; the ranks carry the same pre-event state).  ONE all-gather per event: every rank contributes a fixed-size
+    block [slots, B + 3 B + N_l * D] -- the mixed scores of its candidates, the ABSOLUTE position of each candidate's
+    first pocket atom (the pocket is rigid: that is its whole state) and the candidate latents -- padded with -inf scores
+    for the slots it does not own.  All ranks then rebuild the same winners, ordered like the reference's global top-k over
+    candidate index g * B + i (conditional_model.py:1203-1232; ties: lower index first).
+
+    mixed [n_here * B], big_z [n_here * N_l, D], big_p [n_here * N_p, D]: this rank's candidates, its groups in increasing
+    order.  Returns (z_lig, xh_pocket, lig_mask) of the winners."""
+    dev = xh_pocket.device
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_l, D = lig_mask.shape[0], xh_pocket.shape[1]
+    n_p = xh_pocket.shape[0] // B
+    slots = (G + world - 1) // world                                       # groups per rank, at most
+    mine = [g for g in range(G) if g % world == rank]
+    blk = B + 3 * B + n_l * D
+    buf = torch.zeros((slots, blk), device=dev)
+    buf[:, :B] = float('-inf')
+    first = torch.arange(B, device=dev) * n_p
+    for j, g in enumerate(mine):
+        buf[j, :B] = mixed[j * B:(j + 1) * B]
+        buf[j, B:4 * B] = big_p[j * B * n_p:(j + 1) * B * n_p][first, :3].reshape(-1)
+        buf[j, 4 * B:] = big_z[j * n_l:(j + 1) * n_l].reshape(-1)
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)                                 # the one collective of the event
+    out = torch.stack(outs)
+    # group g sits in block (g % world, g // world)
+    gi = torch.arange(G, device=dev)
+    blocks = out[gi % world, gi // world]                                   # [G, blk], candidate-index order
+    scores = blocks[:, :B].reshape(-1)
+    order = torch.sort(scores, descending=True, stable=True).indices[:B]
+    g_sel, i_sel = order // B, order % B
+    sizes = torch.bincount(lig_mask, minlength=B)
+    starts = torch.cumsum(sizes, 0) - sizes
+    sel_sizes = sizes[i_sel]
+    total = int(sel_sizes.sum())
+    new_m = torch.repeat_interleave(torch.arange(B, device=dev), sel_sizes, output_size=total)
+    new_starts = torch.cumsum(sel_sizes, 0) - sel_sizes
+    row = starts[i_sel][new_m] + (torch.arange(total, device=dev) - new_starts[new_m])
+    lat = blocks[:, 4 * B:].reshape(G, n_l, D)
+    z_new = lat[g_sel[new_m], row].contiguous()
+    # winners' pockets: the local pocket of the source sample as a rigid template, moved to the winner's absolute position
+    pos = blocks[:, B:4 * B].reshape(G, B, 3)[g_sel, i_sel]                  # [B,3] first-atom positions
+    tmpl = xh_pocket.reshape(B, n_p, D)[i_sel].clone()                     # [B, n_p, D]
+    tmpl[:, :, :3] += (pos - tmpl[:, 0, :3])[:, None, :]
+    return z_new, tmpl.reshape(B * n_p, D).contiguous(), new_m

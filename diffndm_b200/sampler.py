@@ -47,6 +47,41 @@ def polynomial_gamma(timesteps: int, precision: float, power: float) -> torch.Te
     return torch.from_numpy(-(np.log(alphas2) - np.log(sigmas2))).float()
 
 
+def _event_fn(reward_fn, kind: str):
+    """The reference scores SPSA rounds with my_reward_for_SPSA and ATP selections with my_reward_for_SVDD
+    (conditional_model.py:743-744, 1187, 1200): a reward object may offer both through ``for_event(kind)``
+    (rewards_rdkit.GuidanceRewards); a plain callable serves every event."""
+    return reward_fn.for_event(kind) if hasattr(reward_fn, 'for_event') else reward_fn
+
+
+class NoiseProvider:
+    """Source of the Gaussian draws of a guided trajectory, for parity tests that replay the reference's draws.  The
+    sampler batches what the reference does sequentially, so it asks for the draws of a whole event at once; an
+    implementation hands them out in whatever order its source recorded them (tests/golden/guidance_common.py walks the
+    reference's torch.randn sequence).  All returns are float32 arrays / tensors, D = 3 + atom_nf.
+
+    step(n_l)                  -> [n_l, D]                       z_T, one reverse step, the final p(x, h | z_0) head
+    spsa(k, sizes)             -> ([k, n_l, 3], [2k, n_l, D])    raw perturbation draws (one per molecule and round in the
+                                                                 reference, :771-782) and the x0 look-ahead draws, +U rounds
+                                                                 first, then -U rounds
+    atp(n_groups, n_l)         -> ([G-1, n_l, D], [G, n_l, D])   extra-candidate reverse steps; x0 look-aheads (group 0 first)
+    mixed(n_groups, k, sizes)  -> ([G-1, n_l, D], [(spsa draws)] * (G-1), [G, n_l, D])   the s == 30 branch: per extra candidate
+                                                                 its reverse step, its SPSA draws, its x0 look-ahead
+    """
+
+    def step(self, n_l):
+        raise NotImplementedError
+
+    def spsa(self, k, sizes):
+        raise NotImplementedError
+
+    def atp(self, n_groups, n_l):
+        raise NotImplementedError
+
+    def mixed(self, n_groups, k, sizes):
+        raise NotImplementedError
+
+
 class _GraphedReverseStep:
     """One unguided reverse step (denoiser forward + noise draw + fused p(z_s|z_t) update, in place on the state buffers)
     captured once in a CUDA graph and replayed with new (t, coefficient) values -- removes the ~60 kernel launches and the
@@ -56,6 +91,7 @@ class _GraphedReverseStep:
     def __init__(self, sampler: 'ConditionalSampler', z_lig, xh_pocket, lig_mask, pocket_mask, B):
         eng = sampler.engine
         dev = sampler.device
+        self.engine = eng
         self.z, self.xp = z_lig, xh_pocket                     # updated in place
         self.lig_mask, self.pocket_mask = lig_mask, pocket_mask   # the graph reads these buffers on every replay
         self.t_buf = torch.zeros((B, 1), device=dev)
@@ -74,6 +110,10 @@ class _GraphedReverseStep:
         with torch.cuda.stream(side):
             body()                                             # warm-up outside capture (allocator, layout cache)
         torch.cuda.current_stream().wait_stream(side)
+        # the captured step derives the per-sample offsets from the masks itself (cache reset -> the first prepare_batch of
+        # the body launches the two mask kernels inside the graph): a replay does not depend on what other calls left in
+        # the engine's scratch buffers
+        eng.set_static_masks(True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             body()
@@ -81,13 +121,14 @@ class _GraphedReverseStep:
         self.xp.copy_(keep_p)
         torch.cuda.synchronize(dev)
         torch.cuda.set_rng_state(rng, dev)
-        eng.read_flags()                                       # the two dry runs may have tripped the COM-drift flag
+        eng.read_flags()                                       # the dry runs may have tripped the COM-drift flag (state restored above)
 
     def __call__(self, t_dev: torch.Tensor, coef_dev: torch.Tensor):
         """t_dev: 0-d device tensor, coef_dev: [3] device tensor (same for every sample of an unguided step)."""
         self.t_buf.copy_(t_dev.expand_as(self.t_buf))
         self.coef_buf.copy_(coef_dev.expand_as(self.coef_buf))
         self.graph.replay()
+        self.engine.set_static_masks(True)      # host-side cache reset: the device scratch now holds THIS graph's layout
 
 
 class ConditionalSampler:
@@ -95,7 +136,7 @@ class ConditionalSampler:
 
     def __init__(self, dynamics: B200EGNNDynamics, timesteps: int = 500, noise_schedule: str = 'polynomial_2',
                  noise_precision: float = 5.0e-4, norm_values=(1.0, 4.0), norm_biases=(None, 0.0),
-                 check_every_step: bool = False):
+                 check_every_step: bool = False, gamma_table: Optional[torch.Tensor] = None):
         assert not dynamics.update_pocket_coords           # conditional_model.py:24
         self.dynamics = dynamics
         self.engine = dynamics.engine
@@ -107,8 +148,14 @@ class ConditionalSampler:
         self.check_every_step = check_every_step
         self.overlap_scoring = True                # SPSA: score one half of a round on the host while the GPU denoises the other
         self._graph_cache = {}                     # (weights version, B, N_l, N_p) -> _GraphedReverseStep
-        assert noise_schedule.startswith('polynomial_')
-        self.gamma = polynomial_gamma(timesteps, noise_precision, float(noise_schedule.split('_')[1]))   # CPU fp32
+        self.atp_group = None                      # torch.distributed group over which ATP candidate groups are split
+        self.cand_gen = None                       # generator of the candidate / perturbation draws (None: default generator)
+        if gamma_table is not None:               # a live reference schedule: PredefinedNoiseSchedule.gamma, en_diffusion.py:1189-1191
+            self.gamma = torch.as_tensor(gamma_table).detach().cpu().float().reshape(-1)
+            assert self.gamma.numel() == timesteps + 1
+        else:
+            assert noise_schedule.startswith('polynomial_')
+            self.gamma = polynomial_gamma(timesteps, noise_precision, float(noise_schedule.split('_')[1]))   # CPU fp32
         self.device = torch.device('cuda', self.engine.device)
         self._build_tables()
 
@@ -216,6 +263,20 @@ class ConditionalSampler:
         zo, po = self.engine.sampler_step(z, None, z, p, coef, lig_mask, pocket_mask, B)
         return zo[:, :3], po[:, :3]
 
+    def set_distributed_atp(self, group, shared_seed: int, rank_seed: Optional[int] = None):
+        """Split the ATP candidate groups of ONE trajectory over the ranks of ``group``.  The ranks must carry the same
+        trajectory state, so everything on the common path -- z_T, the reverse steps, the SPSA perturbations, the s == 30
+        chain -- draws from the default CUDA generator, seeded identically here on every rank, while the extra ATP
+        candidates of a rank come from its own generator (seed ``rank_seed``, default shared_seed + 1 + rank): identical
+        seeds there would make every rank draw the same candidates.  The engine is deterministic, so equal inputs and
+        equal draws keep the states bit-identical between events."""
+        self.atp_group = group
+        torch.cuda.manual_seed(int(shared_seed))
+        torch.manual_seed(int(shared_seed))
+        self.cand_gen = torch.Generator(device=self.device)
+        r = dist.get_rank(group) if group is not None else 0
+        self.cand_gen.manual_seed(int(shared_seed) + 1 + r if rank_seed is None else int(rank_seed))
+
     def _raise_on_flags(self):
         flags = self.engine.read_flags()
         if flags & FLAG_EDGE_OVERFLOW:
@@ -227,14 +288,18 @@ class ConditionalSampler:
 
     # -- SPSA (conditional_model.py:724-813), 2k perturbed copies batched -------------------------------------------
     def my_update_z_lig(self, z_lig, xh_pocket, lig_mask, pocket_mask, t_array, n_samples, zeta, reward_fn,
-                        guidance_scale=1e-3, k=10, perturbations=None, x0_noise=None):
+                        guidance_scale=1e-3, k=10, perturbations=None, x0_noise=None, perturbation_noise=None,
+                        generator=None):
         """Symmetric finite-difference guidance.  The reference runs 2k x my_to_x0 sequentially (:764-800); here the
         2k copies are concatenated along the batch axis: ONE denoiser call at t and ONE at t=0 on 2k*B samples.
-        ``perturbations`` [k, N_l, 3] / ``x0_noise`` [2k, N_l, 13] may be injected for parity tests."""
+        For parity tests ``perturbation_noise`` [k, N_l, 3] (the raw draws, centred and scaled here) or ``perturbations``
+        [k, N_l, 3] (already zeta * centred) and ``x0_noise`` [2k, N_l, 13] (+U rounds first) may be injected."""
         B, n_l, n_p = int(n_samples), z_lig.shape[0], xh_pocket.shape[0]
+        reward_fn = _event_fn(reward_fn, 'spsa')
         sizes = torch.bincount(lig_mask, minlength=B)
         if perturbations is None:                                                   # my_perturbation_for_molecule :724-736
-            noise = torch.randn((k, n_l, 3), device=self.device)
+            noise = (torch.randn((k, n_l, 3), device=self.device, generator=generator) if perturbation_noise is None
+                     else self._h2d(torch.as_tensor(perturbation_noise, dtype=torch.float32)))
             mean = torch.zeros((k, B, 3), device=self.device).index_add_(1, lig_mask, noise) / sizes[None, :, None]
             perturbations = zeta * (noise - mean[:, lig_mask])
         U = self._h2d(perturbations)
@@ -249,7 +314,9 @@ class ConditionalSampler:
         # kept on the host: my_to_x0 looks the schedule up in the CPU table, and a device tensor there would cost a
         # device->host copy that blocks the host until everything queued so far has run
         big_t = t_array.detach().cpu().reshape(1, B, 1).repeat(reps, 1, 1).reshape(reps * B, 1)
-        nz = None if x0_noise is None else x0_noise.reshape(reps * n_l, -1)
+        if x0_noise is None and generator is not None:
+            x0_noise = torch.randn((reps, n_l, self.n_dims + self.atom_nf), device=self.device, generator=generator)
+        nz = None if x0_noise is None else self._h2d(torch.as_tensor(x0_noise, dtype=torch.float32)).reshape(reps * n_l, -1)
         if hasattr(reward_fn, 'submit') and self.overlap_scoring:
             # host scoring overlapped with GPU denoising: the +U copies are denoised first and go to the scorer's worker
             # processes (device->host copy on its side stream, gated by an event) while the GPU denoises the -U copies
@@ -276,8 +343,9 @@ class ConditionalSampler:
             rewards = torch.as_tensor(reward_fn(x_l, h_l.argmax(1), big_lig_mask), dtype=torch.float32,
                                       device=self.device).reshape(reps, B)
         f_plus, f_minus = rewards[:k], rewards[k:]
+        self.last_spsa_rewards = (f_plus, f_minus)                                  # introspection (tests, logging)
         dd = (f_plus - f_minus) / (2 * 1e-4)                                         # hard-coded divisor, :799
-        grad = (dd[:, lig_mask, None] * U).mean(0)                                   # :749-758, :801
+        grad = (dd[:, lig_mask, None] * U).sum(0) / k                                # :749-758, :801 (sum, then / len)
         # x += guidance_scale * grad ; COM removal for ligand and pocket  (:803-812)
         coef = self._const_rows((1.0, 0.0, 0.0), B)
         return self.engine.sampler_step(z_lig, None, z_lig, xh_pocket, coef, lig_mask, pocket_mask, B, grad=grad,
@@ -297,37 +365,58 @@ class ConditionalSampler:
     # -- the sampling loop -------------------------------------------------------------------------------------------
     @torch.no_grad()
     def sample_given_pocket(self, pocket, num_nodes_lig, timesteps: Optional[int] = None, svdd: int = 0, spsa: int = 0,
-                            reward_fn: Optional[Callable] = None, noise: Optional[torch.Tensor] = None,
+                            reward_fn: Optional[Callable] = None, noise=None,
                             spsa_schedule=(30, 2), svdd_schedule=(50, 10), svdd_groups: int = 5, spsa_k: int = 10,
-                            use_cuda_graph: bool = True):
+                            use_cuda_graph: bool = True, mixed_at: Optional[int] = 30, resume=None, stop_after: int = 0):
         """ConditionalDDPM.sample_given_pocket (conditional_model.py:886-1489) without the host chemistry arguments.
 
         ``pocket``: dict with 'x' [N_p,3], 'one_hot' [N_p,residue_nf], 'size' [B], 'mask' [N_p] (prepare_pocket layout,
-        lightning_modules.py:763-801).  ``noise`` [timesteps+2, N_l, 13] injects the Gaussian draws in the reference's
-        order (z_T, one per step, final head) -- only valid for the unguided path.
+        lightning_modules.py:763-801).  ``noise``: either a tensor [timesteps+2, N_l, 13] with the Gaussian draws of an
+        UNGUIDED run in the reference's order (z_T, one per step, final head) or a ``NoiseProvider`` (guided runs).
+        Event order inside one step follows the reference: reverse step, ATP event (svdd, s <= 50, s % 10 == 0; :1085-1241),
+        SPSA update (spsa, s <= 30, s % 2 == 0; :1243-1259) and, at s == ``mixed_at`` (30) with spsa on, the mixed branch
+        (:1261-1418); every event is followed by the reference's feature rescaling (:1235-1240).
         ``use_cuda_graph``: replay the unguided reverse step from a CUDA graph (re-captured after every ATP event, whose
         re-batching changes the masks); the NaN / COM-drift flags are then checked at guidance events and at the end
         instead of at the failing step (``check_every_step=True`` keeps the reference's per-step behaviour, eagerly).
+        ``resume`` = (z_lig, xh_pocket, lig_mask, s_next): continue a trajectory from a saved state (checkpoint / resume);
+        ``stop_after`` = s: return the latent state (z_lig, xh_pocket, lig_mask, pocket_mask) after the events of step s.
         Returns (xh_lig [N_l, 3+atom_nf] with one-hot features, xh_pocket, lig_mask, pocket_mask) like the reference.
         """
         timesteps = self.T if timesteps is None else timesteps
         dev = self.device
         B = len(pocket['size'])
+        provider = noise if isinstance(noise, NoiseProvider) else None
+        table = None if provider is not None else noise
         x_p = pocket['x'].to(dev, torch.float32) / self.norm_values[0]
         h_p = (pocket['one_hot'].to(dev).float() - self.norm_biases[1]) / self.norm_values[1]
         pocket_mask = pocket['mask'].to(dev).long()
         xh0_pocket = torch.cat([x_p, h_p], dim=1).contiguous()
-        sizes = torch.as_tensor(num_nodes_lig, device=dev).long()
-        lig_mask = torch.repeat_interleave(torch.arange(B, device=dev), sizes)          # utils.py:145-153
-        n_l = int(lig_mask.numel())
-        # z_T ~ N(pocket COM, I), projected to the ligand-COM-free subspace (:923-930)
-        cnt = torch.bincount(pocket_mask, minlength=B).clamp(min=1).float()
-        mu_x = torch.zeros((B, 3), device=dev).index_add_(0, pocket_mask, x_p) / cnt[:, None]
-        mu = torch.cat([mu_x, torch.zeros((B, self.atom_nf), device=dev)], dim=1)[lig_mask].contiguous()
-        ident = torch.tensor([[1.0, 0.0, 1.0]], device=dev).repeat(B, 1)
-        z_lig, xh_pocket = self.engine.sampler_step(mu, None, self._noise(n_l, None if noise is None else noise[0]),
-                                                    xh0_pocket, ident, lig_mask, pocket_mask, B)
         step = 0
+
+        def step_noise(n):
+            if provider is not None:
+                return self._h2d(torch.as_tensor(provider.step(n), dtype=torch.float32))
+            return None if table is None else table[step]
+
+        if resume is None:
+            sizes = torch.as_tensor(num_nodes_lig, device=dev).long()
+            lig_mask = torch.repeat_interleave(torch.arange(B, device=dev), sizes)          # utils.py:145-153
+            n_l = int(lig_mask.numel())
+            # z_T ~ N(pocket COM, I), projected to the ligand-COM-free subspace (:923-930)
+            cnt = torch.bincount(pocket_mask, minlength=B).clamp(min=1).float()
+            mu_x = torch.zeros((B, 3), device=dev).index_add_(0, pocket_mask, x_p) / cnt[:, None]
+            mu = torch.cat([mu_x, torch.zeros((B, self.atom_nf), device=dev)], dim=1)[lig_mask].contiguous()
+            ident = torch.tensor([[1.0, 0.0, 1.0]], device=dev).repeat(B, 1)
+            z_lig, xh_pocket = self.engine.sampler_step(mu, None, self._noise(n_l, step_noise(n_l)), xh0_pocket, ident,
+                                                        lig_mask, pocket_mask, B)
+            s_first = timesteps - 1
+        else:
+            z_lig, xh_pocket, lig_mask, s_first = resume
+            z_lig = z_lig.to(dev, torch.float32).contiguous()
+            xh_pocket = xh_pocket.to(dev, torch.float32).contiguous()
+            lig_mask = lig_mask.to(dev).long()
+            step = timesteps - 1 - int(s_first)
         self.engine.set_static_masks(True)          # lig_mask / pocket_mask are fixed tensors between ATP events
         graphed = use_cuda_graph and noise is None and not self.check_every_step
         gstep = None
@@ -337,7 +426,7 @@ class ConditionalSampler:
             t_all = ((s_all + 1) / timesteps).to(dev)
         nan_check, self.dynamics.check_nan = self.dynamics.check_nan, (self.dynamics.check_nan and not graphed)
         try:
-            for s in reversed(range(0, timesteps)):
+            for s in reversed(range(stop_after, int(s_first) + 1)):
                 s_array = torch.full((B, 1), fill_value=s, dtype=torch.float32) / timesteps
                 t_array = torch.full((B, 1), fill_value=s + 1, dtype=torch.float32) / timesteps
                 step += 1
@@ -364,13 +453,13 @@ class ConditionalSampler:
                     gstep(t_all[s], coef_all[s])
                 else:
                     z_lig, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
-                                                                 noise=None if noise is None else noise[step], n_samples=B)
+                                                                 noise=step_noise(int(lig_mask.numel())), n_samples=B)
                 if svdd == 1 and s <= svdd_schedule[0] and s % svdd_schedule[1] == 0:
                     if graphed:
                         self._raise_on_flags()
                     self.engine.set_static_masks(False)     # candidate batches use other masks; the winners get a new one
                     z_lig, xh_pocket, lig_mask = self._atp_event(s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
-                                                                 B, reward_fn, svdd_groups)
+                                                                 B, reward_fn, svdd_groups, provider=provider)
                     z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
                     self.engine.set_static_masks(True)
                     gstep = None                            # new state tensors and ligand mask: capture again
@@ -378,21 +467,40 @@ class ConditionalSampler:
                     if graphed:
                         self._raise_on_flags()
                     zeta = 1e-3 * (s / 500)                                                   # :1244-1245
+                    pn, xn = self._spsa_draws(provider, spsa_k, lig_mask, B)
                     z_lig, xh_pocket = self.my_update_z_lig(z_lig, xh_pocket, lig_mask, pocket_mask, t_array, B, zeta,
-                                                            reward_fn, guidance_scale=1e-3, k=spsa_k)
+                                                            reward_fn, guidance_scale=1e-3, k=spsa_k, perturbation_noise=pn,
+                                                            x0_noise=xn)
                     z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+                    if mixed_at is not None and s == mixed_at:                                # :1261-1418
+                        self.engine.set_static_masks(False)
+                        z_lig, xh_pocket, lig_mask = self._mixed_event(s, s_array, t_array, z_lig, xh_pocket, lig_mask,
+                                                                       pocket_mask, B, reward_fn, svdd_groups, zeta, 1e-3,
+                                                                       spsa_k, provider=provider)
+                        z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
+                        self.engine.set_static_masks(True)
                     gstep = None
+            if stop_after > 0:
+                self._raise_on_flags()
+                return z_lig, xh_pocket, lig_mask, pocket_mask
+            step += 1
+            x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(
+                z_lig, xh_pocket, lig_mask, pocket_mask, B, noise=step_noise(int(lig_mask.numel())))
         finally:
             self.dynamics.check_nan = nan_check
-        x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(
-            z_lig, xh_pocket, lig_mask, pocket_mask, B, noise=None if noise is None else noise[timesteps + 1])
-        self.engine.set_static_masks(False)
+            self.engine.set_static_masks(False)
         self._raise_on_flags()
         # CoG drift correction (:1431-1438)
         cog = torch.zeros((B, 3), device=dev).index_add_(0, lig_mask, x_lig).abs().max().item()
         if cog > 5e-2:
             x_lig, x_pocket = self.remove_mean_batch(x_lig, x_pocket, lig_mask, pocket_mask, B)
         return torch.cat([x_lig, h_lig.float()], dim=1), torch.cat([x_pocket, h_pocket], dim=1), lig_mask, pocket_mask
+
+    def _spsa_draws(self, provider, k, lig_mask, B):
+        if provider is None:
+            return None, None
+        sizes = torch.bincount(lig_mask, minlength=B).tolist()
+        return provider.spsa(k, sizes)
 
     # -- inpainting (RePaint resampling), conditional_model.py:1491-1790 ----------------------------------------------------
     @torch.no_grad()
@@ -484,17 +592,46 @@ class ConditionalSampler:
         return torch.cat([x_lig, h_lig.float()], dim=1), torch.cat([x_pocket, h_pocket], dim=1), lig_mask, pocket_mask
 
     # -- ATP ("SVDD") event, conditional_model.py:1085-1241 -------------------------------------------------------------
-    def _atp_event(self, s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask, B, reward_fn, n_groups):
+    def _rebatch(self, top_idx, big_z, big_p, big_lig_mask, n_p):
+        """Winners in rank order (:1212-1232) as three gathers (no per-winner Python loop; one sync for the new length)."""
+        dev = self.device
+        n_cand = int(big_p.shape[0] // n_p)
+        sizes = torch.bincount(big_lig_mask, minlength=n_cand)
+        starts = torch.cumsum(sizes, 0) - sizes
+        sel_sizes = sizes[top_idx]
+        total = int(sel_sizes.sum())
+        new_m = torch.repeat_interleave(torch.arange(len(top_idx), device=dev), sel_sizes, output_size=total)
+        new_starts = torch.cumsum(sel_sizes, 0) - sel_sizes
+        src = starts[top_idx][new_m] + (torch.arange(total, device=dev) - new_starts[new_m])
+        p_src = (top_idx[:, None] * n_p + torch.arange(n_p, device=dev)[None, :]).reshape(-1)
+        return big_z[src].contiguous(), big_p[p_src].contiguous(), new_m
+
+    def _select(self, s, big_z, big_p, x0_l, h0_types, big_lig_mask, B, n_p, reward_fn, pending_r=None):
+        """mixed = r0 * (s / 250) + r * (250 - s / 250) [sic, :1203]; global top-B; re-batching."""
+        dev = self.device
+        reward_fn = _event_fn(reward_fn, 'svdd')
+        r0 = torch.as_tensor(reward_fn(x0_l, h0_types, big_lig_mask), dtype=torch.float32, device=dev)
+        r = torch.as_tensor(pending_r.result() if pending_r is not None else
+                            reward_fn(big_z[:, :3], big_z[:, 3:].argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
+        mixed = r0 * (s / 250) + r * (250 - s / 250)
+        self.last_atp_rewards = (r0, r)
+        _, top_idx = mixed.topk(k=B, largest=True)                                     # :1205
+        return self._rebatch(top_idx, big_z, big_p, big_lig_mask, n_p)
+
+    def _atp_event(self, s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask, B, reward_fn, n_groups,
+                   provider=None):
         """Draw n_groups-1 extra candidate next-states from (z, s, t), score the current and x0-look-ahead molecules of
         all n_groups*B candidates, keep the global top-B (:1203-1232).  The candidate groups are evaluated as ONE batch of
         n_groups*B samples per denoiser call instead of the reference's sequential calls.
 
-        With ``self.atp_group`` set (a torch.distributed group whose ranks carry the SAME trajectory state), the candidate
-        groups are split over the ranks -- group g is drawn, denoised and scored on rank g % world -- and the winners are
-        rebuilt everywhere from one all-gather of scores, latents and pocket translations (parallel.py)."""
+        With ``self.atp_group`` set (a torch.distributed group whose ranks carry the SAME trajectory state: same seed of the
+        default generator, see ``set_distributed_atp``), the candidate groups are split over the ranks -- group g is drawn
+        (from the per-rank candidate generator), denoised and scored on rank g % world -- and the winners are rebuilt
+        everywhere from ONE all-gather of scores, latents and absolute pocket positions (parallel.py)."""
         dev = self.device
         n_l, n_p = z_lig.shape[0], xh_pocket.shape[0]
         G = n_groups
+        all_events_fn, reward_fn = reward_fn, _event_fn(reward_fn, 'svdd')
         group = getattr(self, 'atp_group', None)
         world = dist.get_world_size(group) if group is not None else 1
         rank = dist.get_rank(group) if group is not None else 0
@@ -504,25 +641,40 @@ class ConditionalSampler:
         offs = torch.arange(max(n_here, 1), device=dev) * B
         big_lig_mask = (lig_mask.unsqueeze(0) + offs[:, None]).reshape(-1)[:n_here * n_l]
         big_pocket_mask = (pocket_mask.unsqueeze(0) + offs[:, None]).reshape(-1)[:n_here * n_p]
+        step_nz = x0_nz = None
+        if provider is not None:
+            assert world == 1, 'injected draws are defined for the single-rank event'
+            step_nz, x0_nz = provider.atp(G, n_l)
+            step_nz = self._h2d(torch.as_tensor(step_nz, dtype=torch.float32)).reshape(n_extra * n_l, -1)
+            x0_nz = self._h2d(torch.as_tensor(x0_nz, dtype=torch.float32)).reshape(G * n_l, -1)
+        gen = self.cand_gen
+        if step_nz is None and gen is not None and n_extra > 0:
+            step_nz = torch.randn((n_extra * n_l, self.n_dims + self.atom_nf), device=dev, generator=gen)
+        if x0_nz is None and gen is not None and n_here > 0:
+            x0_nz = torch.randn((n_here * n_l, self.n_dims + self.atom_nf), device=dev, generator=gen)
         parts_z, parts_p = ([z_lig], [xh_pocket]) if rank == 0 else ([], [])
         if n_extra > 0:                # extra candidates: sample_p_zs_given_zt from the same (already denoised) state, :1109-1117
             zs_extra, xp_extra = self.sample_p_zs_given_zt(
                 s_array.repeat(n_extra, 1), t_array.repeat(n_extra, 1), rep(z_lig, n_extra), rep(xh_pocket, n_extra),
-                big_lig_mask[:n_extra * n_l], big_pocket_mask[:n_extra * n_p], n_samples=n_extra * B)
+                big_lig_mask[:n_extra * n_l], big_pocket_mask[:n_extra * n_p], noise=step_nz, n_samples=n_extra * B)
             parts_z.append(zs_extra)
             parts_p.append(xp_extra)
         if n_here > 0:
             big_z = torch.cat(parts_z, dim=0)
             big_p = torch.cat(parts_p, dim=0)
             pending_r = None
-            if hasattr(reward_fn, 'submit') and self.overlap_scoring:
+            overlap = hasattr(reward_fn, 'submit') and self.overlap_scoring
+            if overlap:
                 # the current candidates are scored by the worker processes while the GPU runs their x0 look-ahead
                 cand_x, cand_t = big_z[:, :3].contiguous(), big_z[:, 3:].argmax(1)
                 ready = torch.cuda.Event()
                 ready.record()
-            x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(n_here, 1), big_z, big_p, big_lig_mask, big_pocket_mask, n_here * B)
-            if hasattr(reward_fn, 'submit') and self.overlap_scoring:
+            x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(n_here, 1), big_z, big_p, big_lig_mask, big_pocket_mask, n_here * B,
+                                             noise=x0_nz)
+            if overlap:
                 pending_r = reward_fn.submit(cand_x, cand_t, big_lig_mask, after=ready)
+            if world == 1:
+                return self._select(s, big_z, big_p, x0_l, h0_l.argmax(1), big_lig_mask, B, n_p // B, reward_fn, pending_r)
             r0 = torch.as_tensor(reward_fn(x0_l, h0_l.argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
             r = torch.as_tensor(pending_r.result() if pending_r is not None else
                                 reward_fn(big_z[:, :3], big_z[:, 3:].argmax(1), big_lig_mask), dtype=torch.float32, device=dev)
@@ -531,27 +683,44 @@ class ConditionalSampler:
             big_z = z_lig[:0]
             big_p = xh_pocket[:0]
             mixed = torch.zeros(0, device=dev)
-        if world > 1:
-            from .parallel import atp_select_distributed
-            sizes = torch.bincount(lig_mask, minlength=B)
-            pstart = torch.searchsorted(pocket_mask, torch.arange(B, device=dev))      # first pocket atom of every sample
-            src = torch.arange(B, device=dev).repeat(n_here)                           # source sample of every candidate
-            first = (torch.arange(n_here, device=dev) * n_p).repeat_interleave(B) + pstart.repeat(n_here)
-            shift = big_p[first, :3] - xh_pocket[pstart.repeat(n_here), :3] if n_here > 0 else big_p[:0, :3]
-            payload = torch.cat([shift, src[:, None].float()], dim=1)
-            z_sel, m_sel, _, pay = atp_select_distributed(mixed, big_z, sizes.repeat(n_here), B, group=group,
-                                                          per_candidate=payload)
-            new_p = []
-            for k in range(B):                                                        # winners' pockets, rank order
-                rows = xh_pocket[pocket_mask == int(pay[k, 3])].clone()
-                rows[:, :3] += pay[k, :3]
-                new_p.append(rows)
-            return z_sel.contiguous(), torch.cat(new_p, 0).contiguous(), m_sel
-        _, top_idx = mixed.topk(k=B, largest=True)                                     # :1205
-        new_z, new_p, new_m = [], [], []
-        for rank_pos, idx in enumerate(top_idx.tolist()):                              # :1212-1227
-            nm = big_lig_mask == idx
-            new_z.append(big_z[nm])
-            new_p.append(big_p[big_pocket_mask == idx])
-            new_m.append(torch.full((int(nm.sum()),), rank_pos, dtype=torch.long, device=dev))
-        return torch.cat(new_z, 0).contiguous(), torch.cat(new_p, 0).contiguous(), torch.cat(new_m, 0)
+        from .parallel import atp_select_packed
+        return atp_select_packed(mixed, big_z, big_p, lig_mask, pocket_mask, xh_pocket, B, G, group)
+
+    # -- the s == 30 branch of a run with SPSA, conditional_model.py:1261-1418 ---------------------------------------------
+    def _mixed_event(self, s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask, B, reward_fn, n_groups, zeta,
+                     guidance_scale, k, provider=None):
+        """Four extra candidates, each one reverse step + SPSA update + feature rescaling; then the ATP selection over the
+        entry state and the four.  The reference REBINDS ``z_lig`` / ``xh_pocket`` inside its loop (:1286): candidate i + 1
+        is drawn from candidate i's SPSA output (before the rescaling), so the candidates form a chain and cannot be batched
+        across groups; ``zeta`` is reset to 1e-3 from the third candidate on (:1284-1285).  The 2k look-aheads inside each
+        SPSA update are batched as everywhere else."""
+        dev = self.device
+        n_l, n_p = z_lig.shape[0], xh_pocket.shape[0]
+        G = n_groups
+        # With ranks sharing one trajectory (atp_group) every rank computes the whole chain from the shared default
+        # generator: the chain cannot be split, and all ranks must leave the event with the same state.
+        step_nz = spsa_nz = x0_nz = None
+        if provider is not None:
+            step_nz, spsa_nz, x0_nz = provider.mixed(G, k, torch.bincount(lig_mask, minlength=B).tolist())
+        cands_z, cands_p = [z_lig], [xh_pocket]
+        z_cur, xp_cur = z_lig, xh_pocket
+        for i in range(G - 1):
+            nz = None if step_nz is None else self._h2d(torch.as_tensor(step_nz[i], dtype=torch.float32))
+            z_tmp, xp_tmp = self.sample_p_zs_given_zt(s_array, t_array, z_cur, xp_cur, lig_mask, pocket_mask, noise=nz,
+                                                      n_samples=B)                               # :1278-1283
+            if i >= 2:
+                zeta = 1e-3
+            pn, xn = spsa_nz[i] if spsa_nz is not None else (None, None)
+            z_cur, xp_cur = self.my_update_z_lig(z_tmp, xp_tmp, lig_mask, pocket_mask, t_array, B, zeta, reward_fn,
+                                                 guidance_scale=guidance_scale, k=k, perturbation_noise=pn, x0_noise=xn)   # :1286
+            z_tmp, xp_tmp = self._unnormalize_quirk(z_cur, xp_cur, lig_mask, pocket_mask, B)  # :1287-1292
+            cands_z.append(z_tmp)
+            cands_p.append(xp_tmp)
+        offs = torch.arange(G, device=dev) * B
+        big_lig_mask = (lig_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
+        big_pocket_mask = (pocket_mask.unsqueeze(0) + offs[:, None]).reshape(-1)
+        big_z = torch.cat(cands_z, dim=0)
+        big_p = torch.cat(cands_p, dim=0)
+        x0n = None if x0_nz is None else self._h2d(torch.as_tensor(x0_nz, dtype=torch.float32)).reshape(G * n_l, -1)
+        x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(G, 1), big_z, big_p, big_lig_mask, big_pocket_mask, G * B, noise=x0n)
+        return self._select(s, big_z, big_p, x0_l, h0_l.argmax(1), big_lig_mask, B, n_p // B, reward_fn)

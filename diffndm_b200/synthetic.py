@@ -49,6 +49,48 @@ def synthetic_ligand_sizes(seed: int, n_samples: int):
     return np.clip(np.rint(rng.normal(23, 8, size=n_samples)), 5, 50).astype(np.int64)
 
 
+_LIGAND_P = np.array([0.70, 0.12, 0.15, 0.01, 0.0, 0.0, 0.01, 0.0, 0.0, 0.01])    # C N O S B Br Cl P I F
+
+
+def synthetic_ligand_pose(seed: int, lig_sizes, center, r_max: float | None = None, bond: float = 1.5,
+                          min_spacing: float = 1.2, atom_nf: int = 10, norm_h: float = 4.0):
+    """A ligand-shaped point cloud per sample in the pocket: a branched random walk with ``bond``-long steps that stays
+    within ``r_max`` of ``center`` (default: 1.15 x the radius of a sphere holding n heavy atoms at the drug-like 18 A^3 per
+    atom, at least 3.5 A -- real ligands are elongated; 3rfm's 14-atom ligand reaches 3.5 A from its centroid) and keeps
+    ``min_spacing`` between atoms where it can.  Returns xh[N_l, 3+atom_nf] in the sampler's normalised units (absolute
+    coordinates, one-hot / norm_h) -- the data point x_0 the synthetic score of bench.py pulls the reverse trajectory
+    towards (random-init weights cannot denoise)."""
+    rng = np.random.default_rng(777 + seed)
+    out = []
+    center = np.asarray(center, np.float64)
+    r_fixed = r_max
+    for n in np.asarray(lig_sizes):
+        r_max = r_fixed if r_fixed is not None else max(3.5, 1.15 * (3.0 * 18.0 * float(n) / (4.0 * np.pi)) ** (1.0 / 3.0))
+        pts = np.zeros((int(n), 3))
+        pts[0] = rng.normal(size=3) * 0.8
+        for i in range(1, int(n)):
+            anchor = pts[rng.integers(max(0, i - 3), i)]          # grow from one of the last atoms: chains with short branches
+            best, best_d = None, -1.0
+            for _ in range(24):
+                d = rng.normal(size=3)
+                cand = anchor + bond * d / np.linalg.norm(d)
+                if np.linalg.norm(cand) > r_max:
+                    continue
+                dm = np.min(np.linalg.norm(pts[:i] - cand, axis=1))
+                if dm >= min_spacing:
+                    best = cand
+                    break
+                if dm > best_d:
+                    best, best_d = cand, dm
+            if best is None:                                       # every try left the cavity: step towards the centre
+                best = anchor * (1.0 - bond / max(np.linalg.norm(anchor), bond))
+            pts[i] = best
+        types = rng.choice(atom_nf, size=int(n), p=_LIGAND_P[:atom_nf] / _LIGAND_P[:atom_nf].sum())
+        onehot = np.eye(atom_nf, dtype=np.float32)[types] / np.float32(norm_h)
+        out.append(np.concatenate([(pts + center).astype(np.float32), onehot], axis=1))
+    return np.concatenate(out, axis=0).astype(np.float32)
+
+
 def make_batch(pocket_x, pocket_types, lig_sizes, seed: int, atom_nf: int = 10, norm_h: float = 4.0):
     """Assemble the reference's batch layout for one pocket repeated len(lig_sizes) times
     (prepare_pocket(repeats=n), lightning_modules.py:763-801; num_nodes_to_batch_mask,

@@ -477,7 +477,7 @@ def inpaint_combine(z_known, z_unknown, xh_pocket, lig_fixed, lig_mask, pocket_m
 
 
 def inpaint(W, lig_x, lig_onehot, lig_mask, pocket_x, pocket_onehot, pocket_mask, lig_fixed, noise, timesteps,
-            resamplings, cfg: OracleConfig = OracleConfig(), T=500, dtype=np.float32):
+            resamplings, cfg: OracleConfig = OracleConfig(), T=500, dtype=np.float32, eps_fn=None):
     """ConditionalDDPM.inpaint (conditional_model.py:1491-1790) with center='ligand', svdd=0 and every Gaussian draw
     injected in the reference's order (``noise`` [n_draws, N_l, 3+atom_nf]); the SPSA window (12 <= s <= 16) is outside
     the fixtures' range.  Returns (xh_lig with one-hot features, xh_pocket) in Angstrom like the reference."""
@@ -498,12 +498,14 @@ def inpaint(W, lig_x, lig_onehot, lig_mask, pocket_x, pocket_onehot, pocket_mask
     xp = xh0_pocket.copy()
     z[:, :3], xp[:, :3] = remove_mean_batch(z[:, :3], xh0_pocket[:, :3], lig_mask, pocket_mask, nb)
     look = lambda tt: gam[int(round(tt * T))]
+    if eps_fn is None:     # ``eps_fn(z, xp, t[B,1], lig_mask, pocket_mask) -> eps_lig`` replaces the plain denoiser call (tests wrap it)
+        eps_fn = lambda z_, xp_, t_, lm_, pm_: dynamics_forward(W, z_, xp_, t_, lm_, pm_, cfg, dtype=dtype)[0]
     for s in reversed(range(timesteps)):
         for u in range(resamplings):
             ts, tt = s / timesteps, (s + 1) / timesteps
             g_s = np.full(nb, look(ts), np.float32)
             g_t = np.full(nb, look(tt), np.float32)
-            eps, _ = dynamics_forward(W, z, xp, np.full((nb, 1), tt, np.float32), lig_mask, pocket_mask, cfg, dtype=dtype)
+            eps = eps_fn(z, xp, np.full((nb, 1), tt, np.float32), lig_mask, pocket_mask)
             z_unknown, xp = sample_p_zs_given_zt(z, xp, eps.astype(np.float32), next(it), g_s, g_t, lig_mask, pocket_mask)
             com_pocket = segment_mean(xp[:, :3], pocket_mask, nb)
             xh_ligand[:, :3] = lx + (com_pocket - com_pocket_0)[lig_mask]
@@ -512,7 +514,7 @@ def inpaint(W, lig_x, lig_onehot, lig_mask, pocket_x, pocket_onehot, pocket_mask
             if u < resamplings - 1:
                 z, xp = sample_p_zt_given_zs(z, xp, next(it), g_t, g_s, lig_mask, pocket_mask)
     g0 = np.full(nb, gam[0], np.float32)
-    eps0, _ = dynamics_forward(W, z, xp, np.zeros((nb, 1), np.float32), lig_mask, pocket_mask, cfg, dtype=dtype)
+    eps0 = eps_fn(z, xp, np.zeros((nb, 1), np.float32), lig_mask, pocket_mask)
     x_l, t_l, x_p, h_p = sample_p_xh_given_z0(z, xp, eps0.astype(np.float32), next(it), g0, lig_mask, pocket_mask, cfg)
     onehot = np.eye(lh.shape[1], dtype=np.float32)[t_l]
     return np.concatenate([x_l, onehot], 1), np.concatenate([x_p, h_p], 1), z, xp

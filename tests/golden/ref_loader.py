@@ -67,8 +67,13 @@ def load_reference():
     return EGNNDynamics, ConditionalDDPM
 
 
-def build_reference_model(cfg, weights, dtype=torch.float32, timesteps=500):
-    """EGNNDynamics + ConditionalDDPM with the kwargs of lightning_modules.py:138-174 and the given weights."""
+def build_reference_model(cfg, weights, dtype=torch.float32, timesteps=500, untie_heads=False):
+    """EGNNDynamics + ConditionalDDPM with the kwargs of lightning_modules.py:138-174 and the given weights.
+
+    The reference builds ONE ``nn.Linear(hidden_nf, 1, bias=False)`` and puts it at the end of both ``coord_mlp`` and
+    ``cross_product_mlp`` (egnn_new.py:78-92): the two state-dict keys alias one Parameter, and ``load_state_dict`` leaves
+    both heads with whichever key it copied last.  ``untie_heads`` gives ``cross_product_mlp`` its own Linear object before
+    loading, so that a table whose two keys differ is represented as written (the engine packs the keys separately)."""
     EGNNDynamics, ConditionalDDPM = load_reference()
     with contextlib.redirect_stdout(io.StringIO()):
         dyn = EGNNDynamics(
@@ -79,6 +84,10 @@ def build_reference_model(cfg, weights, dtype=torch.float32, timesteps=500):
             edge_cutoff_ligand=cfg.edge_cutoff_ligand, edge_cutoff_pocket=cfg.edge_cutoff_pocket,
             edge_cutoff_interaction=cfg.edge_cutoff_interaction, update_pocket_coords=False,
             reflection_equivariant=False, edge_embedding_dim=None)
+        if untie_heads:
+            for i in range(cfg.n_layers):
+                eq = dyn.egnn._modules[f'e_block_{i}']._modules['gcl_equiv']
+                eq.cross_product_mlp[4] = torch.nn.Linear(cfg.hidden_nf, 1, bias=False)
         sd = {k: torch.from_numpy(v.copy()) for k, v in weights.items()}
         missing, unexpected = dyn.load_state_dict(sd, strict=True), None
         ddpm = ConditionalDDPM(dynamics=dyn, atom_nf=cfg.atom_nf, residue_nf=cfg.residue_nf, n_dims=3,

@@ -51,9 +51,41 @@ def _worker(rank, world, port, ret):
     ok = ok and sorted(got[0] + got[1]) == list(range(7)) and q.order == [1, 3, 6, 4, 0, 5, 2]
     ok = ok and all(q.order.index(a) < q.order.index(b) for g in got for a, b in zip(g, g[1:]))
     ok = ok and len(got[0]) >= len(got[1])
+    ok = ok and _packed_atp_case(rank, world)
     ret[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _packed_atp_case(rank, world):
+    """atp_select_packed: the candidate groups of ONE pocket split over the ranks (group g on rank g % world), one
+    all-gather per event, every rank rebuilds the winners of the reference's global top-B over index g * B + i."""
+    from diffndm_b200.parallel import atp_select_packed
+    B, G, n_p, D = 3, 5, 4, 13
+    g = torch.Generator().manual_seed(1)
+    sizes = torch.tensor([2, 5, 3])
+    lig_mask = torch.repeat_interleave(torch.arange(B), sizes)
+    pocket_mask = torch.repeat_interleave(torch.arange(B), n_p)
+    n_l = int(sizes.sum())
+    xh_pocket = torch.randn(B * n_p, D, generator=g)
+    z_all = torch.randn(G, n_l, D, generator=g)                       # latents of every group
+    shift_all = torch.randn(G, B, 3, generator=g)                     # every candidate's pocket translation
+    scores = torch.randn(G * B, generator=g)
+    scores[7] = scores[2]                                             # a tie: the lower candidate index wins
+    p_all = xh_pocket.reshape(1, B, n_p, D).repeat(G, 1, 1, 1)
+    p_all[..., :3] += shift_all[:, :, None, :]
+    mine = [q for q in range(G) if q % world == rank]
+    z, xp, m = atp_select_packed(torch.cat([scores[q * B:(q + 1) * B] for q in mine]), torch.cat([z_all[q] for q in mine]),
+                                 torch.cat([p_all[q].reshape(B * n_p, D) for q in mine]), lig_mask, pocket_mask, xh_pocket,
+                                 B, G, None)
+    order = torch.sort(scores, descending=True, stable=True).indices[:B]
+    ez, ep, em = [], [], []
+    for pos, c in enumerate(order.tolist()):
+        q, i = c // B, c % B
+        ez.append(z_all[q][lig_mask == i])
+        ep.append(p_all[q, i])
+        em += [pos] * int(sizes[i])
+    return torch.equal(z, torch.cat(ez)) and torch.allclose(xp, torch.cat(ep), atol=1e-6) and m.tolist() == em
 
 
 def test_pocket_queue_local():
