@@ -202,11 +202,14 @@ constexpr int EK_EPI_WARPS = 8;                     // warps 0-7: epilogue, colu
 constexpr int EK_PROD_WARPS = 16;                   // warps 8-23: producers, 8 edges of every tile each
 constexpr int EK_PROD_THREADS = EK_PROD_WARPS * 32;
 
-// kBf16Radial (GCL only): assemble the whole first-layer pre-activation in bf16x2 (the round-1 producers; r^2 and r0 are
-// then ROUNDED to bf16 before they meet their weights, which costs accuracy when r^2 is large -- fully connected
-// ligand-ligand edges early in a trajectory -- or the trained radial weights are).  Default (false): P + Q in bf16x2,
-// the two radial FMAs, SiLU and the single rounding to bf16 in fp32 (FFMA2).  DNDM_GCL_BF16_RADIAL=1 selects the old path.
-template <bool kGCL, bool kBf16Radial = false>
+// kBf16Radial (GCL only): assemble the whole first-layer pre-activation in bf16x2: r^2 and r0 are ROUNDED to bf16 before
+// they meet their weights.  The alternative (false; DNDM_GCL_F32_RADIAL=1) keeps P + Q in bf16x2 but does the two radial
+// FMAs (FFMA2), the SiLU and the single rounding to bf16 in fp32.  Measured on B200 against the fp64 reference on the radial
+// stress fixture (tests/golden/parity_r2.npz fwd_r2stress_3rfm_b2: radial weights x 20, ligand-ligand r^2 up to 789):
+// eps_x error 1.42e-2 vs 1.43e-2 at |eps_x| = 8.6, h after six blocks 3.2e-3 relative either way, eps_h 4.3e-3 vs 3.2e-3 --
+// the operand rounding of P/Q/A dominates, not the radial terms -- while the fp32 variant costs 8 % of the kernel
+// (profiles/r2_radial_ab.json).  The packed path therefore stays the default.
+template <bool kGCL, bool kBf16Radial = true>
 __global__ void __launch_bounds__(EK_THREADS, 1)
 edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
                 const __grid_constant__ CUtensorMap tmap_msg, const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,

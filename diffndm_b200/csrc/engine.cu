@@ -31,8 +31,9 @@ static long long g_launches = 0;   // kernels of this library launched (or captu
 // init, TMEM allocation, the 64-128 KiB TMA load of the resident weights -- runs under the tail of the previous kernel
 // of the stream (see pdl_wait / pdl_trigger in common.cuh).  DNDM_PDL=0 in the environment turns the attribute off.
 static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] == '0'); }();
-// DNDM_GCL_BF16_RADIAL=1: the round-1 all-bf16x2 GCL producers (A/B measurements only; see edge_mlp.cuh)
-static bool g_bf16_radial = [] { const char* v = getenv("DNDM_GCL_BF16_RADIAL"); return v && v[0] == '1'; }();
+// GCL producers: all-bf16x2 first-layer pre-activation by default; DNDM_GCL_F32_RADIAL=1 selects the variant with fp32 radial
+// terms and activation (measured on the radial stress fixture: same error to two digits, 8 % slower -- see edge_mlp.cuh)
+static bool g_bf16_radial = [] { const char* v = getenv("DNDM_GCL_F32_RADIAL"); return !(v && v[0] == '1'); }();
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {

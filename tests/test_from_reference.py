@@ -129,6 +129,7 @@ def test_adapter_takes_the_reference_positional_arguments(adapter):
                   'size': torch.tensor([len(px)] * B), 'mask': torch.arange(B).repeat_interleave(len(px))}
     sizes = torch.tensor([5, 8, 6])
     com = torch.zeros(B, 3)
+    adapter.sampler.sample_given_pocket(mk(), sizes, timesteps=20)          # captures the reverse-step graph for this batch shape
     torch.manual_seed(5)
     a = adapter.sample_given_pocket(mk(), sizes, com, None, False, 0, False, 'x', 'cuda', 0, None, None, 0, 0, timesteps=20)
     torch.manual_seed(5)

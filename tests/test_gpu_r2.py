@@ -135,9 +135,9 @@ def test_inpaint_large_pockets_absolute(name, dyn, dev):
 
 
 def test_zz_write_report():
-    """Measured errors of this run -> gpurun_out/r2_parity_errors[_bf16radial].json (copied into profiles/ by hand)."""
+    """Measured errors of this run -> gpurun_out/r2_parity_errors[_f32radial].json (copied into profiles/ by hand)."""
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
     os.makedirs(out, exist_ok=True)
-    tag = '_bf16radial' if os.environ.get('DNDM_GCL_BF16_RADIAL') == '1' else ''
+    tag = '_f32radial' if os.environ.get('DNDM_GCL_F32_RADIAL') == '1' else ''
     with open(os.path.join(out, f'r2_parity_errors{tag}.json'), 'w') as f:
         json.dump(REPORT, f, indent=1)
