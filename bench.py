@@ -62,6 +62,8 @@ def parse():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-job', action='store_true', help='skip the whole-job section (pocket queue -> sampling -> SDF files; ATP over the ranks)')
+    ap.add_argument('--job-pockets', type=int, default=4, help='pockets per GPU in the job section (weak scaling: 4 N pockets on N GPUs)')
     args = ap.parse_args()
     if args.cpu_batch is None:
         args.cpu_batch = max(8, min(32, os.cpu_count() or 8))
@@ -604,6 +606,14 @@ def run_b200(args):
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms_e2e, 'steps': n_e2e, 'cuda_graph': e2e_graphs is not None,
                'transfers_per_step': 'one H2D (all inputs of the call in one pinned block) + one D2H'}
 
+    # ---- the job: what the reference's my_test.py:68-90 does -- many pockets x B ligands, 500 steps each, one SDF per pocket --
+    #      through the shared PocketQueue (largest pocket first), wall clock with a barrier on both sides, max over ranks.  Pocket
+    #      sizes ~ clip(N(330, 80), 150, 700); job-pockets per GPU (weak scaling).  Plus one ATP trajectory (B = 20, 5 candidate
+    #      groups) whose groups are split over the ranks: the NCCL all-gather of the path, one per event. ----
+    job = None
+    if not args.no_job:
+        job = run_job_section(args, dyn, smp, world, rank, dev, B)
+
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -625,11 +635,84 @@ def run_b200(args):
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': cfgd, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps),
-            'gpu_launches_per_step': int(launches_per_step), 'roofline': roof, 'cpu_baseline': cpu,
+            'gpu_launches_per_step': int(launches_per_step), 'roofline': roof, 'cpu_baseline': cpu, 'job': job,
         }
         emit_json(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_job_section(args, dyn, smp, world, rank, dev, B):
+    import shutil
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from diffndm_b200 import engine as E, synthetic
+    from diffndm_b200.chem import BondPerception
+    from diffndm_b200.datasets import crossdock_dataset_info
+    from diffndm_b200.hostpool import PooledReward, radius_of_gyration_score
+    from diffndm_b200.job import run_pocket_job, synthetic_pocket_sizes
+    from diffndm_b200.sampler import ConditionalSampler
+    from diffndm_b200.weights import DynamicsConfig, random_init
+    P = args.job_pockets * world
+    n_atoms = synthetic_pocket_sizes(P)
+    nmax = int(n_atoms.max())
+    cfg = DynamicsConfig()
+    info = crossdock_dataset_info()
+    big = E.B200EGNNDynamics(cfg, random_init(cfg, 0, 0.3), max_nodes=B * (nmax + 60) + 1024, max_edges=B * (nmax + 60) * 48,
+                             max_samples=max(B, 128), check_nan=False).eval()
+    smp_job = ConditionalSampler(big, timesteps=T_STEPS)
+    out_dir = tempfile.mkdtemp(prefix='dndm_job_')
+    dt, gathered, idle = run_pocket_job(smp_job, BondPerception(big.engine, info), info, n_atoms, B, T_STEPS, out_dir)
+    shutil.rmtree(out_dir, ignore_errors=True)
+    done = sorted((p for g in gathered for p in g), key=lambda p: p['id'])
+    assert [p['id'] for p in done] == list(range(P)), 'every pocket exactly once'
+    job = {'pockets': P, 'ligands_per_pocket': B, 'timesteps': T_STEPS, 'seconds': dt, 'value': P * B / dt, 'unit': 'ligands/s',
+           'pockets_per_rank': [len(g) for g in gathered], 'tail_idle_s_per_rank': idle,
+           'pocket_atoms': [p['atoms'] for p in done], 'pocket_seconds': [p['s'] for p in done],
+           'sample_seconds': [p['sample_s'] for p in done], 'output_seconds': [p['output_s'] for p in done],
+           'setup_seconds': [p['setup_s'] for p in done],
+           'ligand_receiver_share': [p['ligand_receiver_share'] for p in done],
+           'what': 'PocketQueue -> pocket batch -> 500-step sampling (graph replay, captured per batch shape) -> GPU bond perception '
+                   '-> largest fragment -> one SDF file per pocket; wall clock, barrier both sides, max over ranks'}
+    # one ATP trajectory shared by all ranks: candidate groups g = 0..4 live on rank g % N, one all-gather per event
+    Ba = 20
+    px, pt = synthetic.synthetic_pocket(9000, POCKET_ATOMS)
+    sizes = synthetic.synthetic_ligand_sizes(9000, Ba)
+    onehot = np.eye(10, dtype=np.float32)[pt]
+    pocket = {'x': torch.from_numpy(px).to(dev).repeat(Ba, 1), 'one_hot': torch.from_numpy(onehot).to(dev).repeat(Ba, 1),
+              'size': torch.tensor([len(px)] * Ba, device=dev), 'mask': torch.arange(Ba, device=dev).repeat_interleave(len(px))}
+    pose = synthetic.synthetic_ligand_pose(9000, sizes, px.mean(axis=0, dtype=np.float64))
+    pose[:, :3] -= px[0]
+    smp_job.eps_transform = synthetic.PointMassScore(pose, smp_job.gamma, len(px), smp_job.T, dev)
+    reward = PooledReward(radius_of_gyration_score, workers=0)
+    if world > 1:
+        smp_job.set_distributed_atp(dist.group.WORLD, shared_seed=4242)
+    else:
+        torch.manual_seed(4242)
+    times = []
+    for rep in range(2):                      # the second run replays the captured reverse-step graphs
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        xh, _, lm, _ = smp_job.sample_given_pocket(pocket, sizes, timesteps=T_STEPS, svdd=1, reward_fn=reward)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    smp_job.eps_transform = None
+    tt = torch.tensor([times[-1]], device=dev)
+    same = torch.tensor([float(xh[:, :3].double().sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sums = [torch.zeros_like(same) for _ in range(world)]
+        dist.all_gather(sums, same)
+        identical = all(float(x) == float(sums[0]) for x in sums)
+    else:
+        identical = True
+    job['atp'] = {'ligands': Ba, 'candidate_groups': 5, 'events': 6, 'ranks': world, 'seconds': float(tt), 'value': Ba / float(tt),
+                  'unit': 'ligands/s', 'first_run_seconds': times[0], 'ranks_end_identical': bool(identical),
+                  'collective': 'one all_gather per event (scores + pocket positions + latents of the rank\'s groups)' if world > 1 else None}
+    return job
 
 
 def main():

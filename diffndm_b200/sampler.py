@@ -99,6 +99,8 @@ class _GraphedReverseStep:
 
         def body():
             eps, _ = eng.forward(self.z, self.xp, self.t_buf, lig_mask, pocket_mask, B, want_pocket=False)
+            if sampler.eps_transform is not None:
+                eps = sampler.eps_transform(eps, self.z, self.xp, self.t_buf, lig_mask, pocket_mask)
             nz = torch.randn_like(self.z)
             eng.sampler_step(self.z, eps, nz, self.xp, self.coef_buf, lig_mask, pocket_mask, B, z_out=self.z,
                              pocket_out=self.xp, check_com=True)
@@ -148,6 +150,10 @@ class ConditionalSampler:
         self.check_every_step = check_every_step
         self.overlap_scoring = True                # SPSA: score one half of a round on the host while the GPU denoises the other
         self._graph_cache = {}                     # (weights version, B, N_l, N_p) -> _GraphedReverseStep
+        # optional device-side hook applied to every denoiser output: eps = f(eps, z, xh_pocket, t [B,1] on the device,
+        # lig_mask, pocket_mask).  Capture-safe callables only (it runs inside the graphed reverse step as well).  Used by
+        # the benchmarks for the synthetic score that stands in for trained weights (synthetic.PointMassScore).
+        self.eps_transform = None
         self.atp_group = None                      # torch.distributed group over which ATP candidate groups are split
         self.cand_gen = None                       # generator of the candidate / perturbation draws (None: default generator)
         if gamma_table is not None:               # a live reference schedule: PredefinedNoiseSchedule.gamma, en_diffusion.py:1189-1191
@@ -204,9 +210,12 @@ class ConditionalSampler:
         keep = self.dynamics.compute_pocket_output
         self.dynamics.compute_pocket_output = False
         try:
-            return self.dynamics(z_lig, xh_pocket, t, lig_mask, pocket_mask, n_samples=B)[0]
+            eps = self.dynamics(z_lig, xh_pocket, t, lig_mask, pocket_mask, n_samples=B)[0]
         finally:
             self.dynamics.compute_pocket_output = keep
+        if self.eps_transform is not None:
+            eps = self.eps_transform(eps, z_lig, xh_pocket, t.to(self.device).reshape(-1, 1), lig_mask, pocket_mask)
+        return eps
 
     def _noise(self, n, noise=None):
         if noise is not None:
