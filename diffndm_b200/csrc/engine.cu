@@ -11,7 +11,6 @@
 #include <vector>
 
 #include "common.cuh"
-#include "gemm_tn.cuh"
 #include "gemm_wres.cuh"
 #include "edge_mlp.cuh"
 #include "graph.cuh"
@@ -253,8 +252,8 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaMemset(e->flags, 0, 4));
     CU_CHECK(cudaMemset(e->hcat, 0, N * 512 * 2));
     CU_CHECK(cudaMemset(e->hid, 0, N * 256 * 2));
-    RET_IF(make_tmap_bf16(&e->tm_hcat, e->hcat, N, 512, 512, GEMM_BM));
-    RET_IF(make_tmap_bf16(&e->tm_hid, e->hid, N, 256, 256, GEMM_BM));
+    RET_IF(make_tmap_bf16(&e->tm_hcat, e->hcat, N, 512, 512, WR_BM));
+    RET_IF(make_tmap_bf16(&e->tm_hid, e->hid, N, 256, 256, WR_BM));
     RET_IF(make_tmap_bf16_box(&e->to_msg, e->msg, E + 128, 256, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_pq32, e->pq, N, 1536, 1536, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_hcat32, e->hcat, N, 512, 512, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
@@ -262,7 +261,6 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
-    CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
@@ -456,8 +454,8 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
             L.c_x.b2[o] = 0.5f * x2b[o]; L.c_x.wout[o] = x4w[o];
         }
         L.att_bias = ab[0];
-        RET_IF(make_tmap_bf16(&L.tm_w3, L.w3, H, 2 * H, 2 * H, GEMM_BN));
-        RET_IF(make_tmap_bf16(&L.tm_w4, L.w4, H, H, H, GEMM_BN));
+        RET_IF(make_tmap_bf16(&L.tm_w3, L.w3, H, 2 * H, 2 * H, 128));
+        RET_IF(make_tmap_bf16(&L.tm_w4, L.w4, H, H, H, 128));
         RET_IF(make_tmap_bf16(&L.tm_w2_e, L.w2_e, H, H, H, 256));
         RET_IF(make_tmap_bf16(&L.tm_w2_c, L.w2_c, H, H, H, 256));
         RET_IF(make_tmap_bf16(&L.tm_w2_x, L.w2_x, H, H, H, 256));
@@ -504,18 +502,6 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static int launch_gemm(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to16,
-                       const CUtensorMap& to32, int M, int Nout, int K, int a_col0, const GemmEpilogue& ep, int n_col0 = 0) {
-    if (M <= 0) return DNDM_OK;
-    const int n_tiles = Nout / GEMM_BN;
-    const int total = ((M + GEMM_BM - 1) / GEMM_BM) * n_tiles;
-    const int grid = total < g_num_sms ? total : g_num_sms;
-    gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tw, to16, to32, M, K, a_col0, n_col0 / GEMM_BN, n_tiles, ep);
-    COUNT_LAUNCH(1);
-    CU_CHECK(cudaGetLastError());
-    return DNDM_OK;
-}
-
 // n_full column groups over M rows followed by n_tail groups over the first M_tail rows (see gemm_wres_kernel)
 template <int kK = 256, int kBN = 256>
 static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to16, int M,
@@ -914,23 +900,35 @@ extern "C" int dndm_set_trace(DndmEngine* e, float* h_trace, float* x_trace, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// GEMM self-test
+// GEMM self-test: the weight-resident node GEMM exactly as the forward launches it
 // ------------------------------------------------------------------------------------------------
-extern "C" int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const float* bias, int32_t act, int32_t M, int32_t N,
-                              int32_t K, float* out, void* stream) {
-    if (!a_bf16 || !w_bf16 || !out) return set_err(DNDM_EINVAL, "null argument");
-    if (K % GEMM_BK != 0 || N % GEMM_BN != 0 || M < 1) return set_err(DNDM_EINVAL, "need K %% 64 == 0 and N %% 128 == 0");
+extern "C" int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const float* bias, const float* residual, int32_t act,
+                              int32_t M, int32_t N, int32_t K, int32_t bn, int32_t n_tail_groups, int32_t m_tail,
+                              float* out_f32, void* out_bf16, void* stream) {
+    if (!a_bf16 || !w_bf16 || (!out_f32 && !out_bf16)) return set_err(DNDM_EINVAL, "null argument");
+    const bool s256 = (K == 256 && bn == 256), s512 = (K == 512 && bn == 128), s128 = (K == 256 && bn == 128);
+    if (!(s256 || s512 || s128)) return set_err(DNDM_EINVAL, "supported shapes: (K, BN) = (256, 256), (512, 128), (256, 128)");
+    if (M < 1 || N % bn != 0 || n_tail_groups < 0 || n_tail_groups * bn >= N + (n_tail_groups ? 0 : 1) || m_tail > M)
+        return set_err(DNDM_EINVAL, "bad sizes");
+    if (residual && N != 256) return set_err(DNDM_EINVAL, "the residual epilogue is defined for 256 output columns");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CUtensorMap ta, tw, to;
-    RET_IF(make_tmap_bf16(&ta, a_bf16, M, K, K, GEMM_BM));
-    RET_IF(make_tmap_bf16(&tw, w_bf16, N, K, K, GEMM_BN));
-    RET_IF(make_tmap_f32_out(&to, out, M, N, N));
-    CU_CHECK(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
             g_num_sms = sms;
     }
-    GemmEpilogue ep{bias, act, nullptr, 0, 1, 0, 0, 0};
-    return launch_gemm(st, ta, tw, to, to, M, N, K, 0, ep);
+    const uint64_t rows = (uint64_t)((M + WR_BM - 1) / WR_BM) * WR_BM;      // the caller pads A / out_bf16 to whole row blocks
+    CUtensorMap ta, tw, to;
+    RET_IF(make_tmap_bf16(&ta, a_bf16, rows, K, K, WR_BM));
+    RET_IF(make_tmap_bf16(&tw, w_bf16, N, K, K, bn));
+    if (out_bf16) RET_IF(make_tmap_bf16_box(&to, out_bf16, rows, N, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    else to = ta;
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
+    WresEpilogue ep{bias, residual, 256, out_f32, N, 0, out_bf16 ? 1 : 0, 0, act};
+    const int n_full = N / bn - n_tail_groups;
+    if (s256) return launch_wres<256, 256>(st, ta, tw, to, M, n_full, 0, 0, ep, n_tail_groups, m_tail);
+    if (s512) return launch_wres<512, 128>(st, ta, tw, to, M, n_full, 0, 0, ep, n_tail_groups, m_tail);
+    return launch_wres<256, 128>(st, ta, tw, to, M, n_full, 0, 0, ep, n_tail_groups, m_tail);
 }

@@ -81,7 +81,7 @@ def load_library() -> ctypes.CDLL:
     lib.dndm_set_static_masks.argtypes = [vp, i32]
     lib.dndm_bond_orders.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp]
     lib.dndm_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32), i32]
-    lib.dndm_test_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.dndm_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -278,15 +278,22 @@ def launch_count() -> int:
     return int(load_library().dndm_launch_count())
 
 
-def test_gemm(a_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0):
-    """C = A W^T (+bias)(SiLU) through the tcgen05 GEMM building block (fp32 out)."""
+def test_gemm(a_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0, bn: int = 256,
+              residual: Optional[torch.Tensor] = None, n_tail_groups: int = 0, m_tail: int = 0, want_bf16: bool = False):
+    """C = A W^T (+bias)(+residual)(SiLU) through ``gemm_wres_kernel``, the weight-resident tcgen05 node GEMM, with the
+    forward's launch geometry.  Returns (out_f32 [M,N], out_bf16 [M,N] or None); outputs the tail groups do not cover are 0."""
     lib = load_library()
     M, K = a_bf16.shape
     N = w_bf16.shape[0]
-    out = torch.empty(M, N, dtype=torch.float32, device=a_bf16.device)
-    rc = lib.dndm_test_gemm(_ptr(a_bf16.contiguous()), _ptr(w_bf16.contiguous()), _ptr(bias), act, M, N, K, _ptr(out), _stream())
+    rows = -(-M // 128) * 128
+    a_pad = torch.zeros(rows, K, dtype=torch.bfloat16, device=a_bf16.device)
+    a_pad[:M] = a_bf16
+    out = torch.zeros(M, N, dtype=torch.float32, device=a_bf16.device)
+    out16 = torch.zeros(rows, N, dtype=torch.bfloat16, device=a_bf16.device) if want_bf16 else None
+    rc = lib.dndm_test_gemm(_ptr(a_pad), _ptr(w_bf16.contiguous()), _ptr(bias), _ptr(residual), act, M, N, K, bn, n_tail_groups,
+                            m_tail, _ptr(out), _ptr(out16), _stream())
     _check(lib, rc, 'dndm_test_gemm')
-    return out
+    return out, (None if out16 is None else out16[:M])
 
 
 class B200EGNNDynamics(torch.nn.Module):

@@ -57,8 +57,8 @@ class LigandGenerator:
                                      device=self.device, pocket_representation=self.pocket_representation)
 
     def _com(self, x: torch.Tensor, mask: torch.Tensor, n: int) -> torch.Tensor:
-        cnt = torch.bincount(mask, minlength=n).clamp(min=1).to(x.dtype)
-        return torch.zeros((n, x.shape[1]), device=x.device, dtype=x.dtype).index_add_(0, mask, x) / cnt[:, None]
+        from .sampler import segment_mean_sorted
+        return segment_mean_sorted(x, mask, n)
 
     @torch.no_grad()
     def generate_ligands(self, pdb_file, n_samples: int, pocket_ids: Optional[Sequence[str]] = None,

@@ -47,6 +47,23 @@ def polynomial_gamma(timesteps: int, precision: float, power: float) -> torch.Te
     return torch.from_numpy(-(np.log(alphas2) - np.log(sigmas2))).float()
 
 
+def segment_sum_sorted(x: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    """Per-segment sums of rows whose segment ids are sorted (batch masks, utils.py:145-153) WITHOUT atomics: an fp64 prefix
+    sum differenced at the segment boundaries.  ``index_add_`` on CUDA adds in whatever order its atomics land, which made
+    two trajectories from the same seed differ in the last bits (amplified by the reverse process); the per-sample means the
+    sampler takes (pocket centre, perturbation centring, inpainting anchors) therefore go through this."""
+    cnt = torch.bincount(idx, minlength=n)
+    ends = torch.cumsum(cnt, 0)
+    cs = torch.cumsum(x.double(), dim=0)
+    cs = torch.cat([torch.zeros_like(cs[:1]), cs], dim=0)
+    return (cs[ends] - cs[ends - cnt]).to(x.dtype)
+
+
+def segment_mean_sorted(x: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    cnt = torch.bincount(idx, minlength=n).clamp(min=1).to(x.dtype)
+    return segment_sum_sorted(x, idx, n) / cnt[:, None]
+
+
 def _event_fn(reward_fn, kind: str):
     """The reference scores SPSA rounds with my_reward_for_SPSA and ATP selections with my_reward_for_SVDD
     (conditional_model.py:743-744, 1187, 1200): a reward object may offer both through ``for_event(kind)``
@@ -309,7 +326,8 @@ class ConditionalSampler:
         if perturbations is None:                                                   # my_perturbation_for_molecule :724-736
             noise = (torch.randn((k, n_l, 3), device=self.device, generator=generator) if perturbation_noise is None
                      else self._h2d(torch.as_tensor(perturbation_noise, dtype=torch.float32)))
-            mean = torch.zeros((k, B, 3), device=self.device).index_add_(1, lig_mask, noise) / sizes[None, :, None]
+            mean = segment_sum_sorted(noise.permute(1, 0, 2).reshape(n_l, k * 3), lig_mask, B).reshape(B, k, 3).permute(1, 0, 2) \
+                / sizes[None, :, None]
             perturbations = zeta * (noise - mean[:, lig_mask])
         U = self._h2d(perturbations)
         reps = 2 * k
@@ -413,8 +431,7 @@ class ConditionalSampler:
             lig_mask = torch.repeat_interleave(torch.arange(B, device=dev), sizes)          # utils.py:145-153
             n_l = int(lig_mask.numel())
             # z_T ~ N(pocket COM, I), projected to the ligand-COM-free subspace (:923-930)
-            cnt = torch.bincount(pocket_mask, minlength=B).clamp(min=1).float()
-            mu_x = torch.zeros((B, 3), device=dev).index_add_(0, pocket_mask, x_p) / cnt[:, None]
+            mu_x = segment_mean_sorted(x_p, pocket_mask, B)
             mu = torch.cat([mu_x, torch.zeros((B, self.atom_nf), device=dev)], dim=1)[lig_mask].contiguous()
             ident = torch.tensor([[1.0, 0.0, 1.0]], device=dev).repeat(B, 1)
             z_lig, xh_pocket = self.engine.sampler_step(mu, None, self._noise(n_l, step_noise(n_l)), xh0_pocket, ident,
@@ -500,7 +517,7 @@ class ConditionalSampler:
             self.engine.set_static_masks(False)
         self._raise_on_flags()
         # CoG drift correction (:1431-1438)
-        cog = torch.zeros((B, 3), device=dev).index_add_(0, lig_mask, x_lig).abs().max().item()
+        cog = segment_sum_sorted(x_lig, lig_mask, B).abs().max().item()
         if cog > 5e-2:
             x_lig, x_pocket = self.remove_mean_batch(x_lig, x_pocket, lig_mask, pocket_mask, B)
         return torch.cat([x_lig, h_lig.float()], dim=1), torch.cat([x_pocket, h_pocket], dim=1), lig_mask, pocket_mask
@@ -543,8 +560,7 @@ class ConditionalSampler:
         nxt = lambda: self._noise(n_l, None if draws is None else next(draws))
 
         def seg_mean(x, idx):
-            cnt = torch.bincount(idx, minlength=B).clamp(min=1).float()
-            return torch.zeros((B, x.shape[1]), device=dev).index_add_(0, idx, x) / cnt[:, None]
+            return segment_mean_sorted(x, idx, B)
 
         com_pocket_0 = seg_mean(xh0_pocket[:, :3], pocket_mask)
         if center == 'ligand':

@@ -153,10 +153,16 @@ int dndm_get_profile(DndmEngine* e, double* ms_per_category, int32_t* launches_p
  * [n_layers, max_trace_nodes, 3] fp32, either may be NULL), every forward stores h and x after each block. */
 int dndm_set_trace(DndmEngine* e, float* h_trace, float* x_trace, int32_t max_trace_nodes);
 
-/* Self-test of the tcgen05 GEMM building block: C[M,N] = A[M,K] W[N,K]^T (+bias, optional SiLU), bf16 DEVICE
- * inputs, fp32 DEVICE output.  K % 64 == 0, N % 128 == 0. */
-int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const float* bias, int32_t act, int32_t M, int32_t N,
-                   int32_t K, float* out, void* stream);
+/* Self-test of the weight-resident tcgen05 node GEMM (gemm_wres_kernel) with the launch geometry of the forward:
+ *   C[M, N] = epilogue( A[M, K] (bf16) x W[N, K]^T (bf16) + bias [+ residual] ),  optional SiLU,
+ * (K, bn) in {(256, 256), (512, 128), (256, 128)}: bn output columns per resident weight group, N % bn == 0.  The last
+ * n_tail_groups column groups are computed for the first m_tail rows only (the ligand-row-only projections of the merged
+ * launch); their other outputs are left untouched.  residual: fp32 [M, 256] or NULL (N == 256).  Outputs: out_f32 fp32
+ * [M, N] and / or out_bf16 bf16 [ceil(M / 128) * 128, N] (TMA store), either may be NULL but not both; a_bf16 must be
+ * readable for ceil(M / 128) * 128 rows.  All pointers DEVICE. */
+int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const float* bias, const float* residual, int32_t act, int32_t M,
+                   int32_t N, int32_t K, int32_t bn, int32_t n_tail_groups, int32_t m_tail, float* out_f32, void* out_bf16,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,19 +56,34 @@ def _edges_from_csr(rp, col):
 # ---------------------------------------------------------------------------------------------------------------
 # tcgen05 GEMM building block
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('M,N,K,act', [(128, 128, 64, 0), (1, 128, 64, 0), (257, 256, 256, 1), (1000, 1536, 256, 0),
-                                       (333, 256, 512, 1)])
-def test_tcgen05_gemm(dev, M, N, K, act):
+@pytest.mark.parametrize('M,N,K,bn,act,res,tail', [
+    (128, 512, 256, 256, 0, False, (0, 0)),      # block-0 projection: two resident 256-column groups
+    (1, 256, 256, 256, 0, False, (0, 0)),
+    (1000, 1536, 256, 256, 0, False, (2, 333)),  # merged projection: 4 full groups + 2 ligand-row-only groups
+    (257, 1024, 256, 256, 0, False, (2, 40)),    # last block: 2 full + 2 tail groups
+    (333, 256, 512, 128, 1, False, (0, 0)),      # node MLP layer 1 (K = 512, SiLU)
+    (700, 256, 256, 128, 0, True, (0, 0)),       # node MLP layer 2 (+ fp32 residual, bf16 copy)
+])
+def test_tcgen05_node_gemm(dev, M, N, K, bn, act, res, tail):
+    """gemm_wres_kernel -- the kernel every node GEMM of the forward launches -- in all three compiled shapes, with tail
+    groups, bias, SiLU, the fp32 residual epilogue and the bf16 (TMA store) output, against a torch fp32 reference."""
     from diffndm_b200.engine import test_gemm
     g = torch.Generator().manual_seed(M * 7 + N)
     a = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
     w = (torch.randn(N, K, generator=g) * 0.1).to(dev).bfloat16()
     bias = torch.randn(N, generator=g).to(dev)
-    out = test_gemm(a, w, bias, act)
+    r = torch.randn(M, 256, generator=g).to(dev) if res else None
+    out, out16 = test_gemm(a, w, bias, act, bn=bn, residual=r, n_tail_groups=tail[0], m_tail=tail[1], want_bf16=True)
     ref = a.float() @ w.float().T + bias
+    if res:
+        ref = ref + r
     if act:
         ref = torch.nn.functional.silu(ref)
-    assert (out - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+    if tail[0]:                                   # tail groups: only the first m_tail rows are computed
+        ref[tail[1]:, N - tail[0] * bn:] = 0
+    tol = 2e-4 * max(1.0, ref.abs().max().item())
+    assert (out - ref).abs().max().item() < tol
+    assert (out16.float() - ref).abs().max().item() < tol + 8e-3 * ref.abs().max().item()      # bf16 rounding of the output
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -554,6 +569,67 @@ def test_atp_event_distributed_two_gpus():
     assert ret.get(0) and ret.get(1)
 
 
+def _atp_traj_worker(rank, world, port, ret):
+    import os
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    from diffndm_b200 import synthetic
+    from diffndm_b200.engine import B200EGNNDynamics
+    from diffndm_b200.sampler import ConditionalSampler
+    from diffndm_b200.weights import DynamicsConfig, random_init
+    dyn = B200EGNNDynamics(DynamicsConfig(), random_init(DynamicsConfig(), 0, 0.3), max_nodes=4096, max_edges=200000,
+                           max_samples=64).eval()
+    px, pt = synthetic.synthetic_pocket(8, 50)
+    B, G = 4, 5
+    sizes = np.array([6, 9, 5, 7])
+    oh = np.eye(10, dtype=np.float32)[pt]
+    pocket = {'x': torch.from_numpy(np.tile(px, (B, 1))), 'one_hot': torch.from_numpy(np.tile(oh, (B, 1))),
+              'size': torch.tensor([len(px)] * B), 'mask': torch.arange(B).repeat_interleave(len(px))}
+    smp = ConditionalSampler(dyn, timesteps=500)
+    pose = synthetic.synthetic_ligand_pose(8, sizes, px.mean(0))
+    pose[:, :3] -= px[0]
+    smp.eps_transform = synthetic.PointMassScore(pose, smp.gamma, len(px), 500, dev)
+    smp.set_distributed_atp(dist.group.WORLD, shared_seed=77)              # same trajectory noise, per-rank candidate draws
+    seen = []
+
+    def reward(x, types, mask):
+        x = x.double()
+        seen.append(float(x.sum()))
+        return [float(((x[mask == i] - x[mask == i].mean(0)) ** 2).sum(1).mean().sqrt()) for i in range(int(mask.max()) + 1)]
+
+    xh, xp, lm, _ = smp.sample_given_pocket(pocket, sizes, svdd=1, reward_fn=reward, svdd_groups=G)     # six ATP events
+    # every rank must end with the same molecules; the candidates the ranks drew must differ
+    zs = [torch.zeros_like(xh) for _ in range(world)] if xh.shape[0] == 27 else None
+    same = zs is not None
+    if same:
+        dist.all_gather(zs, xh.contiguous())
+        same = all(torch.equal(zs[0], q) for q in zs)
+    mine = torch.tensor(seen[:2], device=dev, dtype=torch.float64)       # the first event's look-ahead and candidate sums
+    other = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(other, mine)
+    distinct = not torch.equal(other[0], other[1])
+    ret[rank] = bool(same and distinct and len(seen) == 12 and torch.isfinite(xh).all())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (run under gpurun --gpus 2)')
+def test_atp_trajectory_distributed_two_gpus():
+    """A whole guided trajectory (six ATP events) with the candidate groups split over two ranks that share the trajectory:
+    the shared generator keeps the states identical between events, the per-rank generator makes the candidates distinct,
+    and the packed all-gather rebuilds the same winners (absolute pocket positions) on both ranks."""
+    import os
+    import torch.multiprocessing as mp
+    port = 29700 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_atp_traj_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)
+
+
 BOND_CASES, BOND_META = load_npz_groups('bonds.npz')
 
 
@@ -646,8 +722,6 @@ def test_forward_high_degree_receivers_vs_oracle(dyn, dev, golden_weights):
     px, pt = synthetic.synthetic_pocket(17, 40)
     sizes = np.array([300, 1, 7])
     b = synthetic.make_batch(px, pt, sizes, 17)
-    m0 = b['lig_mask'] == 0
-    b['xh_lig'][m0, :3] *= 3.0                               # spread the big ligand so that it touches the pocket
     t = np.array([[0.7], [0.2], [0.5]], np.float32)
     N, n_l = len(b['lig_mask']) + len(b['pocket_mask']), len(b['lig_mask'])
     trh, trx = dyn.engine.set_trace(N)
