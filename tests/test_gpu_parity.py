@@ -602,9 +602,12 @@ def _atp_traj_worker(rank, world, port, ret):
 
     xh, xp, lm, _ = smp.sample_given_pocket(pocket, sizes, svdd=1, reward_fn=reward, svdd_groups=G)     # six ATP events
     # every rank must end with the same molecules; the candidates the ranks drew must differ
-    zs = [torch.zeros_like(xh) for _ in range(world)] if xh.shape[0] == 27 else None
-    same = zs is not None
+    n = torch.tensor([xh.shape[0]], device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    same = all(int(k) == int(n) for k in ns)
     if same:
+        zs = [torch.zeros_like(xh) for _ in range(world)]
         dist.all_gather(zs, xh.contiguous())
         same = all(torch.equal(zs[0], q) for q in zs)
     mine = torch.tensor(seen[:2], device=dev, dtype=torch.float64)       # the first event's look-ahead and candidate sums
