@@ -83,7 +83,10 @@ def test_tcgen05_node_gemm(dev, M, N, K, bn, act, res, tail):
         ref[tail[1]:, N - tail[0] * bn:] = 0
     tol = 2e-4 * max(1.0, ref.abs().max().item())
     assert (out - ref).abs().max().item() < tol
-    assert (out16.float() - ref).abs().max().item() < tol + 8e-3 * ref.abs().max().item()      # bf16 rounding of the output
+    d16 = (out16.float() - ref).abs()
+    if tail[0]:          # the bf16 path stores whole 128-row blocks: tail-group rows up to the end of m_tail's row block hold
+        d16[tail[1]:-(-tail[1] // 128) * 128, N - tail[0] * bn:] = 0          # (valid) values the forward never reads
+    assert d16.max().item() < tol + 8e-3 * ref.abs().max().item()              # bf16 rounding of the output
 
 
 # ---------------------------------------------------------------------------------------------------------------
