@@ -211,7 +211,7 @@ static int dev_alloc(T** p, size_t n) {
         if (_r != DNDM_OK) return _r; \
     } while (0)
 
-extern "C" const char* dndm_version(void) { return "diffndm_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+extern "C" const char* dndm_version(void) { return "diffndm_b200 0.2 (sm_100a, tcgen05/TMA)"; }
 extern "C" const char* dndm_last_error(void) { return g_err; }
 extern "C" int64_t dndm_launch_count(void) { return g_launches; }
 
