@@ -680,7 +680,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             ProfScope ps(e, PROF_GEMM, st);
             WresEpilogue ep1{L.b3, nullptr, 0, nullptr, 0, 0, 1, 0, 1};          // hid = SiLU(W3 [h | agg] + b3), K = 512
             RET_IF((launch_wres<512, 128>(st, e->tm_hcat, L.tm_w3, e->to_hid32, N, 2, 0, 0, ep1, 0, 0, pdl)));
-            WresEpilogue ep2{L.b4, e->h, 256, e->h, 256, 0, 1, 0};       // h += W4 hid + b4 ; bf16 copy -> hcat[:, :256]
+            WresEpilogue ep2{L.b4, e->h, 256, e->h, 256, 0, 1, 0, 0, e->hcat, 512};   // h += W4 hid + b4 ; bf16 copy -> hcat[:, :256]
             RET_IF((launch_wres<256, 128>(st, e->tm_hid, L.tm_w4, e->to_hcat32, N, 2, 0, 0, ep2, 0, 0, pdl)));
         }
         // ---- node projections: this block's coordinate heads (sender parts for every node, receiver parts for the
@@ -926,7 +926,8 @@ extern "C" int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const floa
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
-    WresEpilogue ep{bias, residual, 256, out_f32, N, 0, out_bf16 ? 1 : 0, 0, act};
+    WresEpilogue ep{bias, residual, 256, out_f32, N, 0, out_bf16 ? 1 : 0, 0, act, reinterpret_cast<__nv_bfloat16*>(out_bf16), N};
+    if (residual && !s128) return set_err(DNDM_EINVAL, "the residual epilogue exists for (K, BN) = (256, 128) only");
     const int n_full = N / bn - n_tail_groups;
     if (s256) return launch_wres<256, 256>(st, ta, tw, to, M, n_full, 0, 0, ep, n_tail_groups, m_tail);
     if (s512) return launch_wres<512, 128>(st, ta, tw, to, M, n_full, 0, 0, ep, n_tail_groups, m_tail);

@@ -31,12 +31,18 @@ constexpr int WR_OUT_BYTES = WR_EPI_WARPS * WR_NSLAB * WR_SLAB16_BYTES;
 // refilled after the MMA that read it has completed, so every row block exposes most of a TMA round trip (~1 us under
 // load; scripts/wr_timeline.py: row-block period 4 100 cycles against 1 100 of MMA) -- the reason these kernels sit at
 // ~2 TB/s of DRAM traffic.  A deeper ring needs BN = 128, which doubles the A re-reads from L2 and ends up equal.
+constexpr int WR_RTILE_LD = 33;                                   // fp32 [32][33] transpose tile per epilogue warp (padded: conflict-free)
+constexpr int WR_RTILE_BYTES = 32 * WR_RTILE_LD * 4;            //   4224
 template <int kK, int kBN>
 struct WresShape {
     static constexpr int w_bytes = kK * kBN * 2;
-    static constexpr int avail = 232448 - 256 - WR_OUT_BYTES - w_bytes;
+    // the residual epilogue (node-MLP layer 2, the only shape with weights small enough to leave room) goes through a
+    // per-warp transpose tile so that the fp32 residual stream is read and written with full 128-byte rows
+    static constexpr bool has_rtile = (kK == 256 && kBN == 128);
+    static constexpr int rtile_bytes = has_rtile ? WR_EPI_WARPS * WR_RTILE_BYTES : 0;
+    static constexpr int avail = 232448 - 256 - WR_OUT_BYTES - w_bytes - rtile_bytes;
     static constexpr int stages = avail / WR_STAGE_BYTES > WR_MAX_STAGES ? WR_MAX_STAGES : avail / WR_STAGE_BYTES;
-    static constexpr int smem_bytes = w_bytes + stages * WR_STAGE_BYTES + WR_OUT_BYTES + 256;
+    static constexpr int smem_bytes = w_bytes + stages * WR_STAGE_BYTES + WR_OUT_BYTES + rtile_bytes + 256;
     static_assert(stages >= 4, "gemm_wres: A ring too shallow");
 };
 
@@ -47,9 +53,11 @@ struct WresEpilogue {
     float* out_f32;           // [M, ld_f32] fp32 destination or nullptr; column offset col0_f32
     int ld_f32;
     int col0_f32;
-    int has_bf16;             // store bf16 through tmap_o16 at column offset col0_bf16
-    int col0_bf16;
+    int has_bf16;             // store bf16 at column offset col0_bf16: through tmap_o16 (TMA) or, in the residual epilogue,
+    int col0_bf16;            // directly to out_bf16 [M, ld_bf16]
     int act;                  // 1: SiLU
+    __nv_bfloat16* out_bf16;  // residual epilogue only
+    int ld_bf16;
 };
 
 #ifdef DNDM_EK_TRACE
@@ -77,7 +85,8 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* sW = smem;                                           // [KB k-chunks][BN rows][128 B]
     uint8_t* sA = smem + kWBytes;                                 // ring of [128 rows][128 B]
     uint8_t* sOut = sA + WR_STAGES * WR_STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + WR_OUT_BYTES);
+    float* sRT = reinterpret_cast<float*>(sOut + WR_OUT_BYTES);   // [epilogue warp][32][33] fp32 (has_rtile shapes only)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + WR_OUT_BYTES + WresShape<kK, kBN>::rtile_bytes);
     uint64_t* empty_bar = full_bar + WR_STAGES;
     uint64_t* acc_full = empty_bar + WR_STAGES;      // [2]
     uint64_t* acc_empty = acc_full + 2;              // [2]
@@ -213,6 +222,61 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
             };
+            if constexpr (WresShape<kK, kBN>::has_rtile) {
+                if (ep.residual) {
+                    // ---- residual epilogue with coalesced global access: h_new = h_old + acc + bias, fp32 in place + bf16 copy.
+                    //      The accumulator arrives one ROW per thread; a padded per-warp tile turns it into 4 rows x 128
+                    //      contiguous bytes per warp instruction for the global read-modify-write. ----
+                    float* tile = sRT + (warp - 2) * (32 * WR_RTILE_LD);
+                    const int rr = lane >> 3, cq = (lane & 7) * 4;          // this lane's row-in-group and 4-column quad
+                    mbar_wait(&acc_full[buf], (it >> 1) & 1);
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int cc = 0; cc < WR_CHUNKS; ++cc) {
+                        const int c = part * WR_CHUNKS + cc;
+                        const int col0 = grp * WR_BN + c * 32;
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + buf * WR_BN + ((uint32_t)(q * 32) << 16) + c * 32, v);
+                        // the old h of the 32 x 32 block: 8 coalesced 16-byte loads per lane, in flight during the TMEM read
+                        float4 hold[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const long gr = (long)row0 + i * 4 + rr;
+                            hold[i] = gr < M ? *reinterpret_cast<const float4*>(ep.residual + gr * ep.ldr + col0 + cq)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        float bq[4] = {0.f, 0.f, 0.f, 0.f};                 // bias of this lane's column quad
+                        if (ep.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cq));
+                            bq[0] = b.x; bq[1] = b.y; bq[2] = b.z; bq[3] = b.w;
+                        }
+                        tmem_ld_wait();
+                        __syncwarp();                                       // the previous chunk's reads of the tile are done
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) tile[lane * WR_RTILE_LD + j] = __uint_as_float(v[j]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + rr;
+                            const long gr = (long)row0 + r;
+                            const float* tp = tile + r * WR_RTILE_LD + cq;
+                            float4 o = make_float4(hold[i].x + (tp[0] + bq[0]), hold[i].y + (tp[1] + bq[1]),
+                                                   hold[i].z + (tp[2] + bq[2]), hold[i].w + (tp[3] + bq[3]));
+                            if (ep.act) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+                            if (gr < M) {
+                                if (ep.out_f32)
+                                    *reinterpret_cast<float4*>(ep.out_f32 + gr * ep.ld_f32 + ep.col0_f32 + col0 + cq) = o;
+                                if (ep.has_bf16)
+                                    *reinterpret_cast<uint2*>(ep.out_bf16 + gr * ep.ld_bf16 + ep.col0_bf16 + col0 + cq) =
+                                        make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+                            }
+                        }
+                    }
+                    tc_fence_before_sync();
+                    mbar_arrive(&acc_empty[buf]);
+                    continue;
+                }
+            }
             float f[32];
             load_addend(part * WR_CHUNKS, f);
             mbar_wait(&acc_full[buf], (it >> 1) & 1);

@@ -140,7 +140,8 @@ class _GraphedReverseStep:
         self.xp.copy_(keep_p)
         torch.cuda.synchronize(dev)
         torch.cuda.set_rng_state(rng, dev)
-        eng.read_flags()                                       # the dry runs may have tripped the COM-drift flag (state restored above)
+        eng.read_flags(consume=FLAG_COM_DRIFT)                 # the dry runs may have tripped the COM-drift flag (state restored
+                                                               # above); NaN / overflow bits of earlier calls stay pending
 
     def __call__(self, t_dev: torch.Tensor, coef_dev: torch.Tensor):
         """t_dev: 0-d device tensor, coef_dev: [3] device tensor (same for every sample of an unguided step)."""

@@ -83,7 +83,7 @@ def test_fixture_matches_weights(fx, golden_weights):
     assert (kinds == 1).sum() == 6 and (kinds == 2).sum() == 16 and (kinds == 3).sum() == 1      # ATP, SPSA, s == 30
 
 
-@pytest.mark.parametrize('s', [30, 28, 0])
+@pytest.mark.parametrize('s', [30, 0])
 def test_spsa_event_matches_reference(fx, golden_weights, s):
     e = fx.ev[f'spsa{s}']
     orc = make_oracle(fx, golden_weights, fx.d0('spsa', s))
@@ -126,7 +126,7 @@ def _perturbations(fx, s, lm, zeta, k):
     return np.stack(out)
 
 
-@pytest.mark.parametrize('s', [50, 40, 30, 20])
+@pytest.mark.parametrize('s', [50, 30, 20])
 def test_atp_event_matches_reference(fx, golden_weights, s):
     e = fx.ev[f'atp{s}']
     orc = make_oracle(fx, golden_weights, fx.d0('atp', s))
