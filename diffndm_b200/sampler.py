@@ -557,8 +557,14 @@ class ConditionalSampler:
         fixed = lig_fixed.to(dev).reshape(-1).float()
         fx = fixed > 0
         n_l = int(lig_mask.numel())
-        draws = iter(noise) if noise is not None else None
-        nxt = lambda: self._noise(n_l, None if draws is None else next(draws))
+        provider = noise if isinstance(noise, NoiseProvider) else None
+        draws = iter(noise) if (noise is not None and provider is None) else None
+
+        def draw_one():
+            if provider is not None:
+                return self._h2d(torch.as_tensor(provider.step(n_l), dtype=torch.float32))
+            return None if draws is None else next(draws)
+        nxt = lambda: self._noise(n_l, draw_one())
 
         def seg_mean(x, idx):
             return segment_mean_sorted(x, idx, B)
@@ -586,11 +592,13 @@ class ConditionalSampler:
             coef_renoise = torch.stack([alpha_ts, zero, torch.sqrt(sigma2_ts)], dim=1).to(dev)
             for u in range(resamplings):
                 z_unknown, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
-                                                                 noise=None if draws is None else next(draws), n_samples=B)
+                                                                 noise=draw_one(), n_samples=B)
                 if reward_fn is not None and spsa_window[0] <= s <= spsa_window[1] and u < 1:
                     zeta = 1e-3 * (s / 1200)                                              # :1571-1572
+                    pn, xn = self._spsa_draws(provider, spsa_k, lig_mask, B)
                     z_upd, xh_pocket = self.my_update_z_lig(z_lig, xh_pocket, lig_mask, pocket_mask, t_array, B, zeta,
-                                                            reward_fn, guidance_scale=1e-3, k=spsa_k)
+                                                            reward_fn, guidance_scale=1e-3, k=spsa_k, perturbation_noise=pn,
+                                                            x0_noise=xn)
                     z_unknown, xh_pocket = self._unnormalize_quirk(z_upd, xh_pocket, lig_mask, pocket_mask, B)
                 # known atoms follow the pocket's accumulated translation, then q(z_s | x)
                 com_pocket = seg_mean(xh_pocket[:, :3], pocket_mask)
@@ -610,10 +618,10 @@ class ConditionalSampler:
                     raise NotImplementedError("ATP re-batching inside inpaint keeps ligand['mask'] (conditional_model.py:"
                                               "1626, 1779): only defined for equally sized ligands")
                 z_lig, xh_pocket, _ = self._atp_event(s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask, B,
-                                                      reward_fn, svdd_groups)
+                                                      reward_fn, svdd_groups, provider=provider, x0_pocket_group0=xh0_pocket)
                 z_lig, xh_pocket = self._unnormalize_quirk(z_lig, xh_pocket, lig_mask, pocket_mask, B)
         x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(
-            z_lig, xh_pocket, lig_mask, pocket_mask, B, noise=None if draws is None else next(draws))
+            z_lig, xh_pocket, lig_mask, pocket_mask, B, noise=draw_one())
         self._raise_on_flags()
         return torch.cat([x_lig, h_lig.float()], dim=1), torch.cat([x_pocket, h_pocket], dim=1), lig_mask, pocket_mask
 
@@ -645,7 +653,7 @@ class ConditionalSampler:
         return self._rebatch(top_idx, big_z, big_p, big_lig_mask, n_p)
 
     def _atp_event(self, s, s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask, B, reward_fn, n_groups,
-                   provider=None):
+                   provider=None, x0_pocket_group0=None):
         """Draw n_groups-1 extra candidate next-states from (z, s, t), score the current and x0-look-ahead molecules of
         all n_groups*B candidates, keep the global top-B (:1203-1232).  The candidate groups are evaluated as ONE batch of
         n_groups*B samples per denoiser call instead of the reference's sequential calls.
@@ -653,7 +661,11 @@ class ConditionalSampler:
         With ``self.atp_group`` set (a torch.distributed group whose ranks carry the SAME trajectory state: same seed of the
         default generator, see ``set_distributed_atp``), the candidate groups are split over the ranks -- group g is drawn
         (from the per-rank candidate generator), denoised and scored on rank g % world -- and the winners are rebuilt
-        everywhere from ONE all-gather of scores, latents and absolute pocket positions (parallel.py)."""
+        everywhere from ONE all-gather of scores, latents and absolute pocket positions (parallel.py).
+
+        ``x0_pocket_group0``: pocket used for the x0 look-ahead of the CURRENT state only.  The inpainting loop passes the
+        original, untranslated pocket there, as the reference does (``my_to_x0(t_array, z_lig, xh0_pocket, ...)``,
+        conditional_model.py:1631, while the extra candidates look ahead from their own translated pockets, :1651)."""
         dev = self.device
         n_l, n_p = z_lig.shape[0], xh_pocket.shape[0]
         G = n_groups
@@ -695,7 +707,10 @@ class ConditionalSampler:
                 cand_x, cand_t = big_z[:, :3].contiguous(), big_z[:, 3:].argmax(1)
                 ready = torch.cuda.Event()
                 ready.record()
-            x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(n_here, 1), big_z, big_p, big_lig_mask, big_pocket_mask, n_here * B,
+            look_p = big_p
+            if x0_pocket_group0 is not None and rank == 0:
+                look_p = torch.cat([x0_pocket_group0.to(big_p.dtype), big_p[n_p:]], dim=0)
+            x0_l, h0_l, _, _ = self.my_to_x0(t_array.repeat(n_here, 1), big_z, look_p, big_lig_mask, big_pocket_mask, n_here * B,
                                              noise=x0_nz)
             if overlap:
                 pending_r = reward_fn.submit(cand_x, cand_t, big_lig_mask, after=ready)

@@ -13,7 +13,7 @@ Follows, call by call and draw by draw, ``ConditionalDDPM`` of /root/reference/e
 * ``handle_to_mol``'s translation      :845-864  (applied to what the reward sees)
 
 Pinned by tests/golden/guidance.npz, which tests/golden/make_golden_guidance.py generates by running the unmodified
-reference with stubbed chemistry (tests/test_oracle_golden.py replays it).
+reference with stubbed chemistry (tests/test_guidance_oracle.py replays it).
 
 Everything that is external in the reference is injected: ``dyn(z, xp, t[B,1], lig_mask, pocket_mask) -> eps_lig`` (the
 denoiser), ``reward_fn(x, types, lig_mask) -> list[float]`` (handle_to_mol + my_reward_for_SPSA/_SVDD) and
@@ -124,10 +124,11 @@ class GuidanceOracle:
         onehot = np.eye(z.shape[1] - 3, dtype=F32)[tl]
         return np.concatenate([xl, onehot], 1), np.concatenate([xpk, hpk], 1)
 
-    def atp_event(self, s, s_arr, t_arr, z, xp, lm, pm, n_extra=4):
-        """:1085-1241."""
+    def atp_event(self, s, s_arr, t_arr, z, xp, lm, pm, n_extra=4, x0_pocket_group0=None):
+        """:1085-1241; the inpainting loop's copy (:1629-1778) looks ahead from the current state with the ORIGINAL pocket
+        ``xh0_pocket`` (:1631) -- pass it as ``x0_pocket_group0``."""
         nb = len(t_arr)
-        cands0 = [self._x0_pair(t_arr, z, xp, lm, pm)]                    # :1095
+        cands0 = [self._x0_pair(t_arr, z, xp if x0_pocket_group0 is None else x0_pocket_group0, lm, pm)]      # :1095 / :1631
         cands = [(z, xp)]
         for _ in range(n_extra):
             z_tmp, xp_tmp = self.reverse_step(s_arr, t_arr, z, xp, lm, pm)            # :1112-1117

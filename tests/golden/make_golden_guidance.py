@@ -151,6 +151,83 @@ def run_full(cfg, W, seed, B, n_atoms, n_pocket, svdd, spsa, timesteps=500):
     return inputs, final, rec.log, stream
 
 
+def run_inpaint(cfg, W, seed, B, n_atoms, n_fixed, n_pocket, timesteps, resamplings, svdd=1):
+    """The unmodified ``ConditionalDDPM.inpaint`` (conditional_model.py:1491-1790) with its hard-wired SPSA window
+    (12 <= s <= 16, first resampling) and, with svdd = 1, the ATP block at s <= 10, s % 2 == 0 (:1629-1778)."""
+    px, pt, sizes, x0_rel = make_case(cfg, W, seed, B, n_atoms, n_pocket)
+    dyn, ddpm = build_reference_model(cfg, W)
+    ddpm.dynamics = SyntheticScoreDynamics(dyn, x0_rel)
+    stream = NoiseStream(seed)
+    rec = Recorder(ddpm, stream)
+    onehot = np.eye(cfg.atom_nf, dtype=np.float32)
+    pocket = {'x': T(np.tile(px, (B, 1))), 'one_hot': T(np.tile(onehot[pt], (B, 1))),
+              'size': torch.tensor([n_pocket] * B), 'mask': torch.arange(B).repeat_interleave(n_pocket)}
+    lig_x = np.tile(x0_rel[:, :3] + px[0], (B, 1)).astype(np.float32)                       # the pose itself is the input ligand
+    lig_t = np.tile(x0_rel[:, 3:].argmax(1), B)
+    fixed = np.tile((np.arange(n_atoms) < n_fixed).astype(np.float32), B)
+    lig_mask = np.repeat(np.arange(B), n_atoms)
+    ligand = {'x': T(lig_x.copy()), 'one_hot': T(onehot[lig_t].copy()), 'size': torch.tensor(sizes), 'mask': T(lig_mask)}
+    com_before = T(np.tile(px.mean(0, dtype=np.float64).astype(np.float32), (B, 1)))
+    keep = torch.randn
+    torch.randn = stream.randn
+    try:
+        with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
+            xh_lig, xh_pocket, lm, pm = ddpm.inpaint(ligand, pocket, T(fixed), svdd, com_before, None, False, 0, False,
+                                                     resamplings=resamplings, return_frames=1, timesteps=timesteps, center='ligand')
+    finally:
+        torch.randn = keep
+        rec.restore()
+    inputs = dict(pocket_x=px, pocket_t=pt, sizes=sizes, x0_rel=x0_rel, com_before=npy(com_before), lig_x=lig_x, lig_t=lig_t,
+                  lig_fixed=fixed, timesteps=np.asarray(timesteps), resamplings=np.asarray(resamplings))
+    final = dict(final_lig=npy(xh_lig), final_pocket=npy(xh_pocket))
+    return inputs, final, rec.log, stream
+
+
+def parse_inpaint_log(log, timesteps, resamplings, svdd, G=5):
+    it = iter(log)
+
+    def nxt(kind, depth):
+        e = next(it)
+        assert e['kind'] == kind and e['depth'] == depth, (e['kind'], e['depth'], kind, depth)
+        return e
+
+    events = []
+    for s in reversed(range(timesteps)):
+        for u in range(resamplings):
+            st = nxt('step', 0)
+            events.append(dict(kind='step', s=s, u=u, d0=st['d0'], z_in=st['z_in'], xp_in=st['xp_in'], lm=st['lm']))
+            if 12 <= s <= 16 and u < 1:
+                up = nxt('spsa', 0)
+                ev = dict(kind='spsa', s=s, d0=up['d0'], z_in=up['z_in'], xp_in=up['xp_in'], lm=up['lm'], zeta=up['zeta'],
+                          guidance_scale=up['guidance_scale'], z_out=up['z_out'], xp_out=up['xp_out'])
+                plus_x, minus_x, fp, fm = [], [], [], []
+                for _ in range(K_SPSA):
+                    nxt('x0', 1); nxt('xh0', 2); nxt('x0', 1); nxt('xh0', 2)
+                    ma = nxt('mol', 1); mb = nxt('mol', 1); ra = nxt('reward', 1); rb = nxt('reward', 1)
+                    plus_x.append(ma['x']); minus_x.append(mb['x']); fp.append(ra['r']); fm.append(rb['r'])
+                ev.update(mol_x=np.stack(plus_x + minus_x).astype(np.float32), f_plus=np.stack(fp), f_minus=np.stack(fm))
+                events.append(ev)
+        if svdd == 1 and s <= 10 and s % 2 == 0:
+            x0c = nxt('x0', 0); nxt('xh0', 1)
+            ev = dict(kind='atp', s=s, d0=x0c['d0'], z_in=x0c['z_in'], xp0=x0c['xp_in'], lm=x0c['lm'])
+            cand_z = []
+            for i in range(G - 1):
+                c = nxt('step', 0)
+                if i == 0:
+                    ev['xp_in'] = c['xp_in']                         # the translated pocket of the current state
+                cand_z.append(c['z_out'])
+                nxt('x0', 0); nxt('xh0', 1)
+            nxt('mol', 0); r0 = nxt('reward', 0); nxt('mol', 0); r1 = nxt('reward', 0)
+            ev.update(cand_z=np.stack(cand_z), r0=r0['r'], r=r1['r'])
+            events.append(ev)
+    fin = nxt('xh0', 0)
+    events.append(dict(kind='final', d0=fin['d0'], z_in=fin['z_in'], xp_in=fin['xp_in'], lm=fin['lm']))
+    for a, b in zip(events[:-1], events[1:]):
+        if a['kind'] == 'atp':
+            a['z_after'], a['xp_after'] = b['z_in'], b['xp_in']
+    return events
+
+
 def parse_log(log, timesteps, svdd, spsa, G=5):
     """Cut the flat call log into the events of the sampling loop (conditional_model.py:944-1420)."""
     it = iter([e for e in log])
@@ -276,6 +353,27 @@ def main():
     store(case, inputs, final, events, stream)
     print(case, 'events', {k: sum(e['kind'] == k for e in events) for k in ('step', 'atp', 'spsa', 'mixed')},
           'draws', len(stream.shapes), '|z| final', np.abs(final['final_lig'][:, :3]).max())
+
+    # inpainting with its guidance branches: SPSA window 12 <= s <= 16, ATP at s <= 10 (svdd = 1)
+    case = 'inpaint_b20'
+    stream_seed[case] = 2025
+    inputs, final, log, stream = run_inpaint(cfg, W, stream_seed[case], B=20, n_atoms=4, n_fixed=2, n_pocket=8, timesteps=20,
+                                             resamplings=2, svdd=1)
+    ev_i = parse_inpaint_log(log, 20, 2, 1)
+    for k, v in {**inputs, **final}.items():
+        out[f'{case}/{k}'] = np.asarray(v)
+    out[f'{case}/noise_seed'] = np.asarray(stream_seed[case])
+    out[f'{case}/draw_shapes'] = np.asarray([list(sh) + [0] * (2 - len(sh)) for sh in stream.shapes], np.int16)
+    index = []
+    for ev in ev_i:
+        index.append((['step', 'atp', 'spsa', 'mixed', 'final'].index(ev['kind']), ev.get('s', -1), ev['d0']))
+        if (ev['kind'], ev.get('s')) in {('spsa', 16), ('spsa', 15), ('atp', 10), ('atp', 8)}:
+            for k, v in ev.items():
+                if k not in ('kind', 's', 'd0'):
+                    out[f'{case}/{ev["kind"]}{ev["s"]}/{k}'] = np.asarray(v)
+    out[f'{case}/event_index'] = np.asarray(index, np.int32)
+    print(case, 'events', {k: sum(e['kind'] == k for e in ev_i) for k in ('step', 'atp', 'spsa')}, 'draws', len(stream.shapes),
+          '|x| final', np.abs(final['final_lig'][:, :3]).max())
 
     path = os.path.join(HERE, 'guidance.npz')
     np.savez_compressed(path, **out)

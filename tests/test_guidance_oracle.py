@@ -169,3 +169,55 @@ def test_mixed_s30_event_matches_reference(fx, golden_weights):
     assert np.abs(r0 - e['r0']).max() < 5e-4 and np.abs(r - e['r']).max() < 5e-5
     assert np.array_equal(lm_new, e['lm_after'])
     assert np.abs(z - e['z_after'])[:, :3].max() < 2e-5 and np.abs(xp - e['xp_after'])[:, :3].max() < 2e-5
+
+
+# ---- the inpainting loop's guidance branches (conditional_model.py:1570-1586 SPSA window, :1629-1778 ATP block) ----------
+@pytest.fixture(scope='module')
+def fxi():
+    return Fixture('inpaint_b20')
+
+
+def test_inpaint_event_schedule(fxi):
+    kinds, s = fxi.index[:, 0], fxi.index[:, 1]
+    assert sorted(s[kinds == 2].tolist()) == [12, 13, 14, 15, 16]              # SPSA: 12 <= s <= 16, first resampling only
+    assert sorted(s[kinds == 1].tolist()) == [0, 2, 4, 6, 8, 10]               # ATP: s <= 10, s % 2 == 0
+    assert (kinds == 0).sum() == 40                                            # 20 steps x 2 resamplings
+
+
+def _arrs_T(fx, s, T):
+    B = fx.B
+    return (np.full((B, 1), s, np.float32) / np.float32(T), (np.full((B, 1), s, np.float32) + np.float32(1)) / np.float32(T))
+
+
+def test_inpaint_spsa_event_matches_reference(fxi, golden_weights):
+    e = fxi.ev['spsa16']
+    assert abs(float(e['zeta']) - 1e-3 * (16 / 1200)) < 1e-12                  # zeta = 1e-3 * s / 1200 here (:1571-1572)
+    orc = make_oracle(fxi, golden_weights, fxi.d0('spsa', 16))
+    _, t_arr = _arrs_T(fxi, 16, 20)
+    lm = e['lm'].astype(np.int64)
+    z, xp = orc.my_update_z_lig(e['z_in'], e['xp_in'], lm, fxi.pm, t_arr, float(e['zeta']), float(e['guidance_scale']))
+    fp, fm = [t for t in orc.trace if t[0] == 'spsa_rewards'][0][1:]
+    assert np.abs(fp - e['f_plus']).max() < 2e-4 and np.abs(fm - e['f_minus']).max() < 2e-4
+    assert np.abs(z - e['z_out'])[:, :3].max() < 2e-6 and np.abs(xp - e['xp_out'])[:, :3].max() < 2e-6
+
+
+@pytest.mark.parametrize('s', [10])
+def test_inpaint_atp_event_matches_reference(fxi, golden_weights, s):
+    """The inpainting copy of the ATP block looks ahead from the current state with the ORIGINAL pocket (:1631)."""
+    e = fxi.ev[f'atp{s}']
+    orc = make_oracle(fxi, golden_weights, fxi.d0('atp', s))
+    s_arr, t_arr = _arrs_T(fxi, s, 20)
+    lm = e['lm'].astype(np.int64)
+    assert np.abs(e['xp0'] - e['xp_in'])[:, :3].max() > 1e-3                   # the two pockets do differ
+    z, xp, lm_new = orc.atp_event(s, s_arr, t_arr, e['z_in'], e['xp_in'], lm, fxi.pm, x0_pocket_group0=e['xp0'])
+    r0, r = [t for t in orc.trace if t[0] == 'atp_rewards'][0][1:]
+    cands = np.stack([t[1] for t in orc.trace if t[0] == 'cand'])
+    scale = max(1.0, float(np.abs(e['z_in'][:, 3:]).max()))
+    assert np.abs(cands - e['cand_z'])[:, :, :3].max() < 1e-4
+    assert np.abs(r - e['r']).max() < 1e-4
+    assert np.abs(r0 - e['r0']).max() < 5e-3 * max(1.0, np.log10(scale))       # look-ahead through a net fed 4^k-scaled features
+    # with the wrong pocket for group 0 the look-ahead rewards of that group change
+    orc2 = make_oracle(fxi, golden_weights, fxi.d0('atp', s))
+    orc2.atp_event(s, s_arr, t_arr, e['z_in'], e['xp_in'], lm, fxi.pm)
+    r0_wrong = [t for t in orc2.trace if t[0] == 'atp_rewards'][0][1]
+    assert np.abs(r0_wrong[:fxi.B] - e['r0'][:fxi.B]).max() > 10 * np.abs(r0[:fxi.B] - e['r0'][:fxi.B]).max()
