@@ -147,13 +147,9 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
     float dot = 0.f;
     uint8_t* rowp = slab + lane * 64;                  // slab = [32 rows][32 bf16 = 64 B], SWIZZLE_64B
     const uint32_t sw = (lane >> 1) & 3;
-#pragma unroll
-    for (int cc_ = 0; cc_ < 8; ++cc_) {
-        const int c = kHalf * 8 + cc_;                 // 16-column chunk of the 256 channels
+    // one 16-column chunk of the accumulator row: SiLU, partial dot, bf16 staging (+ TMA store of every finished 32 columns)
+    auto chunk = [&](int c, uint32_t (&v)[16]) {
         const int col0 = c * 16;
-        uint32_t v[16];
-        tmem_ld16(d_tmem + col0, v);
-        tmem_ld_wait();
         float m[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -182,6 +178,20 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
                 }
             }
         }
+    };
+    // the TMEM load of chunk c + 1 is in flight while chunk c is evaluated (tcgen05.wait::ld covers every outstanding load of
+    // the thread, so the next load is issued right after the wait)
+    uint32_t va[16], vb[16];
+    tmem_ld16(d_tmem + kHalf * 128, va);
+#pragma unroll
+    for (int cc_ = 0; cc_ < 8; cc_ += 2) {
+        const int c = kHalf * 8 + cc_;                 // 16-column chunk of the 256 channels
+        tmem_ld_wait16(va);
+        tmem_ld16(d_tmem + (c + 1) * 16, vb);
+        chunk(c, va);
+        tmem_ld_wait16(vb);
+        if (cc_ + 2 < 8) tmem_ld16(d_tmem + (c + 2) * 16, va);
+        chunk(c + 1, vb);
     }
     return dot;
 }
@@ -249,7 +259,10 @@ edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_consta
         // the resident second-layer weights are constant: their load runs under the predecessor's tail (before pdl_wait)
         mbar_arrive_expect_tx(w_bar, EK_W2_BYTES);
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
+        for (int kc = 0; kc < 4; ++kc) {           // boxes of 128 output channels x 64 inputs (shared with the pair kernel)
+            tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
+            tma_load_2d(sW + kc * 32768 + 16384, tmap_w, w_bar, kc * 64, 128);
+        }
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     // bias step operands (K-major core matrices, no swizzle): A[r][0] = A[r][1] = 1 ; B[n][0] + B[n][1] = b2[n]

@@ -1,0 +1,403 @@
+// Fused per-edge MLP on a CTA PAIR (tcgen05 cta_group::2): the same computation as edge_mlp.cuh (egnn_new.py:31-47 and
+// :96-110), one 256-edge tile per pair and iteration.
+//
+// Why a pair.  With one CTA per 128-edge tile the resident second-layer weights W2 (128 KiB) leave room for ONE A tile
+// (64 KiB): the producers of tile i+1 store only after the MMA of tile i has finished reading it, and the tensor core
+// re-reads all of W2 from shared memory for every 128 edges.  As a pair the two CTAs issue ONE tcgen05.mma of M = 256
+// (each CTA contributes its own 128 edges as A rows) x N = 256 x K = 16, with the B operand SPLIT over the pair: CTA r holds
+// output channels [128 r, 128 r + 128) of W2 (64 KiB).  Per CTA that is 64 KiB of weights + TWO A tiles (2 x 64 KiB): the
+// producers run a whole tile ahead of the tensor core, and the B-operand shared-memory reads per edge are halved.  Each
+// CTA's TMEM receives its own 128 edges x all 256 channels, so the epilogue is unchanged (epilogue_row).
+//
+// Roles per CTA (800 threads as before): warps 0-7 epilogue, 8-23 producers, warp 24 lane 0: MMA issue (leader CTA, rank 0)
+// / weight-arrival forwarding (rank 1).  Cross-CTA signalling goes through mbarriers in the LEADER's shared memory:
+//   a_full[2]     : 16 producer warps of each CTA arrive (remote arrive, release.cluster) when their rows of A[buf] are written
+//   tmem_empty[2] : 8 epilogue warps of each CTA arrive when accumulator buf is drained
+//   mma_done[2]   : in BOTH CTAs, signalled by tcgen05.commit.multicast -- accumulator ready (epilogue) and A[buf] free (producers)
+#pragma once
+#include "edge_mlp.cuh"
+
+namespace dndm {
+
+constexpr int EP_WH_BYTES = 128 * EK_H * 2;             //  65536  this CTA's half of W2: 128 output channels x 256 inputs
+constexpr int EP_BX_BYTES = 128 * 16 * 2;               //   4096  bias step, B slice of this CTA's 128 channels
+constexpr int EP_MISC_BYTES = EK_SLAB_BYTES + EK_AX_BYTES + EP_BX_BYTES + EK_META_BYTES + EK_DOT_BYTES + 256;
+constexpr int EP_SMEM_BYTES = EP_WH_BYTES + 2 * EK_A_BYTES + EP_MISC_BYTES;
+static_assert(EP_SMEM_BYTES <= 232448, "pair edge kernel shared memory exceeds 227 KiB");
+
+DNDM_DEVICE uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+DNDM_DEVICE uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+// Remote arrive with the default semantics, as CUTLASS's generic-proxy -> 2-SM UMMA pipelines do (fence.proxy.async.shared::cta
+// + mbarrier.arrive.shared::cluster on the leader's barrier).  An explicit .release.cluster was measured first: 2 800 cycles
+// per arrive (it drains every outstanding memory operation of the warp, global gathers included).
+DNDM_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+DNDM_DEVICE void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
+DNDM_DEVICE void mbar_wait_park_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
+        "@P bra DONEC_%=;\n\t"
+        "nanosleep.u32 %3;\n\t"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(200000u), "r"(128u)
+        : "memory");
+}
+DNDM_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <uint32_t kCols>
+DNDM_DEVICE void tmem_alloc_pair(uint32_t* smem_slot) {    // one full warp of EACH CTA of the pair, same smem offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+DNDM_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B over the pair: M = 256 (128 rows from each CTA's smem), N = 256 (128 B rows from each)
+DNDM_DEVICE void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all MMAs issued so far arrive on the mbarrier at this shared-memory offset in BOTH CTAs when complete
+DNDM_DEVICE void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <bool kGCL, bool kBf16Radial = true>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EK_THREADS, 1)
+edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
+                 const __grid_constant__ CUtensorMap tmap_msg, const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,
+                 EdgeGraph g, EdgeProblem p0, EdgeProblem p1) {
+    extern __shared__ __align__(1024) uint8_t smem[];            // SW128 operand tiles need 1024-B alignment
+    uint8_t* sW = smem;                                          // [4 k chunks][128 channels][128 B], SW128
+    uint8_t* sA = smem + EP_WH_BYTES;                            // [2 buffers][4 k chunks][128 edges][128 B], SW128
+    uint8_t* misc = smem + EP_WH_BYTES + 2 * EK_A_BYTES;
+    uint8_t* sSlab = misc;                                       // [8 epilogue warps][32 rows][64 B] message staging
+    uint8_t* sAx = misc + EK_SLAB_BYTES;                         // bias step A slice: [16 row groups][2 k cores][8 rows][16 B]
+    uint8_t* sBx = sAx + EK_AX_BYTES;                            // bias step B slice: [16 row groups][2 k cores][8 rows][16 B]
+    int4* sMeta = reinterpret_cast<int4*>(sBx + EP_BX_BYTES);    // [16 producer warps][2 slots][8 edges]
+    float* sDot = reinterpret_cast<float*>(sBx + EP_BX_BYTES + EK_META_BYTES);   // [2 accumulators][128 rows]
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(sBx + EP_BX_BYTES + EK_META_BYTES + EK_DOT_BYTES);
+    uint64_t* w_peer = w_bar + 1;                                // leader: the peer's half of W2 has landed
+    uint64_t* mma_done = w_bar + 2;                              // [2]
+    uint64_t* tmem_empty = mma_done + 2;                         // [2] (leader's copy is the live one)
+    uint64_t* a_full = tmem_empty + 2;                           // [2] (leader's copy is the live one)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 2);
+
+    const bool second = (blockIdx.y != 0);
+    const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
+    const EdgeProblem& pr = second ? p1 : p0;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    pdl_trigger();
+
+    if (tid == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        tma_prefetch_desc(tmap_w);
+        mbar_init(w_bar, 1);
+        mbar_init(w_peer, 1);
+        mbar_init(&mma_done[0], 1);
+        mbar_init(&mma_done[1], 1);
+        mbar_init(&tmem_empty[0], 2 * EK_EPI_WARPS);
+        mbar_init(&tmem_empty[1], 2 * EK_EPI_WARPS);
+        mbar_init(&a_full[0], 2 * EK_PROD_WARPS);
+        mbar_init(&a_full[1], 2 * EK_PROD_WARPS);
+        fence_mbar_init();
+        // the resident second-layer weights are constant: their load runs under the predecessor's tail (before pdl_wait)
+        mbar_arrive_expect_tx(w_bar, EP_WH_BYTES);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * 16384, tmap_w, w_bar, kc * 64, (int)rank * 128);
+    }
+    if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
+    // bias step operands (K-major core matrices, no swizzle): A[r][0] = A[r][1] = 1 ; B[n][0] + B[n][1] = b2[n]
+    {
+        const EdgeConsts& cc = second ? c1 : c0;
+        for (int i = tid; i < (EK_AX_BYTES + EP_BX_BYTES) / 16; i += EK_THREADS) {
+            const int core = i >> 3, r8 = i & 7;                 // 16-byte row r8 of core matrix `core`
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if ((core & 1) == 0) {                               // k core 0 holds k = 0..7
+                if (i < EK_AX_BYTES / 16) {
+                    v.x = 0x3f803f80u;                           // bf16 (1, 1)
+                } else {
+                    const int n = (int)rank * 128 + ((core - EK_AX_BYTES / 128) >> 1) * 8 + r8;
+                    const float b = cc.b2[n];
+                    const float hi = __bfloat162float(__float2bfloat16_rn(b));
+                    v.x = pack_bf16x2(hi, b - hi);
+                }
+            }
+            *reinterpret_cast<uint4*>(sAx + (size_t)i * 16) = v;
+        }
+        fence_proxy_async_all();
+    }
+    tc_fence_before_sync();
+    cluster_sync_all();                          // barriers of both CTAs initialised, TMEM allocated, bias operands written
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                  // everything below reads / writes what earlier kernels of the stream produce
+    const int E = *g.n_edges;
+    const int num_tiles = (E + EK_TILE - 1) / EK_TILE;
+    const int num_tp = (num_tiles + 1) >> 1;     // tile pairs: pair p, iteration it works on tiles 2 (p + it num_pairs) + rank
+
+    if (warp == EK_EPI_WARPS + EK_PROD_WARPS) {
+        // =========================== MMA issuer (one lane of the leader CTA) ===========================
+        if (lane == 0) {
+            mbar_wait(w_bar, 0);                                                      // own half of W2 has landed
+            if (rank != 0) {
+                mbar_arrive_cluster(mapa_shared(smem_u32(w_peer), 0));                // ... tell the leader
+            } else if (pair < num_tp) {
+                constexpr uint32_t idesc = make_idesc_bf16_f32(2 * EK_TILE, EK_H);
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW);
+                const uint64_t ax = make_kmajor_noswz_desc(smem_u32(sAx), 128, 256), bx = make_kmajor_noswz_desc(smem_u32(sBx), 128, 256);
+                mbar_wait_park_cluster(w_peer, 0);
+                int it = 0;
+                for (int tp = pair; tp < num_tp; tp += num_pairs, ++it) {
+                    const int buf = it & 1;
+                    mbar_wait_park_cluster(&a_full[buf], (it >> 1) & 1);                          // both CTAs wrote A[buf]
+                    EK_STAMP(it, 11);
+                    if (it >= 2) mbar_wait_park_cluster(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained in both CTAs
+                    EK_STAMP(it, 5);
+                    tc_fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H;
+                    const uint32_t ab = a0 + (uint32_t)buf * EK_A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16_pair(d_tmem, make_kmajor_sw128_desc(ab + kk * 16384 + k * 32),
+                                           make_kmajor_sw128_desc(b0 + kk * 16384 + k * 32), idesc, (kk | k) != 0);
+                        }
+                    }
+                    umma_bf16_pair(d_tmem, ax, bx, idesc, 1u);                                    // + b2
+                    umma_commit_pair(&mma_done[buf]);
+                    EK_STAMP(it, 6);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= EK_EPI_WARPS) {
+        // =========================== producers ===========================
+        const int pw = warp - EK_EPI_WARPS;
+        // lane owns k = 8*lane .. 8*lane+7 of the (halved) first-layer pre-activation: one 16-byte bf16 unit
+        float wr[8], w0[8];
+        {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(pr.w1e + 8 * lane));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(pr.w1e + 8 * lane + 4));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 8 * lane));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 8 * lane + 4));
+            wr[0] = a.x; wr[1] = a.y; wr[2] = a.z; wr[3] = a.w; wr[4] = b.x; wr[5] = b.y; wr[6] = b.z; wr[7] = b.w;
+            w0[0] = c.x; w0[1] = c.y; w0[2] = c.z; w0[3] = c.w; w0[4] = d.x; w0[5] = d.y; w0[6] = d.z; w0[7] = d.w;
+        }
+        uint32_t wr2[4], w02[4];                     // the same weights as bf16x2 pairs (kBf16Radial producers)
+        uint64_t wrf[4], w0f[4];                     // ... and as fp32 pairs (FFMA2)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            wr2[i] = pack_bf16x2(wr[2 * i], wr[2 * i + 1]);
+            w02[i] = pack_bf16x2(w0[2 * i], w0[2 * i + 1]);
+            wrf[i] = f2_pack(wr[2 * i], wr[2 * i + 1]);
+            w0f[i] = f2_pack(w0[2 * i], w0[2 * i + 1]);
+        }
+        constexpr bool kPacked = kGCL && kBf16Radial; // all-bf16x2 producer arithmetic
+        constexpr bool kMixed = kGCL && !kBf16Radial; // bf16x2 P + Q, fp32 radial terms and activation; the coordinate heads stay
+                                                      // fp32 throughout (measured: packed doubles the x error)
+        const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
+        const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
+        const uint32_t ld4 = (uint32_t)g.ldpq / 8;
+        const uint32_t u = lane & 7;
+        int4* meta = sMeta + pw * 16;                // warp-private slots: [2 tiles][8 edges] x (row, col, radial_now, radial_input)
+        const int l8 = lane & 7;
+        const uint32_t a_full_leader = mapa_shared(smem_u32(a_full), 0);
+
+        struct Meta { int row, col; float r0; };
+        auto meta_l1 = [&](int tile) {                       // level 1: edge -> (row, col, r0); padding edges use node 0
+            Meta m{0, 0, 0.f};
+            const int e = tile * EK_TILE + pw * 8 + l8;
+            if (tile < num_tiles && e < E) { m.row = g.erow[e]; m.col = g.ecol[e]; m.r0 = g.r0[e]; }
+            return m;
+        };
+        // level 2: current squared distance (six dependent loads: issued early, consumed by meta_publish); publish to the warp
+        struct Pos { float rx, ry, rz, cx, cy, cz; };
+        auto meta_pos = [&](const Meta& m) {
+            Pos p;
+            p.rx = g.x[3 * m.row]; p.ry = g.x[3 * m.row + 1]; p.rz = g.x[3 * m.row + 2];
+            p.cx = g.x[3 * m.col]; p.cy = g.x[3 * m.col + 1]; p.cz = g.x[3 * m.col + 2];
+            return p;
+        };
+        auto meta_publish = [&](const Meta& m, const Pos& p, int slot) {
+            const float dx = p.rx - p.cx, dy = p.ry - p.cy, dz = p.rz - p.cz;
+            const float rad = dx * dx + dy * dy + dz * dz;
+            if (lane < 8)
+                meta[slot * 8 + l8] = kPacked ? make_int4(m.row, m.col, (int)pack_bf16x2(rad, rad), (int)pack_bf16x2(m.r0, m.r0))
+                                           : make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
+            __syncwarp();
+        };
+        // The warp's 8 edges of a tile are processed as four ROUNDS of two edges.  The gathers of round r + 1 (P[row], Q[col]:
+        // two 16-byte bf16 units per edge and lane) are issued BEFORE round r is evaluated, across tile boundaries as well
+        // (the next tile's metadata is already in the other slot), so a warp always has one round of loads in flight while it
+        // computes -- with the A tile double-buffered nothing else hides a producer warp's own gather latency.
+        auto issue2 = [&](int slot, int r, uint4 (&pv)[2], uint4 (&qv)[2]) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int2 rc = *reinterpret_cast<const int2*>(&meta[slot * 8 + r * 2 + jj]);        // (row, col): warp-uniform LDS
+                pv[jj] = __ldg(Pb + (uint32_t)rc.x * ld4);
+                qv[jj] = __ldg(Qb + (uint32_t)rc.y * ld4);
+            }
+        };
+        // first-layer activation of two edges, bf16 pack, store into this lane's 16-byte unit of the A rows
+        auto finish2 = [&](int slot, int r, const uint4 (&pv)[2], const uint4 (&qv)[2], uint8_t* sA_lane) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int2 zw = *(reinterpret_cast<const int2*>(&meta[slot * 8 + r * 2 + jj]) + 1);  // (radial_now, radial_input)
+                const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
+                const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
+                uint4 o;
+                if (kPacked) {
+                    const uint32_t rad2 = (uint32_t)zw.x, r02 = (uint32_t)zw.y;
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        ow[i] = bf2_silu_half(bf2_fma(w02[i], r02, bf2_fma(wr2[i], rad2, bf2_add(pw_[i], qw_[i]))));
+                    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                } else if (kMixed) {
+                    const float rad = __int_as_float(zw.x), r0v = __int_as_float(zw.y);
+                    const uint64_t rad2 = f2_pack(rad, rad), r02 = f2_pack(r0v, r0v);
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t s2 = bf2_add(pw_[i], qw_[i]);
+                        const uint64_t pre = f2_fma(w0f[i], r02, f2_fma(wrf[i], rad2,
+                                                    f2_pack(__uint_as_float(s2 << 16), __uint_as_float(s2 & 0xffff0000u))));
+                        float lo, hi;
+                        f2_unpack(pre, lo, hi);
+                        ow[i] = pack_bf16x2(silu_half(lo), silu_half(hi));
+                    }
+                    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                } else {
+                    const float rad = __int_as_float(zw.x), r0v = __int_as_float(zw.y);
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[2 * i] = __uint_as_float(pw_[i] << 16) + __uint_as_float(qw_[i] << 16);
+                        v[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u) + __uint_as_float(qw_[i] & 0xffff0000u);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
+                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                }
+                const uint32_t rr = pw * 8 + r * 2 + jj;
+                *reinterpret_cast<uint4*>(sA_lane + rr * 128 + ((u ^ (rr & 7)) << 4)) = o;
+            }
+        };
+
+        const int tstride = 2 * num_pairs;                   // tile distance between two iterations of this CTA
+        const int tile0 = 2 * pair + (int)rank;
+        {
+            const Meta m0 = meta_l1(tile0);
+            meta_publish(m0, meta_pos(m0), 0);
+        }
+        Meta m_next = meta_l1(tile0 + tstride);
+        uint4 pa[2], qa[2], pb[2], qb[2];                    // two rounds of gathers: one being evaluated, one in flight
+        issue2(0, 0, pa, qa);
+        int it = 0;
+        for (int tp = pair; tp < num_tp; tp += num_pairs, ++it) {
+            const int tile = 2 * tp + (int)rank;
+            const int buf = it & 1, slot = it & 1;
+            uint8_t* sA_lane = sA + buf * EK_A_BYTES + (lane >> 3) * 16384;   // this lane's 16-byte unit of A row r
+            if (lane == 0 && pw == 0) EK_STAMP(it, 0);
+            if (lane == 0 && pw == 15) EK_STAMP(it, 9);
+            const Pos pos_next = meta_pos(m_next);                            // next tile's positions: in flight during two rounds
+            if (lane == 0 && pw == 0) EK_STAMP(it, 1);
+            if (it >= 2) mbar_wait_park(&mma_done[buf], ((it - 2) >> 1) & 1); // the MMA two tiles back has read A[buf]
+            if (lane == 0 && pw == 0) EK_STAMP(it, 2);
+            issue2(slot, 1, pb, qb);
+            finish2(slot, 0, pa, qa, sA_lane);
+            issue2(slot, 2, pa, qa);
+            finish2(slot, 1, pb, qb, sA_lane);
+            meta_publish(m_next, pos_next, slot ^ 1);                         // next tile's metadata -> other slot
+            m_next = meta_l1(tile + 2 * tstride);                             // level-1 loads two tiles ahead
+            if (lane == 0 && pw == 0) EK_STAMP(it, 12);
+            issue2(slot, 3, pb, qb);
+            finish2(slot, 2, pa, qa, sA_lane);
+            issue2(slot ^ 1, 0, pa, qa);                                      // first round of the NEXT tile (padding rows past the end)
+            finish2(slot, 3, pb, qb, sA_lane);
+            if (lane == 0 && pw == 0) EK_STAMP(it, 3);
+            if (lane == 0 && pw == 15) EK_STAMP(it, 10);
+            fence_proxy_async_smem();                 // this thread's rows are visible to the tensor core's proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(a_full_leader + (uint32_t)buf * 8);
+            if (lane == 0 && pw == 0) EK_STAMP(it, 4);
+        }
+    } else {
+        // ============ epilogue (warps 0-7: TMEM lane quarter q = warp % 4, column half hf = warp / 4) ============
+        const int hf = warp >> 2;
+        const int q = warp & 3;
+        const int trow = q * 32 + lane;
+        uint8_t* slab = sSlab + warp * 2048;
+        const uint32_t tmem_empty_leader = mapa_shared(smem_u32(tmem_empty), 0);
+        int it = 0;
+        for (int tp = pair; tp < num_tp; tp += num_pairs, ++it) {
+            const int tile = 2 * tp + (int)rank;
+            const int buf = it & 1;
+            const int e = tile * EK_TILE + trow;
+            const bool valid = e < E;
+            mbar_wait_park(&mma_done[buf], (it >> 1) & 1);
+            if (lane == 0 && warp == 0) EK_STAMP(it, 7);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H + ((uint32_t)(q * 32) << 16);
+            const int row0 = tile * EK_TILE + q * 32;
+            float dot;
+            if (hf) {
+                dot = second ? epilogue_row<kGCL, 1>(c1, d_tmem, slab, &tmap_msg, row0, lane)
+                             : epilogue_row<kGCL, 1>(c0, d_tmem, slab, &tmap_msg, row0, lane);
+                sDot[buf * EK_TILE + trow] = dot;
+                // barrier id alternates with the accumulator (this warp may run one tile ahead of its partner)
+                asm volatile("bar.arrive %0, %1;" ::"r"(2 + 2 * q + buf), "r"(64) : "memory");
+            } else {
+                dot = second ? epilogue_row<kGCL, 0>(c1, d_tmem, slab, &tmap_msg, row0, lane)
+                             : epilogue_row<kGCL, 0>(c0, d_tmem, slab, &tmap_msg, row0, lane);
+                named_bar_sync(2 + 2 * q + buf, 64);
+                dot += sDot[buf * EK_TILE + trow];
+                if (valid) {
+                    if (kGCL) g.att[e] = sigmoid_fast(dot + pr.bout) * pr.out_scale;
+                    else pr.head_out[e] = pr.out_scale * tanhf(dot);
+                }
+            }
+            if (lane == 0 && warp == 0) EK_STAMP(it, 8);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)buf * 8);   // accumulator drained (this warp's part)
+        }
+    }
+    if (kGCL && warp < EK_EPI_WARPS && lane == 0) tma_store_wait_all();   // message writes complete before exit
+    tc_fence_before_sync();
+    cluster_sync_all();                          // no CTA leaves while its peer may still signal it or read its tiles
+    if (warp == 0) tmem_dealloc_pair<512>(tmem_base);
+}
+
+}  // namespace dndm

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_wres.cuh"
 #include "edge_mlp.cuh"
+#include "edge_pair.cuh"
 #include "graph.cuh"
 #include "bonds.cuh"
 #include "node_kernels.cuh"
@@ -33,6 +34,9 @@ static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] 
 // GCL producers: all-bf16x2 first-layer pre-activation by default; DNDM_GCL_F32_RADIAL=1 selects the variant with fp32 radial
 // terms and activation (measured on the radial stress fixture: same error to two digits, 8 % slower -- see edge_mlp.cuh)
 static bool g_bf16_radial = [] { const char* v = getenv("DNDM_GCL_F32_RADIAL"); return !(v && v[0] == '1'); }();
+// Edge MLPs on CTA pairs (edge_pair.cuh: tcgen05 cta_group::2, W2 split over the pair, double-buffered A tile) by default;
+// DNDM_EK_PAIR=0 selects the single-CTA kernel of edge_mlp.cuh (A/B measurements).
+static bool g_ek_pair = [] { const char* v = getenv("DNDM_EK_PAIR"); return !(v && v[0] == '0'); }();
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
@@ -264,6 +268,9 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     *out = e;
     return DNDM_OK;
 }
@@ -456,9 +463,9 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         L.att_bias = ab[0];
         RET_IF(make_tmap_bf16(&L.tm_w3, L.w3, H, 2 * H, 2 * H, 128));
         RET_IF(make_tmap_bf16(&L.tm_w4, L.w4, H, H, H, 128));
-        RET_IF(make_tmap_bf16(&L.tm_w2_e, L.w2_e, H, H, H, 256));
-        RET_IF(make_tmap_bf16(&L.tm_w2_c, L.w2_c, H, H, H, 256));
-        RET_IF(make_tmap_bf16(&L.tm_w2_x, L.w2_x, H, H, H, 256));
+        RET_IF(make_tmap_bf16(&L.tm_w2_e, L.w2_e, H, H, H, 128));      // one box = 128 output channels x 64 inputs
+        RET_IF(make_tmap_bf16(&L.tm_w2_c, L.w2_c, H, H, H, 128));      // one box = 128 output channels x 64 inputs
+        RET_IF(make_tmap_bf16(&L.tm_w2_x, L.w2_x, H, H, H, 128));      // one box = 128 output channels x 64 inputs
     }
     // ---- merged projection weights for the weight-resident GEMM (pq columns: [0,512) edge P|Q of the NEXT block,
     //      [512,1024) coord Q | cross Q, [1024,1536) coord P | cross P of THIS block); all pre-halved ----
@@ -667,8 +674,13 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         {
             ProfScope ps(e, PROF_GCL, st);
             // PDL: preceded by the merged projection GEMM (block 0) / coord_update (later blocks) on this stream
-            CU_CHECK(launch_pdl(pdl, g_bf16_radial ? edge_mlp_kernel<true, true> : edge_mlp_kernel<true, false>, dim3(e->num_sms, 1),
-                                dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e, L.c_e, g, pe, pe));
+            if (g_ek_pair)
+                CU_CHECK(launch_pdl(pdl, g_bf16_radial ? edge_pair_kernel<true, true> : edge_pair_kernel<true, false>,
+                                    dim3(e->num_sms & ~1, 1), dim3(EK_THREADS), EP_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e,
+                                    L.c_e, g, pe, pe));
+            else
+                CU_CHECK(launch_pdl(pdl, g_bf16_radial ? edge_mlp_kernel<true, true> : edge_mlp_kernel<true, false>, dim3(e->num_sms, 1),
+                                    dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e, L.c_e, g, pe, pe));
         }
         {
             ProfScope ps(e, PROF_NODE, st);
@@ -700,8 +712,12 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
             {
                 ProfScope ps(e, PROF_HEAD, st);
-                CU_CHECK(launch_pdl(pdl, edge_mlp_kernel<false>, dim3(gx, 2), dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_c, L.tm_w2_x,
-                                    e->to_msg, L.c_c, L.c_x, gh, pc, px));
+                if (g_ek_pair)
+                    CU_CHECK(launch_pdl(pdl, edge_pair_kernel<false>, dim3(gx > 1 ? gx & ~1 : 2, 2), dim3(EK_THREADS), EP_SMEM_BYTES, st,
+                                        L.tm_w2_c, L.tm_w2_x, e->to_msg, L.c_c, L.c_x, gh, pc, px));
+                else
+                    CU_CHECK(launch_pdl(pdl, edge_mlp_kernel<false>, dim3(gx, 2), dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_c, L.tm_w2_x,
+                                        e->to_msg, L.c_c, L.c_x, gh, pc, px));
             }
             ProfScope ps2(e, PROF_NODE, st);
             coord_update_kernel<<<(n_lig * 32 + 255) / 256, 256, 0, st>>>(x_cur, x_next, e->row_ptr, e->ecol, e->phi, e->psi,
