@@ -117,6 +117,20 @@ DNDM_DEVICE uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+// fp32 pair -> bf16x2 for the staged messages.  F2FP.BF16.F32.PACK_AB executes on the XU pipe at the MUFU rate (ncu:
+// sm__inst_executed_pipe_xu = MUFU + F2FP at 8 cycles per warp instruction and SM sub-partition), so the 128 packs per
+// accumulator row are a fifth of the kernel's XU time.  The alternative (-DDNDM_EP_PACK_ALU: two integer adds + one byte
+// permute on the ALU pipe, round to nearest with ties away from zero) was measured SLOWER on B200 (step 1.70 -> 1.74 ms):
+// the epilogue warps are bound by their own instruction stream, not by the XU, and the alternative adds two instructions per
+// pair.  Even a truncating pack (one PRMT, no XU) changed nothing.
+DNDM_DEVICE uint32_t pack_bf16x2_epi(float lo, float hi) {
+#ifdef DNDM_EP_PACK_ALU
+    const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
+    return __byte_perm(a, b, 0x7632);
+#else
+    return pack_bf16x2(lo, hi);
+#endif
+}
 DNDM_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 // mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of burning issue slots
@@ -144,17 +158,22 @@ DNDM_DEVICE void mbar_wait_park(uint64_t* bar, uint32_t parity) {
 template <bool kGCL, int kHalf>
 DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* slab, const CUtensorMap* tmap_msg, int row0,
                                int lane) {
-    float dot = 0.f;
+    uint64_t dot2 = 0ull;                              // (even, odd) partial sums of the dot product
     uint8_t* rowp = slab + lane * 64;                  // slab = [32 rows][32 bf16 = 64 B], SWIZZLE_64B
     const uint32_t sw = (lane >> 1) & 3;
     // one 16-column chunk of the accumulator row: SiLU, partial dot, bf16 staging (+ TMA store of every finished 32 columns)
+    // (packed fp32 pairs: one FFMA2 for two SiLUs and one for two terms of the dot product -- half the FMA-pipe instructions
+    //  of this thread's 128 columns; the even / odd partial sums meet at the end)
     auto chunk = [&](int c, uint32_t (&v)[16]) {
         const int col0 = c * 16;
         float m[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            m[j] = silu_half(__uint_as_float(v[j]));
-            dot = fmaf(m[j], cc.wout[col0 + j], dot);
+        for (int j = 0; j < 16; j += 2) {
+            const float h0 = __uint_as_float(v[j]), h1 = __uint_as_float(v[j + 1]);
+            const uint64_t h2 = f2_pack(h0, h1);
+            const uint64_t m2 = f2_fma(h2, f2_pack(tanh_approx(h0), tanh_approx(h1)), h2);
+            dot2 = f2_fma(m2, f2_pack(cc.wout[col0 + j], cc.wout[col0 + j + 1]), dot2);
+            f2_unpack(m2, m[j], m[j + 1]);
         }
         if (kGCL) {
             if ((c & 1) == 0) {                        // slab reuse: the previous 32-column TMA store has read it
@@ -164,8 +183,8 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {
                 uint4 o;
-                o.x = pack_bf16x2(m[j], m[j + 1]);     o.y = pack_bf16x2(m[j + 2], m[j + 3]);
-                o.z = pack_bf16x2(m[j + 4], m[j + 5]); o.w = pack_bf16x2(m[j + 6], m[j + 7]);
+                o.x = pack_bf16x2_epi(m[j], m[j + 1]);     o.y = pack_bf16x2_epi(m[j + 2], m[j + 3]);
+                o.z = pack_bf16x2_epi(m[j + 4], m[j + 5]); o.w = pack_bf16x2_epi(m[j + 6], m[j + 7]);
                 const uint32_t unit = (c & 1) * 2 + (j >> 3);
                 *reinterpret_cast<uint4*>(rowp + ((unit ^ sw) << 4)) = o;
             }
@@ -193,7 +212,9 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
         if (cc_ + 2 < 8) tmem_ld16(d_tmem + (c + 2) * 16, va);
         chunk(c + 1, vb);
     }
-    return dot;
+    float d0, d1;
+    f2_unpack(dot2, d0, d1);
+    return d0 + d1;
 }
 
 #ifdef DNDM_EK_TRACE

@@ -112,7 +112,10 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
     const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
     const EdgeProblem& pr = second ? p1 : p0;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast through a shuffle: the compiler then KNOWS the role index is warp-uniform and keeps descriptors, barrier
+    // addresses and loop state of the role branches on the uniform datapath (without it: an R2UR pair in front of every LDG / LDTM)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     pdl_trigger();
@@ -225,9 +228,10 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
         constexpr bool kPacked = kGCL && kBf16Radial; // all-bf16x2 producer arithmetic
         constexpr bool kMixed = kGCL && !kBf16Radial; // bf16x2 P + Q, fp32 radial terms and activation; the coordinate heads stay
                                                       // fp32 throughout (measured: packed doubles the x error)
-        const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
-        const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
-        const uint32_t ld4 = (uint32_t)g.ldpq / 8;
+        // this lane's 16-byte unit of a P / Q row; row address = base + row * (row bytes) as ONE 32 x 32 -> 64-bit multiply-add
+        const char* Pb = reinterpret_cast<const char*>(pr.P) + lane * 16;
+        const char* Qb = reinterpret_cast<const char*>(pr.Q) + lane * 16;
+        const uint32_t ldb = (uint32_t)g.ldpq * 2;
         const uint32_t u = lane & 7;
         int4* meta = sMeta + pw * 16;                // warp-private slots: [2 tiles][8 edges] x (row, col, radial_now, radial_input)
         const int l8 = lane & 7;
@@ -264,8 +268,8 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int2 rc = *reinterpret_cast<const int2*>(&meta[slot * 8 + r * 2 + jj]);        // (row, col): warp-uniform LDS
-                pv[jj] = __ldg(Pb + (uint32_t)rc.x * ld4);
-                qv[jj] = __ldg(Qb + (uint32_t)rc.y * ld4);
+                pv[jj] = __ldg(reinterpret_cast<const uint4*>(Pb + (uint64_t)(uint32_t)rc.x * ldb));
+                qv[jj] = __ldg(reinterpret_cast<const uint4*>(Qb + (uint64_t)(uint32_t)rc.y * ldb));
             }
         };
         // first-layer activation of two edges, bf16 pack, store into this lane's 16-byte unit of the A rows
@@ -333,7 +337,7 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
             if (lane == 0 && pw == 15) EK_STAMP(it, 9);
             const Pos pos_next = meta_pos(m_next);                            // next tile's positions: in flight during two rounds
             if (lane == 0 && pw == 0) EK_STAMP(it, 1);
-            if (it >= 2) mbar_wait_park(&mma_done[buf], ((it - 2) >> 1) & 1); // the MMA two tiles back has read A[buf]
+            if (it >= 2) mbar_wait_park(&mma_done[buf], ((it - 2) >> 1) & 1);      // the MMA two tiles back has read A[buf]
             if (lane == 0 && pw == 0) EK_STAMP(it, 2);
             issue2(slot, 1, pb, qb);
             finish2(slot, 0, pa, qa, sA_lane);
