@@ -493,9 +493,9 @@ def run_b200(args):
                 traffic_src = cap.get('source')
         except Exception:
             pass
-        roof = {'bound': 'tensor', 'kernel': 'edge_mlp_kernel<GCL>', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+        roof = {'bound': 'tensor', 'kernel': 'edge_pair_kernel<GCL>', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
-                'peak_source': peak_src, 'limiter': 'XU (MUFU.TANH, two SiLU per edge and channel): see DESIGN.md section 5',
+                'peak_source': peak_src, 'limiter': 'XU pipe (MUFU.TANH for two SiLU per edge and channel + F2FP packs) and issue slots: see DESIGN.md section 5',
                 'us_per_launch': t_launch * 1e6, 'edges_per_launch': edges_timed / max(g_n, 1), 'edges': E_edges,
                 'edges_last_block': E_last,
                 'flop_per_edge_executed': EXEC_FLOP_PER_EDGE_GCL,

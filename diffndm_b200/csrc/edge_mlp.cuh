@@ -1,37 +1,24 @@
-// Fused per-edge MLP (GCL edge model / EquivariantUpdate heads), egnn_new.py:31-47 and :96-110.
+// Shared pieces of the fused per-edge MLP (GCL edge model / EquivariantUpdate heads), egnn_new.py:31-47 and :96-110: the
+// arithmetic helpers, the accumulator-drain routine of the epilogue warps and the per-receiver segment reduction.  The
+// kernel itself is edge_pair.cuh (one 256-edge tile per CTA pair, tcgen05 cta_group::2).
 //
 // Algebra: the first Linear of every edge MLP acts on [h_row, h_col, e]; its h-parts are hoisted to the
 // nodes (P = W1a h + b1, Q = W1b h, one dense node GEMM), so per edge only
-//     a   = SiLU(P[row] + Q[col] + w_r * |x_r - x_c|^2 + w_0 * r0)            (gather + fp32 adds, bf16 out)
-//     D   = a . W2^T + b2                                                     (tcgen05, M=128 edges, N=256, K=256+16)
+//     a   = SiLU(P[row] + Q[col] + w_r * |x_r - x_c|^2 + w_0 * r0)            (gather + adds, bf16 out)
+//     D   = a . W2^T + b2                                                     (tcgen05, N=256, K=256+16)
 //     m   = SiLU(D)
 //   GCL : att = sigmoid(w_a . m + b_a);  agg[row] += att * m / norm           (deterministic segmented sum)
 //   HEAD: out[e] = range * tanh(w5 . m)                                       (coord / cross scalar heads)
 // remains.
-//
-// Persistent, warp-specialised CTA (800 threads, 1 CTA / SM, <= 80 registers per thread):
-//   warps 8-23  producers : gather + first-layer epilogue -> bf16 A tile in SWIZZLE_128B K-major smem (8 edges per
-//                           warp and tile, metadata prefetched a tile ahead); each warp arrives on the `a_full`
-//                           mbarrier when its rows are written -- producers never wait for each other
-//   warp 24     MMA issuer: one lane waits for a_full and a drained accumulator, issues the 17 tcgen05.mma
-//                           (M128 N256 K16) of the tile into TMEM accumulator (it & 1) and commits to mma_done
-//   warps 0-7   epilogue  : every tile is drained by all eight warps -- warp w reads TMEM lane quarter w % 4 (32 edges)
-//                           and column half w / 4 (128 of the 256 channels), so the accumulator is free again after half
-//                           the time; per edge: tcgen05.ld -> m = SiLU(D) -> partial dot with the attention / head
-//                           weights (the two halves meet through shared memory and a 64-thread named barrier)
-//                           weights; GCL stages m (bf16) in a swizzled smem slab per warp and TMA-stores it to the
-//                           message buffer, plus att[e]; HEAD writes the scalar
 // The second-layer bias rides on the tensor core: a 17th K=16 MMA step multiplies a constant A slice (columns 0,1 = 1)
 // with a B slice holding b2 split into two bf16 terms (hi + lo), so the accumulator already is the SiLU argument
 // (W2 and b2 are pre-halved on the host) and the epilogue spends no instruction on it.
-// W2 (128 KiB bf16) is TMA-loaded once per CTA and stays resident; the MMA of tile i and the production of tile i+1
-// run under the epilogue of tile i-1 (two TMEM accumulators).
 //
 // The per-receiver sum is a separate streaming kernel (segment_reduce_kernel): edges are receiver-sorted, so the
 // messages of a node are one contiguous block that a warp adds up in edge order -- deterministic, no atomics, and it
 // emits the bf16 operand of the node MLP directly.  (An in-kernel segmented reduction through shared memory was
 // measured first: its staging + barriers made the epilogue 3x longer than the producer.)
-// P and Q are stored in bf16 (half the gather bytes); their sum and the distance terms are fp32.
+// P and Q are stored in bf16 (half the gather bytes).
 #pragma once
 #include "common.cuh"
 
@@ -39,17 +26,8 @@ namespace dndm {
 
 constexpr int EK_TILE = 128;      // edges per tile (UMMA M)
 constexpr int EK_H = 256;         // hidden size (UMMA N and K)
-constexpr int EK_THREADS = 800;    // 8 epilogue + 16 producer warps + 1 MMA-issue warp, <= 80 registers each
-constexpr int EK_W2_BYTES = EK_H * EK_H * 2;            // 131072
-constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536
-constexpr int EK_SLAB_BYTES = 8 * 2048;                 // message staging, one [32 rows][64 B] SW64 slab per epilogue warp
-constexpr int EK_AX_BYTES = EK_TILE * 16 * 2;           //   4096  bias step, A slice (no swizzle)
-constexpr int EK_BX_BYTES = EK_H * 16 * 2;              //   8192  bias step, B slice (no swizzle)
-constexpr int EK_META_BYTES = 16 * 2 * 8 * 16;          //   4096
-constexpr int EK_DOT_BYTES = 2 * EK_TILE * 4;           //   1024  partial dot products of the upper column half, per accumulator
-constexpr int EK_MISC_BYTES = EK_SLAB_BYTES + EK_AX_BYTES + EK_BX_BYTES + EK_META_BYTES + EK_DOT_BYTES + 256;
-constexpr int EK_SMEM_BYTES = EK_W2_BYTES + EK_A_BYTES + EK_MISC_BYTES;
-static_assert(EK_SMEM_BYTES <= 232448, "edge kernel shared memory exceeds 227 KiB");
+constexpr int EK_A_BYTES = EK_TILE * EK_H * 2;          //  65536  one A tile: 128 edges x 256 first-layer activations, bf16
+constexpr int EK_META_BYTES = 16 * 2 * 8 * 16;          //   4096  [16 producer warps][2 tiles][8 edges] x (row, col, radial, radial_input)
 
 struct EdgeConsts {         // lives in the kernel-parameter constant bank: warp-uniform reads
     float b2[EK_H];        // HALF of the second-layer bias (the SiLU argument is evaluated as x/2); fed to the bias MMA step
@@ -155,7 +133,8 @@ DNDM_DEVICE void mbar_wait_park(uint64_t* bar, uint32_t parity) {
 // GCL additionally stages m as bf16 in this warp's shared-memory slab ([32 rows][64 columns], SWIZZLE_128B) and hands
 // every finished 64-column quarter to a TMA store into the message buffer.
 // `cc` must be one of the __grid_constant__ kernel parameters so that b2/wout become constant-bank operands.
-template <bool kGCL, int kHalf>
+// The warp drains the 16-column chunks [kChunk0, kChunk0 + kNChunks) of its 32 accumulator rows (both even).
+template <bool kGCL, int kChunk0, int kNChunks>
 DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* slab, const CUtensorMap* tmap_msg, int row0,
                                int lane) {
     uint64_t dot2 = 0ull;                              // (even, odd) partial sums of the dot product
@@ -201,15 +180,16 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
     // the TMEM load of chunk c + 1 is in flight while chunk c is evaluated (tcgen05.wait::ld covers every outstanding load of
     // the thread, so the next load is issued right after the wait)
     uint32_t va[16], vb[16];
-    tmem_ld16(d_tmem + kHalf * 128, va);
+    static_assert(kChunk0 % 2 == 0 && kNChunks % 2 == 0, "chunks are stored in pairs of 32 columns");
+    tmem_ld16(d_tmem + kChunk0 * 16, va);
 #pragma unroll
-    for (int cc_ = 0; cc_ < 8; cc_ += 2) {
-        const int c = kHalf * 8 + cc_;                 // 16-column chunk of the 256 channels
+    for (int cc_ = 0; cc_ < kNChunks; cc_ += 2) {
+        const int c = kChunk0 + cc_;                   // 16-column chunk of the 256 channels
         tmem_ld_wait16(va);
         tmem_ld16(d_tmem + (c + 1) * 16, vb);
         chunk(c, va);
         tmem_ld_wait16(vb);
-        if (cc_ + 2 < 8) tmem_ld16(d_tmem + (c + 2) * 16, va);
+        if (cc_ + 2 < kNChunks) tmem_ld16(d_tmem + (c + 2) * 16, va);
         chunk(c + 1, vb);
     }
     float d0, d1;
@@ -218,8 +198,8 @@ DNDM_DEVICE float epilogue_row(const EdgeConsts& cc, uint32_t d_tmem, uint8_t* s
 }
 
 #ifdef DNDM_EK_TRACE
-// Development aid (build with DNDM_EXTRA_NVCC_FLAGS=-DDNDM_EK_TRACE): clock64 stamps of CTA 0 of the GCL kernel,
-// [iteration][event], read back through dndm_debug_copy(what = 5).  See scripts/ek_timeline.py for the event list.
+// Development aid (build with DNDM_EXTRA_NVCC_FLAGS=-DDNDM_EK_TRACE): clock64 stamps of CTA 0 (leader of pair 0) of the GCL kernel,
+// [iteration][event], read back through dndm_debug_copy(what = 5).  See scripts/ep_timeline.py for the event list.
 __device__ unsigned long long g_ek_trace[64 * 16];
 #define EK_STAMP(it, ev)                                                                       \
     do {                                                                                       \
@@ -228,305 +208,6 @@ __device__ unsigned long long g_ek_trace[64 * 16];
 #else
 #define EK_STAMP(it, ev) do {} while (0)
 #endif
-
-constexpr int EK_EPI_WARPS = 8;                     // warps 0-7: epilogue, column half = warp / 4, TMEM lane quarter = warp % 4
-constexpr int EK_PROD_WARPS = 16;                   // warps 8-23: producers, 8 edges of every tile each
-constexpr int EK_PROD_THREADS = EK_PROD_WARPS * 32;
-
-// kBf16Radial (GCL only): assemble the whole first-layer pre-activation in bf16x2: r^2 and r0 are ROUNDED to bf16 before
-// they meet their weights.  The alternative (false; DNDM_GCL_F32_RADIAL=1) keeps P + Q in bf16x2 but does the two radial
-// FMAs (FFMA2), the SiLU and the single rounding to bf16 in fp32.  Measured on B200 against the fp64 reference on the radial
-// stress fixture (tests/golden/parity_r2.npz fwd_r2stress_3rfm_b2: radial weights x 20, ligand-ligand r^2 up to 789):
-// eps_x error 1.42e-2 vs 1.43e-2 at |eps_x| = 8.6, h after six blocks 3.2e-3 relative either way, eps_h 4.3e-3 vs 3.2e-3 --
-// the operand rounding of P/Q/A dominates, not the radial terms -- while the fp32 variant costs 8 % of the kernel
-// (profiles/r2_radial_ab.json).  The packed path therefore stays the default.
-template <bool kGCL, bool kBf16Radial = true>
-__global__ void __launch_bounds__(EK_THREADS, 1)
-edge_mlp_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
-                const __grid_constant__ CUtensorMap tmap_msg, const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,
-                EdgeGraph g, EdgeProblem p0, EdgeProblem p1) {
-    extern __shared__ __align__(1024) uint8_t smem[];            // SW128 operand tiles need 1024-B alignment
-    uint8_t* sW = smem;
-    uint8_t* sA = smem + EK_W2_BYTES;
-    uint8_t* misc = smem + EK_W2_BYTES + EK_A_BYTES;
-    uint8_t* sSlab = misc;                                       // [8 epilogue warps][32 rows][64 B] message staging
-    uint8_t* sAx = misc + EK_SLAB_BYTES;                         // bias step A slice: [16 row groups][2 k cores][8 rows][16 B]
-    uint8_t* sBx = sAx + EK_AX_BYTES;                            // bias step B slice: [32 row groups][2 k cores][8 rows][16 B]
-    int4* sMeta = reinterpret_cast<int4*>(sBx + EK_BX_BYTES);    // [16 producer warps][2 slots][8 edges]
-    float* sDot = reinterpret_cast<float*>(sBx + EK_BX_BYTES + EK_META_BYTES);   // [2 accumulators][128 rows]
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(sBx + EK_BX_BYTES + EK_META_BYTES + EK_DOT_BYTES);
-    uint64_t* mma_done = w_bar + 1;                              // [2]
-    uint64_t* tmem_empty = mma_done + 2;                         // [2]
-    uint64_t* a_full = tmem_empty + 2;                           // A tile of the current iteration completely written
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
-
-    const bool second = (blockIdx.y != 0);
-    const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
-    const EdgeProblem& pr = second ? p1 : p0;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    pdl_trigger();
-
-    if (tid == 0) {
-        if (smem_u32(smem) & 1023u) __trap();
-        tma_prefetch_desc(tmap_w);
-        mbar_init(w_bar, 1);
-        mbar_init(&mma_done[0], 1);
-        mbar_init(&mma_done[1], 1);
-        mbar_init(&tmem_empty[0], EK_EPI_WARPS * 32);
-        mbar_init(&tmem_empty[1], EK_EPI_WARPS * 32);
-        mbar_init(a_full, EK_PROD_WARPS);
-        fence_mbar_init();
-        // the resident second-layer weights are constant: their load runs under the predecessor's tail (before pdl_wait)
-        mbar_arrive_expect_tx(w_bar, EK_W2_BYTES);
-#pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {           // boxes of 128 output channels x 64 inputs (shared with the pair kernel)
-            tma_load_2d(sW + kc * 32768, tmap_w, w_bar, kc * 64, 0);
-            tma_load_2d(sW + kc * 32768 + 16384, tmap_w, w_bar, kc * 64, 128);
-        }
-    }
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
-    // bias step operands (K-major core matrices, no swizzle): A[r][0] = A[r][1] = 1 ; B[n][0] + B[n][1] = b2[n]
-    {
-        const EdgeConsts& cc = second ? c1 : c0;
-        for (int i = tid; i < (EK_AX_BYTES + EK_BX_BYTES) / 16; i += EK_THREADS) {
-            const int core = i >> 3, r8 = i & 7;                 // 16-byte row r8 of core matrix `core`
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if ((core & 1) == 0) {                               // k core 0 holds k = 0..7
-                if (i < EK_AX_BYTES / 16) {
-                    v.x = 0x3f803f80u;                           // bf16 (1, 1)
-                } else {
-                    const int n = ((core - EK_AX_BYTES / 128) >> 1) * 8 + r8;
-                    const float b = cc.b2[n];
-                    const float hi = __bfloat162float(__float2bfloat16_rn(b));
-                    v.x = pack_bf16x2(hi, b - hi);
-                }
-            }
-            *reinterpret_cast<uint4*>(sAx + (size_t)i * 16) = v;
-        }
-        fence_proxy_async_smem();
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                                  // everything below reads / writes what earlier kernels of the stream produce
-    const int E = *g.n_edges;
-    const int num_tiles = (E + EK_TILE - 1) / EK_TILE;
-
-    if (warp == EK_EPI_WARPS + EK_PROD_WARPS) {
-        // =========================== MMA issuer (one lane) ===========================
-        if (lane == 0 && (int)blockIdx.x >= num_tiles) mbar_wait(w_bar, 0);     // no tile: the weight load must land before exit
-        if (lane == 0 && (int)blockIdx.x < num_tiles) {
-            constexpr uint32_t idesc = make_idesc_bf16_f32(EK_TILE, EK_H);
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW);
-            const uint64_t ax = make_kmajor_noswz_desc(smem_u32(sAx), 128, 256), bx = make_kmajor_noswz_desc(smem_u32(sBx), 128, 256);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                mbar_wait_park(a_full, it & 1);                                       // all 16 producer warps wrote their rows
-                if (it >= 2) mbar_wait_park(&tmem_empty[buf], ((it - 2) >> 1) & 1);   // D[buf] drained by the epilogue
-                EK_STAMP(it, 5);
-                tc_fence_after_sync();
-                if (it == 0) mbar_wait(w_bar, 0);
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_bf16(d_tmem, make_kmajor_sw128_desc(a0 + kk * 16384 + k * 32),
-                                  make_kmajor_sw128_desc(b0 + kk * 32768 + k * 32), idesc, (kk | k) != 0);
-                    }
-                }
-                umma_bf16(d_tmem, ax, bx, idesc, 1u);                                 // + b2
-                umma_commit(&mma_done[buf]);
-                EK_STAMP(it, 6);
-            }
-        }
-        __syncwarp();
-    } else if (warp >= EK_EPI_WARPS) {
-        // =========================== producers ===========================
-        const int pw = warp - EK_EPI_WARPS;
-        // lane owns k = 8*lane .. 8*lane+7 of the (halved) first-layer pre-activation: one 16-byte bf16 unit
-        float wr[8], w0[8];
-        {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(pr.w1e + 8 * lane));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(pr.w1e + 8 * lane + 4));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 8 * lane));
-            const float4 d = __ldg(reinterpret_cast<const float4*>(pr.w1e + 256 + 8 * lane + 4));
-            wr[0] = a.x; wr[1] = a.y; wr[2] = a.z; wr[3] = a.w; wr[4] = b.x; wr[5] = b.y; wr[6] = b.z; wr[7] = b.w;
-            w0[0] = c.x; w0[1] = c.y; w0[2] = c.z; w0[3] = c.w; w0[4] = d.x; w0[5] = d.y; w0[6] = d.z; w0[7] = d.w;
-        }
-        uint32_t wr2[4], w02[4];                     // the same weights as bf16x2 pairs (kBf16Radial producers)
-        uint64_t wrf[4], w0f[4];                     // ... and as fp32 pairs (FFMA2)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            wr2[i] = pack_bf16x2(wr[2 * i], wr[2 * i + 1]);
-            w02[i] = pack_bf16x2(w0[2 * i], w0[2 * i + 1]);
-            wrf[i] = f2_pack(wr[2 * i], wr[2 * i + 1]);
-            w0f[i] = f2_pack(w0[2 * i], w0[2 * i + 1]);
-        }
-        constexpr bool kPacked = kGCL && kBf16Radial; // all-bf16x2 producer arithmetic
-        constexpr bool kMixed = kGCL && !kBf16Radial; // bf16x2 P + Q, fp32 radial terms and activation; the coordinate heads stay
-                                                      // fp32 throughout (measured: packed doubles the x error)
-        const uint4* Pb = reinterpret_cast<const uint4*>(pr.P) + lane;          // row stride ldpq/8 uint4
-        const uint4* Qb = reinterpret_cast<const uint4*>(pr.Q) + lane;
-        const uint32_t ld4 = (uint32_t)g.ldpq / 8;
-        uint8_t* sA_lane = sA + (lane >> 3) * 16384;   // this lane's 16-byte unit of A row r: + r*128 + ((u ^ (r&7)) << 4)
-        const uint32_t u = lane & 7;
-        // warp-private metadata slots: [2 tiles][8 edges] x (row, col, radial_now, radial_input)
-        int4* meta = sMeta + pw * 16;
-        const int l8 = lane & 7;
-
-        // metadata is fetched one tile ahead (two dependent global loads); gathers are issued 4 edges at a time and
-        // their latency is hidden by the other producer warps of the SM sub-partition
-        struct Meta { int row, col; float r0; };
-        auto meta_l1 = [&](int tile) {                       // level 1: edge -> (row, col, r0); padding edges use node 0
-            Meta m{0, 0, 0.f};
-            const int e = tile * EK_TILE + pw * 8 + l8;
-            if (tile < num_tiles && e < E) { m.row = g.erow[e]; m.col = g.ecol[e]; m.r0 = g.r0[e]; }
-            return m;
-        };
-        auto meta_l2 = [&](const Meta& m, int slot) {        // level 2: current squared distance; publish to the warp
-            const float dx = g.x[3 * m.row] - g.x[3 * m.col];
-            const float dy = g.x[3 * m.row + 1] - g.x[3 * m.col + 1];
-            const float dz = g.x[3 * m.row + 2] - g.x[3 * m.col + 2];
-            const float rad = dx * dx + dy * dy + dz * dz;
-            // GCL: both radial features as duplicated bf16x2 words; HEAD: fp32
-            if (lane < 8)
-                meta[slot * 8 + l8] = kPacked ? make_int4(m.row, m.col, (int)pack_bf16x2(rad, rad), (int)pack_bf16x2(m.r0, m.r0))
-                                           : make_int4(m.row, m.col, __float_as_int(rad), __float_as_int(m.r0));
-            __syncwarp();
-        };
-        // 4 edges: gather P[row], Q[col] (two 16-byte bf16 units per edge), first-layer activation, bf16 pack.  The results
-        // stay in registers until `before_store` returns, so that for the first half of a tile everything up to the
-        // shared-memory stores overlaps the previous tile's MMA (which is still reading the A tile).
-        auto compute4 = [&](int slot, int half, auto&& before_store) {
-            uint4 pv[4], qv[4];
-            int4 md[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                md[jj] = meta[slot * 8 + half * 4 + jj];
-                pv[jj] = __ldg(Pb + (uint32_t)md[jj].x * ld4);
-                qv[jj] = __ldg(Qb + (uint32_t)md[jj].y * ld4);
-            }
-            uint4 o[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
-                const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
-                if (kPacked) {
-                    const uint32_t rad2 = (uint32_t)md[jj].z, r02 = (uint32_t)md[jj].w;
-                    uint32_t ow[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        ow[i] = bf2_silu_half(bf2_fma(w02[i], r02, bf2_fma(wr2[i], rad2, bf2_add(pw_[i], qw_[i]))));
-                    o[jj] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                } else if (kMixed) {
-                    const float rad = __int_as_float(md[jj].z), r0v = __int_as_float(md[jj].w);
-                    const uint64_t rad2 = f2_pack(rad, rad), r02 = f2_pack(r0v, r0v);
-                    uint32_t ow[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t s2 = bf2_add(pw_[i], qw_[i]);
-                        const uint64_t pre = f2_fma(w0f[i], r02, f2_fma(wrf[i], rad2,
-                                                    f2_pack(__uint_as_float(s2 << 16), __uint_as_float(s2 & 0xffff0000u))));
-                        float lo, hi;
-                        f2_unpack(pre, lo, hi);
-                        ow[i] = pack_bf16x2(silu_half(lo), silu_half(hi));
-                    }
-                    o[jj] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                } else {
-                    const float rad = __int_as_float(md[jj].z), r0v = __int_as_float(md[jj].w);
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[2 * i] = __uint_as_float(pw_[i] << 16) + __uint_as_float(qw_[i] << 16);
-                        v[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u) + __uint_as_float(qw_[i] & 0xffff0000u);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
-                    o[jj].x = pack_bf16x2(v[0], v[1]); o[jj].y = pack_bf16x2(v[2], v[3]);
-                    o[jj].z = pack_bf16x2(v[4], v[5]); o[jj].w = pack_bf16x2(v[6], v[7]);
-                }
-            }
-            before_store();
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const uint32_t r = pw * 8 + half * 4 + jj;
-                *reinterpret_cast<uint4*>(sA_lane + r * 128 + ((u ^ (r & 7)) << 4)) = o[jj];
-            }
-        };
-
-        {
-            const Meta m0 = meta_l1(blockIdx.x);
-            meta_l2(m0, 0);
-        }
-        Meta m_next = meta_l1(blockIdx.x + gridDim.x);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1, slot = it & 1;
-            if (lane == 0 && pw == 0) EK_STAMP(it, 0);
-            if (lane == 0 && pw == 15) EK_STAMP(it, 9);
-            meta_l2(m_next, slot ^ 1);                                           // next tile's metadata -> other slot
-            m_next = meta_l1(tile + 2 * gridDim.x);                              // level-1 loads two tiles ahead
-            compute4(slot, 0, [&] {
-                if (lane == 0 && pw == 0) EK_STAMP(it, 1);
-                if (it >= 1) mbar_wait_park(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);   // A smem free again
-                if (lane == 0 && pw == 0) EK_STAMP(it, 2);
-            });
-            compute4(slot, 1, [] {});
-            if (lane == 0 && pw == 0) EK_STAMP(it, 3);
-            if (lane == 0 && pw == 15) EK_STAMP(it, 10);
-            fence_proxy_async_smem();                 // this thread's rows are visible to the tensor core's proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full);
-            if (lane == 0 && pw == 0) EK_STAMP(it, 4);
-        }
-    } else {
-        // ============ epilogue (warps 0-7: TMEM lane quarter q = warp % 4, column half hf = warp / 4) ============
-        const int hf = warp >> 2;
-        const int q = warp & 3;
-        const int trow = q * 32 + lane;
-        uint8_t* slab = sSlab + warp * 2048;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const int e = tile * EK_TILE + trow;
-            const bool valid = e < E;
-            mbar_wait_park(&mma_done[buf], (it >> 1) & 1);
-            if (lane == 0 && warp == 0) EK_STAMP(it, 7);
-            tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H + ((uint32_t)(q * 32) << 16);
-            const int row0 = tile * EK_TILE + q * 32;
-            float dot;
-            if (hf) {
-                dot = second ? epilogue_row<kGCL, 1>(c1, d_tmem, slab, &tmap_msg, row0, lane)
-                             : epilogue_row<kGCL, 1>(c0, d_tmem, slab, &tmap_msg, row0, lane);
-                sDot[buf * EK_TILE + trow] = dot;
-                // partial published to the lower-half warp.  The barrier id alternates with the accumulator: this warp may
-                // run one tile ahead of its partner, and two arrivals on ONE barrier would complete it without the partner.
-                asm volatile("bar.arrive %0, %1;" ::"r"(2 + 2 * q + buf), "r"(64) : "memory");
-            } else {
-                dot = second ? epilogue_row<kGCL, 0>(c1, d_tmem, slab, &tmap_msg, row0, lane)
-                             : epilogue_row<kGCL, 0>(c0, d_tmem, slab, &tmap_msg, row0, lane);
-                named_bar_sync(2 + 2 * q + buf, 64);
-                dot += sDot[buf * EK_TILE + trow];
-                if (valid) {
-                    if (kGCL) g.att[e] = sigmoid_fast(dot + pr.bout) * pr.out_scale;
-                    else pr.head_out[e] = pr.out_scale * tanhf(dot);
-                }
-            }
-            if (lane == 0 && warp == 0) EK_STAMP(it, 8);
-            tc_fence_before_sync();
-            mbar_arrive(&tmem_empty[buf]);             // accumulator drained: the MMA of tile it+2 may overwrite it
-        }
-    }
-    if (kGCL && warp < EK_EPI_WARPS && lane == 0) tma_store_wait_all();   // message writes complete before exit
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem_base);
-}
 
 // Deterministic per-receiver reduction of the gated messages (replaces unsorted_segment_sum, egnn_new.py:319-335, and
 // feeds the node MLP):  agg[n] = sum_{e in row n} att[e] * msg[e]  in CSR (= edge) order, written as the bf16 operand

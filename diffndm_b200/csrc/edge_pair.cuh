@@ -9,8 +9,8 @@
 // producers run a whole tile ahead of the tensor core, and the B-operand shared-memory reads per edge are halved.  Each
 // CTA's TMEM receives its own 128 edges x all 256 channels, so the epilogue is unchanged (epilogue_row).
 //
-// Roles per CTA (800 threads as before): warps 0-7 epilogue, 8-23 producers, warp 24 lane 0: MMA issue (leader CTA, rank 0)
-// / weight-arrival forwarding (rank 1).  Cross-CTA signalling goes through mbarriers in the LEADER's shared memory:
+// Roles per CTA (928 threads, <= 64 registers): warps 0-11 epilogue (4 TMEM lane quarters x 3 column groups), 12-27 producers,
+// warp 28 lane 0: MMA issue (leader CTA, rank 0) / weight-arrival forwarding (rank 1).  Cross-CTA signalling goes through mbarriers in the LEADER's shared memory:
 //   a_full[2]     : 16 producer warps of each CTA arrive (remote arrive, release.cluster) when their rows of A[buf] are written
 //   tmem_empty[2] : 8 epilogue warps of each CTA arrive when accumulator buf is drained
 //   mma_done[2]   : in BOTH CTAs, signalled by tcgen05.commit.multicast -- accumulator ready (epilogue) and A[buf] free (producers)
@@ -21,7 +21,14 @@ namespace dndm {
 
 constexpr int EP_WH_BYTES = 128 * EK_H * 2;             //  65536  this CTA's half of W2: 128 output channels x 256 inputs
 constexpr int EP_BX_BYTES = 128 * 16 * 2;               //   4096  bias step, B slice of this CTA's 128 channels
-constexpr int EP_MISC_BYTES = EK_SLAB_BYTES + EK_AX_BYTES + EP_BX_BYTES + EK_META_BYTES + EK_DOT_BYTES + 256;
+// 29 warps (928 threads, <= 64 registers): 12 epilogue warps = 4 TMEM lane quarters x 3 column groups, 16 producers, 1 issuer
+constexpr int EP_EPI_WARPS = 12;
+constexpr int EP_PROD_WARPS = 16;
+constexpr int EP_THREADS = (EP_EPI_WARPS + EP_PROD_WARPS + 1) * 32;
+constexpr int EP_SLAB_BYTES = EP_EPI_WARPS * 2048;      //  24576  message staging, one [32 rows][64 B] SW64 slab per epilogue warp
+constexpr int EP_AX_BYTES = 256;                        //    256  bias step, A slice: ONE 8-row group (every row is [1, 1, 0 ...]), SBO = 0
+constexpr int EP_DOT_BYTES = 2 * 2 * EK_TILE * 4;       //   2048  partial dot products of column groups 1 and 2, per accumulator
+constexpr int EP_MISC_BYTES = EP_SLAB_BYTES + EP_AX_BYTES + EP_BX_BYTES + EK_META_BYTES + EP_DOT_BYTES + 256;
 constexpr int EP_SMEM_BYTES = EP_WH_BYTES + 2 * EK_A_BYTES + EP_MISC_BYTES;
 static_assert(EP_SMEM_BYTES <= 232448, "pair edge kernel shared memory exceeds 227 KiB");
 
@@ -88,7 +95,7 @@ DNDM_DEVICE void umma_commit_pair(uint64_t* bar) {
 }
 
 template <bool kGCL, bool kBf16Radial = true>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EK_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EP_THREADS, 1)
 edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_msg, const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,
                  EdgeGraph g, EdgeProblem p0, EdgeProblem p1) {
@@ -96,12 +103,12 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
     uint8_t* sW = smem;                                          // [4 k chunks][128 channels][128 B], SW128
     uint8_t* sA = smem + EP_WH_BYTES;                            // [2 buffers][4 k chunks][128 edges][128 B], SW128
     uint8_t* misc = smem + EP_WH_BYTES + 2 * EK_A_BYTES;
-    uint8_t* sSlab = misc;                                       // [8 epilogue warps][32 rows][64 B] message staging
-    uint8_t* sAx = misc + EK_SLAB_BYTES;                         // bias step A slice: [16 row groups][2 k cores][8 rows][16 B]
-    uint8_t* sBx = sAx + EK_AX_BYTES;                            // bias step B slice: [16 row groups][2 k cores][8 rows][16 B]
+    uint8_t* sSlab = misc;                                       // [12 epilogue warps][32 rows][64 B] message staging
+    uint8_t* sAx = misc + EP_SLAB_BYTES;                         // bias step A slice: [2 k cores][8 rows][16 B], shared by all row groups
+    uint8_t* sBx = sAx + EP_AX_BYTES;                            // bias step B slice: [16 row groups][2 k cores][8 rows][16 B]
     int4* sMeta = reinterpret_cast<int4*>(sBx + EP_BX_BYTES);    // [16 producer warps][2 slots][8 edges]
-    float* sDot = reinterpret_cast<float*>(sBx + EP_BX_BYTES + EK_META_BYTES);   // [2 accumulators][128 rows]
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(sBx + EP_BX_BYTES + EK_META_BYTES + EK_DOT_BYTES);
+    float* sDot = reinterpret_cast<float*>(sBx + EP_BX_BYTES + EK_META_BYTES);   // [2 accumulators][2 column groups][128 rows]
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(sBx + EP_BX_BYTES + EK_META_BYTES + EP_DOT_BYTES);
     uint64_t* w_peer = w_bar + 1;                                // leader: the peer's half of W2 has landed
     uint64_t* mma_done = w_bar + 2;                              // [2]
     uint64_t* tmem_empty = mma_done + 2;                         // [2] (leader's copy is the live one)
@@ -127,10 +134,10 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
         mbar_init(w_peer, 1);
         mbar_init(&mma_done[0], 1);
         mbar_init(&mma_done[1], 1);
-        mbar_init(&tmem_empty[0], 2 * EK_EPI_WARPS);
-        mbar_init(&tmem_empty[1], 2 * EK_EPI_WARPS);
-        mbar_init(&a_full[0], 2 * EK_PROD_WARPS);
-        mbar_init(&a_full[1], 2 * EK_PROD_WARPS);
+        mbar_init(&tmem_empty[0], 2 * EP_EPI_WARPS);
+        mbar_init(&tmem_empty[1], 2 * EP_EPI_WARPS);
+        mbar_init(&a_full[0], 2 * EP_PROD_WARPS);
+        mbar_init(&a_full[1], 2 * EP_PROD_WARPS);
         fence_mbar_init();
         // the resident second-layer weights are constant: their load runs under the predecessor's tail (before pdl_wait)
         mbar_arrive_expect_tx(w_bar, EP_WH_BYTES);
@@ -141,14 +148,14 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
     // bias step operands (K-major core matrices, no swizzle): A[r][0] = A[r][1] = 1 ; B[n][0] + B[n][1] = b2[n]
     {
         const EdgeConsts& cc = second ? c1 : c0;
-        for (int i = tid; i < (EK_AX_BYTES + EP_BX_BYTES) / 16; i += EK_THREADS) {
+        for (int i = tid; i < (EP_AX_BYTES + EP_BX_BYTES) / 16; i += EP_THREADS) {
             const int core = i >> 3, r8 = i & 7;                 // 16-byte row r8 of core matrix `core`
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if ((core & 1) == 0) {                               // k core 0 holds k = 0..7
-                if (i < EK_AX_BYTES / 16) {
+                if (i < EP_AX_BYTES / 16) {
                     v.x = 0x3f803f80u;                           // bf16 (1, 1)
                 } else {
-                    const int n = (int)rank * 128 + ((core - EK_AX_BYTES / 128) >> 1) * 8 + r8;
+                    const int n = (int)rank * 128 + ((core - EP_AX_BYTES / 128) >> 1) * 8 + r8;
                     const float b = cc.b2[n];
                     const float hi = __bfloat162float(__float2bfloat16_rn(b));
                     v.x = pack_bf16x2(hi, b - hi);
@@ -167,7 +174,7 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
     const int num_tiles = (E + EK_TILE - 1) / EK_TILE;
     const int num_tp = (num_tiles + 1) >> 1;     // tile pairs: pair p, iteration it works on tiles 2 (p + it num_pairs) + rank
 
-    if (warp == EK_EPI_WARPS + EK_PROD_WARPS) {
+    if (warp == EP_EPI_WARPS + EP_PROD_WARPS) {
         // =========================== MMA issuer (one lane of the leader CTA) ===========================
         if (lane == 0) {
             mbar_wait(w_bar, 0);                                                      // own half of W2 has landed
@@ -176,7 +183,8 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
             } else if (pair < num_tp) {
                 constexpr uint32_t idesc = make_idesc_bf16_f32(2 * EK_TILE, EK_H);
                 const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW);
-                const uint64_t ax = make_kmajor_noswz_desc(smem_u32(sAx), 128, 256), bx = make_kmajor_noswz_desc(smem_u32(sBx), 128, 256);
+                // A slice: stride 0 between the 8-row groups -- all 128 rows read the same core-matrix pair
+                const uint64_t ax = make_kmajor_noswz_desc(smem_u32(sAx), 128, 0), bx = make_kmajor_noswz_desc(smem_u32(sBx), 128, 256);
                 mbar_wait_park_cluster(w_peer, 0);
                 int it = 0;
                 for (int tp = pair; tp < num_tp; tp += num_pairs, ++it) {
@@ -203,9 +211,9 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
             }
         }
         __syncwarp();
-    } else if (warp >= EK_EPI_WARPS) {
+    } else if (warp >= EP_EPI_WARPS) {
         // =========================== producers ===========================
-        const int pw = warp - EK_EPI_WARPS;
+        const int pw = warp - EP_EPI_WARPS;
         // lane owns k = 8*lane .. 8*lane+7 of the (halved) first-layer pre-activation: one 16-byte bf16 unit
         float wr[8], w0[8];
         {
@@ -263,7 +271,8 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
         // The warp's 8 edges of a tile are processed as four ROUNDS of two edges.  The gathers of round r + 1 (P[row], Q[col]:
         // two 16-byte bf16 units per edge and lane) are issued BEFORE round r is evaluated, across tile boundaries as well
         // (the next tile's metadata is already in the other slot), so a warp always has one round of loads in flight while it
-        // computes -- with the A tile double-buffered nothing else hides a producer warp's own gather latency.
+        // computes -- with the A tile double-buffered nothing else hides a producer warp's own gather latency.  (A ring of four
+        // single-edge slots, three edges in flight, measured 2 % slower.)
         auto issue2 = [&](int slot, int r, uint4 (&pv)[2], uint4 (&qv)[2]) {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
@@ -358,8 +367,9 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
             if (lane == 0 && pw == 0) EK_STAMP(it, 4);
         }
     } else {
-        // ============ epilogue (warps 0-7: TMEM lane quarter q = warp % 4, column half hf = warp / 4) ============
-        const int hf = warp >> 2;
+        // ===== epilogue (warps 0-11: TMEM lane quarter q = warp % 4, column group cg = warp / 4 drains chunks [0,4) / [4,10) / [10,16)) =====
+        // Group 0 gets the short range: it also waits for the other two partial dot products and writes the gate / head value.
+        const int cg = warp >> 2;
         const int q = warp & 3;
         const int trow = q * 32 + lane;
         uint8_t* slab = sSlab + warp * 2048;
@@ -376,17 +386,23 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
             const uint32_t d_tmem = tmem_base + (uint32_t)buf * EK_H + ((uint32_t)(q * 32) << 16);
             const int row0 = tile * EK_TILE + q * 32;
             float dot;
-            if (hf) {
-                dot = second ? epilogue_row<kGCL, 1>(c1, d_tmem, slab, &tmap_msg, row0, lane)
-                             : epilogue_row<kGCL, 1>(c0, d_tmem, slab, &tmap_msg, row0, lane);
-                sDot[buf * EK_TILE + trow] = dot;
-                // barrier id alternates with the accumulator (this warp may run one tile ahead of its partner)
-                asm volatile("bar.arrive %0, %1;" ::"r"(2 + 2 * q + buf), "r"(64) : "memory");
+            if (cg == 2) {
+                dot = second ? epilogue_row<kGCL, 10, 6>(c1, d_tmem, slab, &tmap_msg, row0, lane)
+                             : epilogue_row<kGCL, 10, 6>(c0, d_tmem, slab, &tmap_msg, row0, lane);
+            } else if (cg == 1) {
+                dot = second ? epilogue_row<kGCL, 4, 6>(c1, d_tmem, slab, &tmap_msg, row0, lane)
+                             : epilogue_row<kGCL, 4, 6>(c0, d_tmem, slab, &tmap_msg, row0, lane);
             } else {
-                dot = second ? epilogue_row<kGCL, 0>(c1, d_tmem, slab, &tmap_msg, row0, lane)
-                             : epilogue_row<kGCL, 0>(c0, d_tmem, slab, &tmap_msg, row0, lane);
-                named_bar_sync(2 + 2 * q + buf, 64);
-                dot += sDot[buf * EK_TILE + trow];
+                dot = second ? epilogue_row<kGCL, 0, 4>(c1, d_tmem, slab, &tmap_msg, row0, lane)
+                             : epilogue_row<kGCL, 0, 4>(c0, d_tmem, slab, &tmap_msg, row0, lane);
+            }
+            if (cg != 0) {
+                sDot[(buf * 2 + cg - 1) * EK_TILE + trow] = dot;
+                // barrier id alternates with the accumulator (a warp may run one tile ahead of its partners)
+                asm volatile("bar.arrive %0, %1;" ::"r"(2 + 2 * q + buf), "r"(96) : "memory");
+            } else {
+                named_bar_sync(2 + 2 * q + buf, 96);
+                dot += sDot[(buf * 2) * EK_TILE + trow] + sDot[(buf * 2 + 1) * EK_TILE + trow];
                 if (valid) {
                     if (kGCL) g.att[e] = sigmoid_fast(dot + pr.bout) * pr.out_scale;
                     else pr.head_out[e] = pr.out_scale * tanhf(dot);
@@ -398,7 +414,7 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
             if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)buf * 8);   // accumulator drained (this warp's part)
         }
     }
-    if (kGCL && warp < EK_EPI_WARPS && lane == 0) tma_store_wait_all();   // message writes complete before exit
+    if (kGCL && warp < EP_EPI_WARPS && lane == 0) tma_store_wait_all();   // message writes complete before exit
     tc_fence_before_sync();
     cluster_sync_all();                          // no CTA leaves while its peer may still signal it or read its tiles
     if (warp == 0) tmem_dealloc_pair<512>(tmem_base);

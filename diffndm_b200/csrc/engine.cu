@@ -34,9 +34,6 @@ static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] 
 // GCL producers: all-bf16x2 first-layer pre-activation by default; DNDM_GCL_F32_RADIAL=1 selects the variant with fp32 radial
 // terms and activation (measured on the radial stress fixture: same error to two digits, 8 % slower -- see edge_mlp.cuh)
 static bool g_bf16_radial = [] { const char* v = getenv("DNDM_GCL_F32_RADIAL"); return !(v && v[0] == '1'); }();
-// Edge MLPs on CTA pairs (edge_pair.cuh: tcgen05 cta_group::2, W2 split over the pair, double-buffered A tile) by default;
-// DNDM_EK_PAIR=0 selects the single-CTA kernel of edge_mlp.cuh (A/B measurements).
-static bool g_ek_pair = [] { const char* v = getenv("DNDM_EK_PAIR"); return !(v && v[0] == '0'); }();
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
@@ -82,19 +79,6 @@ static PFN_encodeTiled get_encode_fn() {
             fn = reinterpret_cast<PFN_encodeTiled>(p);
     }
     return fn;
-}
-static int make_tmap_f32_out(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
-    PFN_encodeTiled fn = get_encode_fn();
-    if (!fn) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld * 4};
-    cuuint32_t box[2] = {32, 32};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_err(DNDM_ECUDA, "cuTensorMapEncodeTiled (f32 out) failed with %d", (int)r);
-    return DNDM_OK;
 }
 static int make_tmap_bf16_box(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                               uint32_t box_rows, CUtensorMapSwizzle swz) {
@@ -215,7 +199,7 @@ static int dev_alloc(T** p, size_t n) {
         if (_r != DNDM_OK) return _r; \
     } while (0)
 
-extern "C" const char* dndm_version(void) { return "diffndm_b200 0.2 (sm_100a, tcgen05/TMA)"; }
+extern "C" const char* dndm_version(void) { return "diffndm_b200 0.3 (sm_100a, tcgen05 cta_group::2 / TMA)"; }
 extern "C" const char* dndm_last_error(void) { return g_err; }
 extern "C" int64_t dndm_launch_count(void) { return g_launches; }
 
@@ -265,9 +249,6 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
-    CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
-    CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
-    CU_CHECK(cudaFuncSetAttribute(edge_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EK_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
@@ -674,13 +655,9 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         {
             ProfScope ps(e, PROF_GCL, st);
             // PDL: preceded by the merged projection GEMM (block 0) / coord_update (later blocks) on this stream
-            if (g_ek_pair)
-                CU_CHECK(launch_pdl(pdl, g_bf16_radial ? edge_pair_kernel<true, true> : edge_pair_kernel<true, false>,
-                                    dim3(e->num_sms & ~1, 1), dim3(EK_THREADS), EP_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e,
-                                    L.c_e, g, pe, pe));
-            else
-                CU_CHECK(launch_pdl(pdl, g_bf16_radial ? edge_mlp_kernel<true, true> : edge_mlp_kernel<true, false>, dim3(e->num_sms, 1),
-                                    dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e, L.c_e, g, pe, pe));
+            CU_CHECK(launch_pdl(pdl, g_bf16_radial ? edge_pair_kernel<true, true> : edge_pair_kernel<true, false>,
+                                dim3(e->num_sms & ~1, 1), dim3(EP_THREADS), EP_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e,
+                                L.c_e, g, pe, pe));
         }
         {
             ProfScope ps(e, PROF_NODE, st);
@@ -712,12 +689,9 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
             {
                 ProfScope ps(e, PROF_HEAD, st);
-                if (g_ek_pair)
-                    CU_CHECK(launch_pdl(pdl, edge_pair_kernel<false>, dim3(gx > 1 ? gx & ~1 : 2, 2), dim3(EK_THREADS), EP_SMEM_BYTES, st,
-                                        L.tm_w2_c, L.tm_w2_x, e->to_msg, L.c_c, L.c_x, gh, pc, px));
-                else
-                    CU_CHECK(launch_pdl(pdl, edge_mlp_kernel<false>, dim3(gx, 2), dim3(EK_THREADS), EK_SMEM_BYTES, st, L.tm_w2_c, L.tm_w2_x,
-                                        e->to_msg, L.c_c, L.c_x, gh, pc, px));
+                // CTA pairs: an even number of CTAs per problem
+                CU_CHECK(launch_pdl(pdl, edge_pair_kernel<false>, dim3(gx > 1 ? gx & ~1 : 2, 2), dim3(EP_THREADS), EP_SMEM_BYTES, st,
+                                    L.tm_w2_c, L.tm_w2_x, e->to_msg, L.c_c, L.c_x, gh, pc, px));
             }
             ProfScope ps2(e, PROF_NODE, st);
             coord_update_kernel<<<(n_lig * 32 + 255) / 256, 256, 0, st>>>(x_cur, x_next, e->row_ptr, e->ecol, e->phi, e->psi,

@@ -4,7 +4,7 @@
     python scripts/ncu_summary.py list  gpurun_out/<launches>.csv  profiles/<out>_summary.csv
 
 ``full``: the metrics the roofline discussion uses, per profiled launch (raw page).  With --edges-per-launch it also writes
-profiles/gcl_traffic.json -- DRAM bytes per edge of edge_mlp_kernel<GCL> -- which bench.py reads for ``roofline.traffic``.
+profiles/gcl_traffic.json -- DRAM bytes per edge of edge_pair_kernel<GCL> -- which bench.py reads for ``roofline.traffic``.
 ``list``: per kernel name the launch count, total and share of device time (ncu --metrics gpu__time_duration.sum)."""
 import csv
 import json
@@ -38,7 +38,7 @@ def full(rep, out, edges=None, version=None):
     json.dump({'source': os.path.basename(rep), 'command': 'ncu --set full --clock-control none --import-source on', 'launches': res},
               open(out, 'w'), indent=1)
     if edges:
-        gcl = [o for o in res if 'edge_mlp_kernel<1' in o['kernel'] or 'edge_mlp_kernel<(bool)1' in o['kernel']]
+        gcl = [o for o in res if 'edge_pair_kernel<1' in o['kernel'] or 'edge_pair_kernel<(bool)1' in o['kernel']]
         if gcl:
             to_b = lambda o, k: o[k] * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[o[k + ' [unit]']]
             tot = sum(to_b(o, 'dram__bytes_read.sum') + to_b(o, 'dram__bytes_write.sum') for o in gcl) / len(gcl)
