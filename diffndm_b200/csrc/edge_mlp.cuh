@@ -111,22 +111,6 @@ DNDM_DEVICE uint32_t pack_bf16x2_epi(float lo, float hi) {
 }
 DNDM_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
-// mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of burning issue slots
-DNDM_DEVICE void mbar_wait_park(uint64_t* bar, uint32_t parity) {
-    // a failed (timed-out) try_wait backs off before polling again: 25 warps share four schedulers, and a waiting warp
-    // that keeps re-issuing try_wait takes issue slots from the ones that have work
-    asm volatile(
-        "{\n\t.reg .pred P;\n"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
-        "@P bra DONE_%=;\n\t"
-        "nanosleep.u32 %3;\n\t"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(200000u), "r"(256u)
-        : "memory");
-}
-
 // Epilogue of one tile row (one thread = one edge): m = SiLU(D) (D = half pre-activation incl. bias), dot with wout.
 // GCL additionally writes m as bf16 to the message buffer (64 contiguous bytes per 32-column chunk).
 // `cc` must be one of the __grid_constant__ kernel parameters so that b2/wout become constant-bank operands.

@@ -32,68 +32,6 @@ constexpr int EP_MISC_BYTES = EP_SLAB_BYTES + EP_AX_BYTES + EP_BX_BYTES + EK_MET
 constexpr int EP_SMEM_BYTES = EP_WH_BYTES + 2 * EK_A_BYTES + EP_MISC_BYTES;
 static_assert(EP_SMEM_BYTES <= 232448, "pair edge kernel shared memory exceeds 227 KiB");
 
-DNDM_DEVICE uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-DNDM_DEVICE uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-    return r;
-}
-// Remote arrive with the default semantics, as CUTLASS's generic-proxy -> 2-SM UMMA pipelines do (fence.proxy.async.shared::cta
-// + mbarrier.arrive.shared::cluster on the leader's barrier).  An explicit .release.cluster was measured first: 2 800 cycles
-// per arrive (it drains every outstanding memory operation of the warp, global gathers included).
-DNDM_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-DNDM_DEVICE void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
-DNDM_DEVICE void mbar_wait_park_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred P;\n"
-        "WAITC_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
-        "@P bra DONEC_%=;\n\t"
-        "nanosleep.u32 %3;\n\t"
-        "bra WAITC_%=;\n"
-        "DONEC_%=:\n\t}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(200000u), "r"(128u)
-        : "memory");
-}
-DNDM_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-template <uint32_t kCols>
-DNDM_DEVICE void tmem_alloc_pair(uint32_t* smem_slot) {    // one full warp of EACH CTA of the pair, same smem offset
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <uint32_t kCols>
-DNDM_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-// D[tmem of both CTAs] (+)= A * B over the pair: M = 256 (128 rows from each CTA's smem), N = 256 (128 B rows from each)
-DNDM_DEVICE void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// all MMAs issued so far arrive on the mbarrier at this shared-memory offset in BOTH CTAs when complete
-DNDM_DEVICE void umma_commit_pair(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-
 template <bool kGCL, bool kBf16Radial = true>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EP_THREADS, 1)
 edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,

@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
-#include "gemm_wres.cuh"
+#include "gemm_pair.cuh"
 #include "edge_mlp.cuh"
 #include "edge_pair.cuh"
 #include "graph.cuh"
@@ -115,7 +115,7 @@ struct LayerWeights {
     __nv_bfloat16 *wproj_e, *w2_e, *w2_c, *w2_x, *w3, *w4;             // device bf16
     __nv_bfloat16* wm;                                                  // merged projections [next-edge P|Q ; coord Q ; cross Q ; coord P ; cross P]
     float* bias_m;
-    CUtensorMap tm_wm, tm_we0;                                    // 256-row boxes for the weight-resident GEMM
+    CUtensorMap tm_wm, tm_we0;                                    // 128-row boxes (half a 256-column group per CTA of a pair)
     float *bias_e, *b3, *b4, *w1e_e, *w1e_c, *w1e_x;                   // device fp32
     CUtensorMap tm_w2_e, tm_w2_c, tm_w2_x, tm_w3, tm_w4;
     EdgeConsts c_e, c_c, c_x;                                            // host copies (kernel parameters)
@@ -246,9 +246,9 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(make_tmap_bf16_box(&e->to_pq32, e->pq, N, 1536, 1536, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_hcat32, e->hcat, N, 512, 512, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RET_IF(make_tmap_bf16_box(&e->to_hid32, e->hid, N, 256, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
@@ -442,8 +442,8 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
             L.c_x.b2[o] = 0.5f * x2b[o]; L.c_x.wout[o] = x4w[o];
         }
         L.att_bias = ab[0];
-        RET_IF(make_tmap_bf16(&L.tm_w3, L.w3, H, 2 * H, 2 * H, 128));
-        RET_IF(make_tmap_bf16(&L.tm_w4, L.w4, H, H, H, 128));
+        RET_IF(make_tmap_bf16(&L.tm_w3, L.w3, H, 2 * H, 2 * H, 64));        // boxes of BN/2 weight rows: one CTA's half of a column group
+        RET_IF(make_tmap_bf16(&L.tm_w4, L.w4, H, H, H, 64));
         RET_IF(make_tmap_bf16(&L.tm_w2_e, L.w2_e, H, H, H, 128));      // one box = 128 output channels x 64 inputs
         RET_IF(make_tmap_bf16(&L.tm_w2_c, L.w2_c, H, H, H, 128));      // one box = 128 output channels x 64 inputs
         RET_IF(make_tmap_bf16(&L.tm_w2_x, L.w2_x, H, H, H, 128));      // one box = 128 output channels x 64 inputs
@@ -480,8 +480,8 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
             bm[5 * H + o] = 0.5f * x0b[o];
         }
         RET_IF(upload(e, wm, &L.wm)); RET_IF(upload(e, bm, &L.bias_m));
-        RET_IF(make_tmap_bf16(&L.tm_wm, L.wm, 6 * H, H, H, 256));
-        RET_IF(make_tmap_bf16(&L.tm_we0, L.wproj_e, 2 * H, H, H, 256));
+        RET_IF(make_tmap_bf16(&L.tm_wm, L.wm, 6 * H, H, H, 128));
+        RET_IF(make_tmap_bf16(&L.tm_we0, L.wproj_e, 2 * H, H, H, 128));
     }
     e->weights_loaded = true;
     return DNDM_OK;
@@ -490,26 +490,28 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-// n_full column groups over M rows followed by n_tail groups over the first M_tail rows (see gemm_wres_kernel)
+// n_full column groups over M rows followed by n_tail groups over the first M_tail rows (see gemm_pair_kernel); every group
+// is served by CTA pairs that stride over its 256-row blocks
 template <int kK = 256, int kBN = 256>
 static int launch_wres(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to16, int M,
                        int n_full, int g0, int a_col0, const WresEpilogue& ep, int n_tail = 0, int M_tail = 0, bool pdl = false) {
     if (M <= 0) return DNDM_OK;
     if (M_tail <= 0) n_tail = 0;
-    const int m_tiles = (M + WR_BM - 1) / WR_BM, t_tiles = (M_tail + WR_BM - 1) / WR_BM;
-    int ctas_tail = 0;
+    const int m_pairs = (M + 2 * WR_BM - 1) / (2 * WR_BM), t_pairs = (M_tail + 2 * WR_BM - 1) / (2 * WR_BM);
+    const int slots = g_num_sms / 2 > 0 ? g_num_sms / 2 : 1;      // co-resident CTA pairs
+    int pairs_tail = 0;
     if (n_tail > 0) {                                   // share the SMs in proportion to the row blocks
-        const double per_cta = (double)(n_full * m_tiles + n_tail * t_tiles) / g_num_sms;
-        ctas_tail = (int)(t_tiles / per_cta + 0.999);
-        if (ctas_tail < 1) ctas_tail = 1;
-        if (ctas_tail > t_tiles) ctas_tail = t_tiles;
+        const double per_pair = (double)(n_full * m_pairs + n_tail * t_pairs) / slots;
+        pairs_tail = (int)(t_pairs / per_pair + 0.999);
+        if (pairs_tail < 1) pairs_tail = 1;
+        if (pairs_tail > t_pairs) pairs_tail = t_pairs;
     }
-    int ctas_full = (g_num_sms - n_tail * ctas_tail) / n_full;
-    if (ctas_full < 1) ctas_full = 1;
-    if (ctas_full > m_tiles) ctas_full = m_tiles;
-    const int grid = n_full * ctas_full + n_tail * ctas_tail;
-    CU_CHECK(launch_pdl(pdl, gemm_wres_kernel<kK, kBN>, dim3(grid), dim3(WR_THREADS), WresShape<kK, kBN>::smem_bytes, st, ta, tw, to16,
-                        M, M_tail, a_col0, g0, n_full, ctas_full, ctas_tail > 0 ? ctas_tail : 1, ep));
+    int pairs_full = (slots - n_tail * pairs_tail) / n_full;
+    if (pairs_full < 1) pairs_full = 1;
+    if (pairs_full > m_pairs) pairs_full = m_pairs;
+    const int grid = 2 * (n_full * pairs_full + n_tail * pairs_tail);
+    CU_CHECK(launch_pdl(pdl, gemm_pair_kernel<kK, kBN>, dim3(grid), dim3(WR_THREADS), WresShape<kK, kBN>::smem_bytes, st, ta, tw, to16,
+                        M, M_tail, a_col0, g0, n_full, pairs_full, pairs_tail > 0 ? pairs_tail : 1, ep));
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
@@ -910,12 +912,12 @@ extern "C" int dndm_test_gemm(const void* a_bf16, const void* w_bf16, const floa
     const uint64_t rows = (uint64_t)((M + WR_BM - 1) / WR_BM) * WR_BM;      // the caller pads A / out_bf16 to whole row blocks
     CUtensorMap ta, tw, to;
     RET_IF(make_tmap_bf16(&ta, a_bf16, rows, K, K, WR_BM));
-    RET_IF(make_tmap_bf16(&tw, w_bf16, N, K, K, bn));
+    RET_IF(make_tmap_bf16(&tw, w_bf16, N, K, K, bn / 2));
     if (out_bf16) RET_IF(make_tmap_bf16_box(&to, out_bf16, rows, N, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     else to = ta;
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
-    CU_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
+    CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
     WresEpilogue ep{bias, residual, 256, out_f32, N, 0, out_bf16 ? 1 : 0, 0, act, reinterpret_cast<__nv_bfloat16*>(out_bf16), N};
     if (residual && !s128) return set_err(DNDM_EINVAL, "the residual epilogue exists for (K, BN) = (256, 128) only");
     const int n_full = N / bn - n_tail_groups;

@@ -280,7 +280,7 @@ def launch_count() -> int:
 
 def test_gemm(a_bf16: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0, bn: int = 256,
               residual: Optional[torch.Tensor] = None, n_tail_groups: int = 0, m_tail: int = 0, want_bf16: bool = False):
-    """C = A W^T (+bias)(+residual)(SiLU) through ``gemm_wres_kernel``, the weight-resident tcgen05 node GEMM, with the
+    """C = A W^T (+bias)(+residual)(SiLU) through ``gemm_pair_kernel``, the weight-resident tcgen05 node GEMM, with the
     forward's launch geometry.  Returns (out_f32 [M,N], out_bf16 [M,N] or None); outputs the tail groups do not cover are 0."""
     lib = load_library()
     M, K = a_bf16.shape

@@ -153,7 +153,7 @@ int dndm_get_profile(DndmEngine* e, double* ms_per_category, int32_t* launches_p
  * [n_layers, max_trace_nodes, 3] fp32, either may be NULL), every forward stores h and x after each block. */
 int dndm_set_trace(DndmEngine* e, float* h_trace, float* x_trace, int32_t max_trace_nodes);
 
-/* Self-test of the weight-resident tcgen05 node GEMM (gemm_wres_kernel) with the launch geometry of the forward:
+/* Self-test of the weight-resident tcgen05 node GEMM (gemm_pair_kernel) with the launch geometry of the forward:
  *   C[M, N] = epilogue( A[M, K] (bf16) x W[N, K]^T (bf16) + bias [+ residual] ),  optional SiLU,
  * (K, bn) in {(256, 256), (512, 128), (256, 128)}: bn output columns per resident weight group, N % bn == 0.  The last
  * n_tail_groups column groups are computed for the first m_tail rows only (the ligand-row-only projections of the merged

@@ -1,4 +1,4 @@
-"""Per-row-block timeline of the merged projection GEMM (gemm_wres_kernel<256,256>, CTA 0) from clock64 stamps.
+"""Per-row-block timeline of the merged projection GEMM (gemm_pair_kernel<256,256>, CTA 0 = leader of pair 0) from clock64 stamps.
 Needs a library built with DNDM_EXTRA_NVCC_FLAGS=-DDNDM_EK_TRACE (development only).
 events: 0 producer: row block start | 1 producer: 4 TMA loads issued | 2 MMA: first k-block landed | 3 MMA: last k-block
 landed | 4 MMA: committed | 5 drain warp: accumulator ready | 6 drain warp: row block stored"""

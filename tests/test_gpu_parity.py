@@ -65,7 +65,7 @@ def _edges_from_csr(rp, col):
     (700, 256, 256, 128, 0, True, (0, 0)),       # node MLP layer 2 (+ fp32 residual, bf16 copy)
 ])
 def test_tcgen05_node_gemm(dev, M, N, K, bn, act, res, tail):
-    """gemm_wres_kernel -- the kernel every node GEMM of the forward launches -- in all three compiled shapes, with tail
+    """gemm_pair_kernel -- the kernel every node GEMM of the forward launches -- in all three compiled shapes, with tail
     groups, bias, SiLU, the fp32 residual epilogue and the bf16 (TMA store) output, against a torch fp32 reference."""
     from diffndm_b200.engine import test_gemm
     g = torch.Generator().manual_seed(M * 7 + N)
