@@ -109,6 +109,11 @@ DNDM_DEVICE uint32_t pack_bf16x2_epi(float lo, float hi) {
     return pack_bf16x2(lo, hi);
 #endif
 }
+DNDM_DEVICE uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 DNDM_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 // Epilogue of one tile row (one thread = one edge): m = SiLU(D) (D = half pre-activation incl. bias), dot with wout.

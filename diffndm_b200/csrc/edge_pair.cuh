@@ -249,17 +249,22 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
                     }
                     o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 } else {
+                    // coordinate heads: fp32 throughout, two channels per instruction (FADD2 / FFMA2 -- same IEEE results as scalar)
                     const float rad = __int_as_float(zw.x), r0v = __int_as_float(zw.y);
-                    float v[8];
+                    const uint64_t rad2 = f2_pack(rad, rad), r02 = f2_pack(r0v, r0v);
+                    uint32_t ow[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        v[2 * i] = __uint_as_float(pw_[i] << 16) + __uint_as_float(qw_[i] << 16);
-                        v[2 * i + 1] = __uint_as_float(pw_[i] & 0xffff0000u) + __uint_as_float(qw_[i] & 0xffff0000u);
+                        const uint64_t p2 = f2_pack(__uint_as_float(pw_[i] << 16), __uint_as_float(pw_[i] & 0xffff0000u));
+                        const uint64_t q2 = f2_pack(__uint_as_float(qw_[i] << 16), __uint_as_float(qw_[i] & 0xffff0000u));
+                        const uint64_t pre = f2_fma(w0f[i], r02, f2_fma(wrf[i], rad2, f2_add(p2, q2)));
+                        float lo, hi;
+                        f2_unpack(pre, lo, hi);
+                        float m0, m1;
+                        f2_unpack(f2_fma(pre, f2_pack(tanh_approx(lo), tanh_approx(hi)), pre), m0, m1);
+                        ow[i] = pack_bf16x2(m0, m1);
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = silu_half(fmaf(w0[i], r0v, fmaf(wr[i], rad, v[i])));
-                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
                 const uint32_t rr = pw * 8 + r * 2 + jj;
                 *reinterpret_cast<uint4*>(sA_lane + rr * 128 + ((u ^ (rr & 7)) << 4)) = o;

@@ -8,6 +8,11 @@
 // an A ring of ONE row block, a stage refilled only after its MMA completed -> a TMA round trip exposed per row block, row-
 // block period 4 100 cycles against 1 100 of MMA) the halved weights leave room for an 8-stage ring = two row blocks in
 // flight, and the B-operand shared-memory reads per row are halved.
+// Measured on B200: node GEMMs 0.444 -> 0.432 ms per step.  The clock64 timelines (scripts/wr_timeline.py) show what is left:
+// a CTA sees only 2-5 row-block iterations per launch, so the fixed part -- set-up 2 700 cycles, the first TMA round trip
+// 2 500 (up to 9 000 next to the residual epilogue's global traffic), the last drain 3 000 -- is as long as the streaming part.
+// Whole 256-column groups for the node MLP (its input read once instead of twice; (512, 256) and (256, 256) + residual fit a
+// pair) were measured SLOWER (0.447): half as many iterations per pair and a half-row-block ring for K = 512.
 //
 // Persistent, warp-specialised (1 CTA / SM):
 //   warp 0     TMA producer : half of the W group once; A tiles (128 x 64 bf16, SWIZZLE_128B) into the ring; the completion
@@ -59,10 +64,15 @@ struct WresEpilogue {
 };
 
 #ifdef DNDM_EK_TRACE
+#ifndef DNDM_WR_TRACE_K            // which shape is traced (default: the merged projection)
+#define DNDM_WR_TRACE_K 256
+#define DNDM_WR_TRACE_BN 256
+#endif
 __device__ unsigned long long g_wr_trace[64 * 8];
 #define WR_STAMP(it, ev)                                                                                      \
     do {                                                                                                      \
-        if (kK == 256 && kBN == 256 && blockIdx.x == 0 && (it) < 64) g_wr_trace[(it) * 8 + (ev)] = clock64(); \
+        if (kK == DNDM_WR_TRACE_K && kBN == DNDM_WR_TRACE_BN && blockIdx.x == 0 && (it) < 64)                 \
+            g_wr_trace[(it) * 8 + (ev)] = clock64();                                                          \
     } while (0)
 #else
 #define WR_STAMP(it, ev) do {} while (0)
@@ -113,6 +123,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int m_pairs = (m_tiles + 1) >> 1;          // 256-row blocks; CTA `rank` takes row block 2 * mp + rank
     const bool has_work = pair_rank < m_pairs;
     pdl_trigger();
+    if (threadIdx.x == 0) WR_STAMP(0, 7);            // kernel entry
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -134,6 +145,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     cluster_sync_all();                              // barriers of both CTAs initialised before any cross-CTA signal
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) WR_STAMP(2, 7);            // set-up done
 
     if (warp == 0) {
         if (elect_one() && has_work) {
@@ -144,6 +156,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int kc = 0; kc < KB; ++kc)
                 tma_load_2d_pair(sW + kc * (WR_BN / 2 * 128), &tmap_w, w_bar_leader, kc * 64, grp * WR_BN + (int)rank * (WR_BN / 2));
             pdl_wait();                              // A belongs to earlier kernels of the stream
+            WR_STAMP(3, 7);
             const uint32_t full_leader = mapa_shared(smem_u32(full_bar), 0);
             int kq = 0, itp = 0;
             for (int mp = pair_rank; mp < m_pairs; mp += pair_stride, ++itp) {
@@ -343,6 +356,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before_sync();
     cluster_sync_all();              // no CTA leaves while its peer may still signal it or read its tiles
+    if (threadIdx.x == 0) WR_STAMP(1, 7);            // kernel exit
     if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 

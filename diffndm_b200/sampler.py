@@ -457,9 +457,10 @@ class ConditionalSampler:
                 s_array = torch.full((B, 1), fill_value=s, dtype=torch.float32) / timesteps
                 t_array = torch.full((B, 1), fill_value=s + 1, dtype=torch.float32) / timesteps
                 step += 1
-                # inside a guidance window the state is replaced every few steps (and ATP re-batches it): capturing a graph
-                # there costs more than the launches it saves, so those steps run eagerly (without per-step host syncs)
-                in_window = (svdd == 1 and s <= svdd_schedule[0]) or (spsa == 1 and s <= spsa_schedule[0])
+                # inside an ATP window the batch is re-built every few steps (other ligand sizes, another mask): capturing a graph
+                # per event costs more than the launches it saves, so those steps run eagerly (without per-step host syncs).
+                # An SPSA update keeps shapes and masks: the cached graph is reused, the new state is copied into its buffers.
+                in_window = svdd == 1 and s <= svdd_schedule[0]
                 if graphed and not in_window:
                     if gstep is None:
                         # graphs are kept across trajectories: the same pocket with the same ligand sizes (the usual

@@ -24,6 +24,8 @@ dyn.engine.lib.dndm_debug_copy(dyn.engine._h, 6, ctypes.c_void_p(buf.data_ptr())
 torch.cuda.synchronize()
 tr = buf.cpu().numpy().reshape(64, 8)
 base = tr[0, 0]
+print('kernel entry 0 | set-up done', tr[2, 7] - tr[0, 7], '| predecessor done (pdl_wait)', tr[3, 7] - tr[0, 7], '| exit', tr[1, 7] - tr[0, 7])
+base = tr[0, 7]
 print('it | prod_start loads_issued | first_kb last_kb committed | acc_ready stored')
 for it in range(0, 9):
     r = tr[it] - base

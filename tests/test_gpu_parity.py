@@ -63,6 +63,7 @@ def _edges_from_csr(rp, col):
     (257, 1024, 256, 256, 0, False, (2, 40)),    # last block: 2 full + 2 tail groups
     (333, 256, 512, 128, 1, False, (0, 0)),      # node MLP layer 1 (K = 512, SiLU)
     (700, 256, 256, 128, 0, True, (0, 0)),       # node MLP layer 2 (+ fp32 residual, bf16 copy)
+    (129, 256, 256, 128, 0, True, (0, 0)),       # ... with an odd number of row blocks (the peer CTA's last block is empty)
 ])
 def test_tcgen05_node_gemm(dev, M, N, K, bn, act, res, tail):
     """gemm_pair_kernel -- the kernel every node GEMM of the forward launches -- in all three compiled shapes, with tail
@@ -767,6 +768,47 @@ def test_graphed_sampling_matches_eager(dyn, dev):
     assert float((outs[0][0][:, 3:].argmax(1) == outs[1][0][:, 3:].argmax(1)).float().mean()) > 0.9
     assert float((outs[0][1] - outs[1][1]).abs().max()) / scale < 5e-4
     assert dyn.engine.read_flags() & 5 == 0
+
+
+def test_graphed_spsa_window_matches_eager(dyn, dev):
+    """Inside an SPSA-only guidance window the reverse steps keep replaying the cached CUDA graph (an SPSA update changes the
+    state, not the shapes or masks: the new state is copied into the graph's buffers).  Same seeds, same stand-in reward: the
+    graphed and the eager trajectory agree, and the graph is captured once for the whole run."""
+    from diffndm_b200 import synthetic
+    from diffndm_b200.sampler import ConditionalSampler, _GraphedReverseStep
+    px, pt = synthetic.synthetic_pocket(11, 70)
+    sizes = np.array([7, 12, 9, 5])
+    B = len(sizes)
+    onehot = np.eye(10, dtype=np.float32)[pt]
+    pocket = {'x': torch.from_numpy(np.tile(px, (B, 1))), 'one_hot': torch.from_numpy(np.tile(onehot, (B, 1))),
+              'size': torch.tensor([len(px)] * B), 'mask': torch.arange(B).repeat_interleave(len(px))}
+
+    def reward(x, types, mask):                     # smooth geometric stand-in (no chemistry in the image)
+        r2 = torch.zeros(int(mask.max()) + 1, device=x.device).index_add_(0, mask, (x * x).sum(1))
+        return (-1e-3 * r2).cpu().tolist()
+
+    smp = ConditionalSampler(dyn, timesteps=500)
+    captures, init = [], _GraphedReverseStep.__init__
+
+    def counting_init(self, *a, **k):
+        captures.append(1)
+        init(self, *a, **k)
+
+    outs = []
+    _GraphedReverseStep.__init__ = counting_init
+    try:
+        for graph in (False, True):
+            torch.manual_seed(321)
+            torch.cuda.manual_seed(321)
+            xh, xp, lm, pm = smp.sample_given_pocket(pocket, sizes, timesteps=8, spsa=1, spsa_schedule=(5, 2), spsa_k=3,
+                                                     reward_fn=reward, mixed_at=None, use_cuda_graph=graph)
+            outs.append((xh.clone(), xp.clone()))
+    finally:
+        _GraphedReverseStep.__init__ = init
+    assert len(captures) == 1                       # one capture, reused across the three SPSA updates
+    scale = max(1.0, float(outs[0][0][:, :3].abs().max()))
+    assert float((outs[0][0][:, :3] - outs[1][0][:, :3]).abs().max()) / scale < 5e-4
+    assert float((outs[0][1] - outs[1][1]).abs().max()) / scale < 5e-4
 
 
 # ---------------------------------------------------------------------------------------------------------------
