@@ -12,7 +12,6 @@
 
 #include "common.cuh"
 #include "gemm_pair.cuh"
-#include "node_fused.cuh"
 #include "edge_mlp.cuh"
 #include "edge_pair.cuh"
 #include "graph.cuh"
@@ -34,9 +33,6 @@ static long long g_launches = 0;   // kernels of this library launched (or captu
 static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] == '0'); }();
 // GCL producers: all-bf16x2 first-layer pre-activation by default; DNDM_GCL_F32_RADIAL=1 selects the variant with fp32 radial
 // terms and activation (measured on the radial stress fixture: same error to two digits, 8 % slower -- see edge_mlp.cuh)
-// Node side of a block: three weight-resident GEMM launches (node-MLP layer 1, layer 2, merged projection); DNDM_NODE_FUSED=1
-// selects the experimental single persistent kernel (node_fused.cuh): measured equal eagerly and 2 % slower under the graph.
-static bool g_node_fused = [] { const char* v = getenv("DNDM_NODE_FUSED"); return v && v[0] == '1'; }();
 static bool g_bf16_radial = [] { const char* v = getenv("DNDM_GCL_F32_RADIAL"); return !(v && v[0] == '1'); }();
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -121,9 +117,6 @@ struct LayerWeights {
     float* bias_m;
     CUtensorMap tm_wm, tm_we0;                                    // 128-row boxes (half a 256-column group per CTA of a pair)
     float *bias_e, *b3, *b4, *w1e_e, *w1e_c, *w1e_x;                   // device fp32
-    __nv_bfloat16* w3h;                                                 // fused node kernel: HALF of W3 (SiLU on x/2), with b3h
-    float* b3h;
-    CUtensorMap tm_w3f, tm_w4f;                                         // ... and 128-row boxes of W3/2 and W4
     CUtensorMap tm_w2_e, tm_w2_c, tm_w2_x, tm_w3, tm_w4;
     EdgeConsts c_e, c_c, c_x;                                            // host copies (kernel parameters)
     float att_bias;
@@ -256,7 +249,6 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 256>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<512, 128>::smem_bytes));
     CU_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WresShape<256, 128>::smem_bytes));
-    CU_CHECK(cudaFuncSetAttribute(node_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NF_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
@@ -444,11 +436,6 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         RET_IF(upload(e, to_bf_half(x2w, (size_t)H * H), &L.w2_x));
         RET_IF(upload(e, to_bf(n0w, (size_t)H * 2 * H), &L.w3)); RET_IF(upload(e, to_bf(n2w, (size_t)H * H), &L.w4));
         RET_IF(upload(e, std::vector<float>(n0b, n0b + H), &L.b3)); RET_IF(upload(e, std::vector<float>(n2b, n2b + H), &L.b4));
-        {
-            std::vector<float> b3h(H);
-            for (int o = 0; o < H; ++o) b3h[o] = 0.5f * n0b[o];
-            RET_IF(upload(e, to_bf_half(n0w, (size_t)H * 2 * H), &L.w3h)); RET_IF(upload(e, b3h, &L.b3h));
-        }
         for (int o = 0; o < H; ++o) {
             L.c_e.b2[o] = 0.5f * e2b[o]; L.c_e.wout[o] = aw[o];
             L.c_c.b2[o] = 0.5f * c2b[o]; L.c_c.wout[o] = c4w[o];
@@ -457,8 +444,6 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         L.att_bias = ab[0];
         RET_IF(make_tmap_bf16(&L.tm_w3, L.w3, H, 2 * H, 2 * H, 64));        // boxes of BN/2 weight rows: one CTA's half of a column group
         RET_IF(make_tmap_bf16(&L.tm_w4, L.w4, H, H, H, 64));
-        RET_IF(make_tmap_bf16(&L.tm_w3f, L.w3h, H, 2 * H, 2 * H, 128));
-        RET_IF(make_tmap_bf16(&L.tm_w4f, L.w4, H, H, H, 128));
         RET_IF(make_tmap_bf16(&L.tm_w2_e, L.w2_e, H, H, H, 128));      // one box = 128 output channels x 64 inputs
         RET_IF(make_tmap_bf16(&L.tm_w2_c, L.w2_c, H, H, H, 128));      // one box = 128 output channels x 64 inputs
         RET_IF(make_tmap_bf16(&L.tm_w2_x, L.w2_x, H, H, H, 128));      // one box = 128 output channels x 64 inputs
@@ -684,28 +669,18 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         // ---- node MLP with residual + node projections: this block's coordinate heads (sender parts for every node, receiver
         //      parts for the ligand rows) and the next block's edge model ----
         const bool has_next = l + 1 < e->cfg.n_layers;
-        if (g_node_fused) {
+        {
             ProfScope ps(e, PROF_GEMM, st);
-            NodeFusedParams np{L.b3h, L.b4, L.bias_m, e->h, N, n_lig, has_next ? 0 : 2};
-            const int m_pairs = (N + 255) / 256, slots = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
-            const int pairs = m_pairs < slots ? m_pairs : slots;
-            CU_CHECK(launch_pdl(pdl, node_fused_kernel<0>, dim3(2 * pairs), dim3(NF_THREADS), NF_SMEM_BYTES, st, e->tm_hcat, L.tm_w3f,
-                                L.tm_w4f, L.tm_wm, e->to_pq32, np));
-            COUNT_LAUNCH(1);
-        } else {
-            {
-                ProfScope ps(e, PROF_GEMM, st);
-                WresEpilogue ep1{L.b3, nullptr, 0, nullptr, 0, 0, 1, 0, 1};          // hid = SiLU(W3 [h | agg] + b3), K = 512
-                RET_IF((launch_wres<512, 128>(st, e->tm_hcat, L.tm_w3, e->to_hid32, N, 2, 0, 0, ep1, 0, 0, pdl)));
-                WresEpilogue ep2{L.b4, e->h, 256, e->h, 256, 0, 1, 0, 0, e->hcat, 512};   // h += W4 hid + b4 ; bf16 copy -> hcat[:, :256]
-                RET_IF((launch_wres<256, 128>(st, e->tm_hid, L.tm_w4, e->to_hcat32, N, 2, 0, 0, ep2, 0, 0, pdl)));
-            }
-            {
-                ProfScope ps(e, PROF_GEMM, st);
-                WresEpilogue epm{L.bias_m, nullptr, 0, nullptr, 0, 0, 1, 0};
-                // column groups 0-3 over all nodes (0,1 only when a next block exists), groups 4,5 over the ligand rows only
-                RET_IF(launch_wres(st, e->tm_hcat, L.tm_wm, e->to_pq32, N, has_next ? 4 : 2, has_next ? 0 : 2, 0, epm, 2, n_lig, pdl));
-            }
+            WresEpilogue ep1{L.b3, nullptr, 0, nullptr, 0, 0, 1, 0, 1};          // hid = SiLU(W3 [h | agg] + b3), K = 512
+            RET_IF((launch_wres<512, 128>(st, e->tm_hcat, L.tm_w3, e->to_hid32, N, 2, 0, 0, ep1, 0, 0, pdl)));
+            WresEpilogue ep2{L.b4, e->h, 256, e->h, 256, 0, 1, 0, 0, e->hcat, 512};   // h += W4 hid + b4 ; bf16 copy -> hcat[:, :256]
+            RET_IF((launch_wres<256, 128>(st, e->tm_hid, L.tm_w4, e->to_hcat32, N, 2, 0, 0, ep2, 0, 0, pdl)));
+        }
+        {
+            ProfScope ps(e, PROF_GEMM, st);
+            WresEpilogue epm{L.bias_m, nullptr, 0, nullptr, 0, 0, 1, 0};
+            // column groups 0-3 over all nodes (0,1 only when a next block exists), groups 4,5 over the ligand rows only
+            RET_IF(launch_wres(st, e->tm_hcat, L.tm_wm, e->to_pq32, N, has_next ? 4 : 2, has_next ? 0 : 2, 0, epm, 2, n_lig, pdl));
         }
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
         {
@@ -864,11 +839,6 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
         case 6: {
             bytes = sizeof(g_wr_trace) < (size_t)dst_bytes ? sizeof(g_wr_trace) : dst_bytes;
             CU_CHECK(cudaMemcpyFromSymbolAsync(dst, g_wr_trace, bytes, 0, cudaMemcpyDeviceToDevice, st));
-            return bytes;
-        }
-        case 7: {
-            bytes = sizeof(g_nf_trace) < (size_t)dst_bytes ? sizeof(g_nf_trace) : dst_bytes;
-            CU_CHECK(cudaMemcpyFromSymbolAsync(dst, g_nf_trace, bytes, 0, cudaMemcpyDeviceToDevice, st));
             return bytes;
         }
         case 5: {
