@@ -154,18 +154,6 @@ DNDM_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
-// TMEM -> registers, 16 lanes x 256 bits, four 8-column groups: thread t holds, for group i, r[4i], r[4i+1] = lane base + t/4,
-// columns 8i + 2 (t%4) + {0, 1} and r[4i+2], r[4i+3] = lane base + t/4 + 8, same columns (the 8 x 8 core-matrix fragment).
-// A warp instruction on these fragments touches 8 rows x 32 contiguous bytes: full sectors for row-major fp32 global data.
-DNDM_DEVICE void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
 DNDM_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Same wait, but ties the destination registers of an earlier (still in-flight) tcgen05.ld to the wait so that the
 // compiler cannot schedule a read of them above it -- needed when other work is placed between the load and the wait.

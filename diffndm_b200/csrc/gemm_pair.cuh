@@ -12,7 +12,9 @@
 // a CTA sees only 2-5 row-block iterations per launch, so the fixed part -- set-up 2 700 cycles, the first TMA round trip
 // 2 500 (up to 9 000 next to the residual epilogue's global traffic), the last drain 3 000 -- is as long as the streaming part.
 // Whole 256-column groups for the node MLP (its input read once instead of twice; (512, 256) and (256, 256) + residual fit a
-// pair) were measured SLOWER (0.447): half as many iterations per pair and a half-row-block ring for K = 512.
+// pair) were measured SLOWER (0.447): half as many iterations per pair and a half-row-block ring for K = 512.  So was a residual
+// epilogue on 16 x 256-bit accumulator fragments (tcgen05.ld.16x256b: 8 rows x 32 contiguous bytes per warp instruction, no
+// transposition tile, two more ring stages): 0.453 -- 128-byte rows through the tile beat 32-byte sectors.
 //
 // Persistent, warp-specialised (1 CTA / SM):
 //   warp 0     TMA producer : half of the W group once; A tiles (128 x 64 bf16, SWIZZLE_128B) into the ring; the completion
