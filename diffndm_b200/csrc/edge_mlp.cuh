@@ -38,6 +38,8 @@ struct EdgeProblem {
     const __nv_bfloat16* P;  // [N, ldpq] : (W1a h + b1)/2 (row / receiver part), bf16
     const __nv_bfloat16* Q;  // [N, ldpq] : (W1b h)/2      (col / sender part), bf16
     const float* w1e;        // [2][256]  : HALF the first-layer weights of (radial_now, radial_input)
+    const void* etab;        // edge-type embedding folded through the first layer (dynamics.py:118-127): HALF of W1[:, 2H+2:] E[type]
+                             // as [3 types][256] bf16 (GCL) / fp32 (HEAD); nullptr without edge types
     float* head_out;         // HEAD: [E] scalar per edge
     float bout;              // GCL: attention bias
     float out_scale;         // GCL: 1/normalization_factor ; HEAD: coords_range
@@ -49,6 +51,7 @@ struct EdgeGraph {
     const float* r0;         // [E] |x_r - x_c|^2 of the INPUT coordinates (egnn_new.py:228)
     const float* x;          // [N,3] current coordinates
     const int* n_edges;      // device scalar: number of edges this launch covers
+    int n_lig;               // nodes [0, n_lig) are ligand atoms (edge types: 0 ligand-pocket, 1 ligand-ligand, 2 pocket-pocket)
     int ldpq;
     __nv_bfloat16* msg;      // GCL: [E,256] ungated messages m_ij (bf16)
     float* att;              // GCL: [E] attention gate / normalization_factor

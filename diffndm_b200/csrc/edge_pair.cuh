@@ -32,7 +32,9 @@ constexpr int EP_MISC_BYTES = EP_SLAB_BYTES + EP_AX_BYTES + EP_BX_BYTES + EK_MET
 constexpr int EP_SMEM_BYTES = EP_WH_BYTES + 2 * EK_A_BYTES + EP_MISC_BYTES;
 static_assert(EP_SMEM_BYTES <= 232448, "pair edge kernel shared memory exceeds 227 KiB");
 
-template <bool kGCL, bool kBf16Radial = true>
+// kEdgeTypes: the first layer also sees a learned embedding of the edge type (moad_fullatom_cond); its contribution is one
+// constant hidden vector per type (EdgeProblem::etab), added to the pre-activation in the producers.
+template <bool kGCL, bool kBf16Radial = true, bool kEdgeTypes = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EP_THREADS, 1)
 edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_msg, const __grid_constant__ EdgeConsts c0, const __grid_constant__ EdgeConsts c1,
@@ -224,8 +226,19 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int2 zw = *(reinterpret_cast<const int2*>(&meta[slot * 8 + r * 2 + jj]) + 1);  // (radial_now, radial_input)
-                const uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
+                uint32_t pw_[4] = {pv[jj].x, pv[jj].y, pv[jj].z, pv[jj].w};
                 const uint32_t qw_[4] = {qv[jj].x, qv[jj].y, qv[jj].z, qv[jj].w};
+                int etype = 0;
+                if (kEdgeTypes) {
+                    const int2 rc = *reinterpret_cast<const int2*>(&meta[slot * 8 + r * 2 + jj]);
+                    const bool rl = rc.x < g.n_lig, cl = rc.y < g.n_lig;
+                    etype = (rl != cl) ? 0 : (rl ? 1 : 2);
+                    if (kGCL) {                      // this lane's 8 channels of the type vector, bf16: folded into P
+                        const uint4 ct = __ldg(reinterpret_cast<const uint4*>(pr.etab) + etype * 32 + lane);
+                        pw_[0] = bf2_add(pw_[0], ct.x); pw_[1] = bf2_add(pw_[1], ct.y);
+                        pw_[2] = bf2_add(pw_[2], ct.z); pw_[3] = bf2_add(pw_[3], ct.w);
+                    }
+                }
                 uint4 o;
                 if (kPacked) {
                     const uint32_t rad2 = (uint32_t)zw.x, r02 = (uint32_t)zw.y;
@@ -257,7 +270,11 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_const
                     for (int i = 0; i < 4; ++i) {
                         const uint64_t p2 = f2_pack(__uint_as_float(pw_[i] << 16), __uint_as_float(pw_[i] & 0xffff0000u));
                         const uint64_t q2 = f2_pack(__uint_as_float(qw_[i] << 16), __uint_as_float(qw_[i] & 0xffff0000u));
-                        const uint64_t pre = f2_fma(w0f[i], r02, f2_fma(wrf[i], rad2, f2_add(p2, q2)));
+                        uint64_t pre = f2_fma(w0f[i], r02, f2_fma(wrf[i], rad2, f2_add(p2, q2)));
+                        if (kEdgeTypes) {
+                            const float2 ct = __ldg(reinterpret_cast<const float2*>(pr.etab) + etype * 128 + lane * 4 + i);
+                            pre = f2_add(pre, f2_pack(ct.x, ct.y));
+                        }
                         float lo, hi;
                         f2_unpack(pre, lo, hi);
                         float m0, m1;

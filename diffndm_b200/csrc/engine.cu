@@ -119,6 +119,8 @@ struct LayerWeights {
     float *bias_e, *b3, *b4, *w1e_e, *w1e_c, *w1e_x;                   // device fp32
     CUtensorMap tm_w2_e, tm_w2_c, tm_w2_x, tm_w3, tm_w4;
     EdgeConsts c_e, c_c, c_x;                                            // host copies (kernel parameters)
+    __nv_bfloat16* et_e = nullptr;                                       // edge-type vectors of the edge model: [3][256] bf16, halved
+    float *et_c = nullptr, *et_x = nullptr;                              // ... of the coordinate heads: [3][256] fp32, halved
     float att_bias;
 };
 
@@ -126,6 +128,7 @@ struct DndmEngine {
     DndmConfig cfg;
     int num_sms = 148;
     bool weights_loaded = false;
+    bool edge_types = false;       // the weight table carries edge-type vectors (dynamics.py:118-127)
     // workspace
     float *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *att = nullptr;
     __nv_bfloat16* msg = nullptr;  // [E,256] bf16 edge messages of the current block
@@ -208,7 +211,7 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     if (cfg->hidden_nf != EK_H) return set_err(DNDM_EINVAL, "hidden_nf=%d unsupported (compiled for %d)", cfg->hidden_nf, EK_H);
     if (cfg->atom_nf < 1 || cfg->atom_nf > 29 || cfg->residue_nf < 1 || cfg->residue_nf > 29)
         return set_err(DNDM_EINVAL, "atom_nf/residue_nf must be in [1,29]");
-    if (2 * cfg->atom_nf > 32 || 2 * cfg->residue_nf > 32) return set_err(DNDM_EINVAL, "encoder hidden width > 32 unsupported");
+    if (2 * cfg->atom_nf > 64 || 2 * cfg->residue_nf > 64) return set_err(DNDM_EINVAL, "encoder hidden width > 64 unsupported");
     if (cfg->max_nodes < 1 || cfg->max_edges < 1 || cfg->max_samples < 1) return set_err(DNDM_EINVAL, "bad capacities");
     CU_CHECK(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
@@ -252,6 +255,9 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(edge_pair_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM_BYTES));
     *out = e;
     return DNDM_OK;
 }
@@ -302,6 +308,7 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
     CU_CHECK(cudaSetDevice(e->cfg.device));
     CU_CHECK(cudaDeviceSynchronize());
     free_weights(e);
+    e->edge_types = false;
     std::map<std::string, HostW> W;
     for (int i = 0; i < n_weights; ++i) W[weights[i].name] = HostW{weights[i].data, weights[i].rows, weights[i].cols};
     auto need = [&](const std::string& k, int rows, int cols, const float** out) -> int {
@@ -427,6 +434,22 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
         RET_IF(upload(e, be, &L.bias_e));
         RET_IF(upload(e, edge_cols(e0w), &L.w1e_e)); RET_IF(upload(e, edge_cols(c0w), &L.w1e_c));
         RET_IF(upload(e, edge_cols(x0w), &L.w1e_x));
+        {   // optional: <mlp>.0.edge_type_bias [3, H] = W1[:, 2H+2:] E[type] (folded by the host binding); all three or none
+            auto tb = [&](const char* m) -> const float* {
+                auto it = W.find(p + m + ".0.edge_type_bias");
+                return (it != W.end() && it->second.rows == 3 && it->second.cols == H) ? it->second.d : nullptr;
+            };
+            const float *te = tb("gcl_0.edge_mlp"), *tc = tb("gcl_equiv.coord_mlp"), *tx = tb("gcl_equiv.cross_product_mlp");
+            if ((te != nullptr) != (tc != nullptr) || (te != nullptr) != (tx != nullptr) || (l > 0 && (te != nullptr) != e->edge_types))
+                return set_err(DNDM_EWEIGHTS, "edge_type_bias must be given for every edge MLP of every block or for none");
+            e->edge_types = te != nullptr;
+            if (te) {
+                std::vector<__nv_bfloat16> be(3 * H);
+                std::vector<float> bc(3 * H), bx(3 * H);
+                for (int i = 0; i < 3 * H; ++i) { be[i] = f2bf(0.5f * te[i]); bc[i] = 0.5f * tc[i]; bx[i] = 0.5f * tx[i]; }
+                RET_IF(upload(e, be, &L.et_e)); RET_IF(upload(e, bc, &L.et_c)); RET_IF(upload(e, bx, &L.et_x));
+            }
+        }
         auto to_bf_half = [&](const float* w, size_t n) {       // edge-MLP second layers: the kernel evaluates SiLU on x/2
             std::vector<__nv_bfloat16> v(n);
             for (size_t i = 0; i < n; ++i) v[i] = f2bf(0.5f * w[i]);
@@ -632,9 +655,14 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         ProfScope ps(e, PROF_NODE, st);
         const int lig_ctas = (n_lig + ENC_NODES_PER_CTA - 1) / ENC_NODES_PER_CTA;
         const int pok_ctas = (n_pocket + ENC_NODES_PER_CTA - 1) / ENC_NODES_PER_CTA;
-        encode_embed_kernel<<<lig_ctas + pok_ctas, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len,
-                                                                 e->node_sample, e->enc_l, e->enc_p, lig_ctas, e->x0, e->xa,
-                                                                 e->xb, e->h, e->hcat);
+        if (2 * A <= 32 && 2 * R <= 32)
+            encode_embed_kernel<32><<<lig_ctas + pok_ctas, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len,
+                                                                         e->node_sample, e->enc_l, e->enc_p, lig_ctas, e->x0, e->xa,
+                                                                         e->xb, e->h, e->hcat);
+        else    // C-alpha pockets: 20 residue types, encoder hidden width 40
+            encode_embed_kernel<64><<<lig_ctas + pok_ctas, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len,
+                                                                         e->node_sample, e->enc_l, e->enc_p, lig_ctas, e->x0, e->xa,
+                                                                         e->xb, e->h, e->hcat);
         COUNT_LAUNCH(1);
     }
     float* x_cur = e->xa;
@@ -652,14 +680,15 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         if (pruned && fork) CU_CHECK(cudaStreamWaitEvent(st, e->ev_join_last, 0));
         // ---- GCL edge model + attention + deterministic aggregation ----
         EdgeGraph g{pruned ? e->erow_c : e->erow, pruned ? e->ecol_c : e->ecol, pruned ? e->r0_c : e->r0, x_cur,
-                    e->scalars + (pruned ? 2 : 0), 1536, e->msg, e->att};
-        EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, nullptr, L.att_bias, inv_norm};
+                    e->scalars + (pruned ? 2 : 0), n_lig, 1536, e->msg, e->att};
+        EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, L.et_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
             // PDL: preceded by the merged projection GEMM (block 0) / coord_update (later blocks) on this stream
-            CU_CHECK(launch_pdl(pdl, g_bf16_radial ? edge_pair_kernel<true, true> : edge_pair_kernel<true, false>,
-                                dim3(e->num_sms & ~1, 1), dim3(EP_THREADS), EP_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg, L.c_e,
-                                L.c_e, g, pe, pe));
+            auto gcl = e->edge_types ? (g_bf16_radial ? edge_pair_kernel<true, true, true> : edge_pair_kernel<true, false, true>)
+                                     : (g_bf16_radial ? edge_pair_kernel<true, true> : edge_pair_kernel<true, false>);
+            CU_CHECK(launch_pdl(pdl, gcl, dim3(e->num_sms & ~1, 1), dim3(EP_THREADS), EP_SMEM_BYTES, st, L.tm_w2_e, L.tm_w2_e, e->to_msg,
+                                L.c_e, L.c_e, g, pe, pe));
         }
         {
             ProfScope ps(e, PROF_NODE, st);
@@ -684,15 +713,16 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         }
         // ---- EquivariantUpdate: two scalar heads on the ligand-receiver edges, then the coordinate update ----
         {
-            EdgeGraph gh{e->erow, e->ecol, e->r0, x_cur, e->scalars + 1, 1536, nullptr, nullptr};
-            EdgeProblem pc{e->pq + 1024, e->pq + 512, L.w1e_c, e->phi, 0.f, e->cfg.coords_range};
-            EdgeProblem px{e->pq + 1280, e->pq + 768, L.w1e_x, e->psi, 0.f, e->cfg.coords_range};
+            EdgeGraph gh{e->erow, e->ecol, e->r0, x_cur, e->scalars + 1, n_lig, 1536, nullptr, nullptr};
+            EdgeProblem pc{e->pq + 1024, e->pq + 512, L.w1e_c, L.et_c, e->phi, 0.f, e->cfg.coords_range};
+            EdgeProblem px{e->pq + 1280, e->pq + 768, L.w1e_x, L.et_x, e->psi, 0.f, e->cfg.coords_range};
             const int gx = e->num_sms / 2 > 0 ? e->num_sms / 2 : 1;
             {
                 ProfScope ps(e, PROF_HEAD, st);
                 // CTA pairs: an even number of CTAs per problem
-                CU_CHECK(launch_pdl(pdl, edge_pair_kernel<false>, dim3(gx > 1 ? gx & ~1 : 2, 2), dim3(EP_THREADS), EP_SMEM_BYTES, st,
-                                    L.tm_w2_c, L.tm_w2_x, e->to_msg, L.c_c, L.c_x, gh, pc, px));
+                CU_CHECK(launch_pdl(pdl, e->edge_types ? edge_pair_kernel<false, true, true> : edge_pair_kernel<false>,
+                                    dim3(gx > 1 ? gx & ~1 : 2, 2), dim3(EP_THREADS), EP_SMEM_BYTES, st, L.tm_w2_c, L.tm_w2_x, e->to_msg,
+                                    L.c_c, L.c_x, gh, pc, px));
             }
             ProfScope ps2(e, PROF_NODE, st);
             coord_update_kernel<<<(n_lig * 32 + 255) / 256, 256, 0, st>>>(x_cur, x_next, e->row_ptr, e->ecol, e->phi, e->psi,
@@ -768,11 +798,10 @@ extern "C" int dndm_sampler_step(DndmEngine* e, const float* z_in, const float* 
                                  const int64_t* lig_mask, const int64_t* pocket_mask, int32_t n_lig, int32_t n_pocket,
                                  int32_t n_samples, float* z_out, float* xh_pocket_out, int32_t check_input_com, void* stream) {
     if (!e || !z_in || !noise || !coef || !lig_mask || !z_out) return set_err(DNDM_EINVAL, "null argument");
-    if (e->cfg.atom_nf != e->cfg.residue_nf) return set_err(DNDM_EINVAL, "sampler step requires atom_nf == residue_nf");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     RET_IF(prepare_batch(e, lig_mask, pocket_mask, n_lig, n_pocket, n_samples, st));
     sampler_step_kernel<<<n_samples, 128, 0, st>>>(z_in, eps ? eps : noise, noise, xh_pocket_in, coef, grad, lambda, e->lig_ptr,
-                                                   e->pok_ptr, e->cfg.atom_nf, z_out, xh_pocket_out, e->flags, check_input_com != 0);
+                                                   e->pok_ptr, e->cfg.atom_nf, e->cfg.residue_nf, z_out, xh_pocket_out, e->flags, check_input_com != 0);
     COUNT_LAUNCH(1);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;

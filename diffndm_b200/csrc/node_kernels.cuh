@@ -26,9 +26,11 @@ struct EncoderWeights {
 // activations are warp-broadcast 128-bit shared loads, the stores are fully coalesced (fp32 h and the bf16 copy).
 // CTAs [0, lig_ctas) take ligand atoms, the rest pocket atoms (different encoder weights).
 constexpr int ENC_NODES_PER_CTA = 64;
-constexpr int ENC_MAX_HID = 32;
 constexpr int ENC_MAX_NF = 32;
 
+// kMaxHid: compile-time bound of the encoders' hidden width 2 * nf (32 for the full-atom vocabularies, 64 for the 20 amino
+// acids of C-alpha pockets)
+template <int ENC_MAX_HID>
 __global__ void __launch_bounds__(256)
 encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ xh_pok, int n_lig, int n_nodes,
                     int ld_lig, int ld_pok, const float* __restrict__ t, int t_len, const int* __restrict__ node_sample,
@@ -208,7 +210,7 @@ decode_kernel(const float* __restrict__ h, const float* __restrict__ x_final, co
         const float4 b = *reinterpret_cast<const float4*>(h + (size_t)node * 256 + 128 + 4 * lane);
         hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
     }
-    float s = 0.f;     // lane j keeps hidden unit j
+    float s = 0.f, s_hi = 0.f;     // lane j keeps hidden units j and 32 + j (hid <= 64)
 #pragma unroll 4
     for (int j = 0; j < w.hid; ++j) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(w.wc + (size_t)j * 256 + 4 * lane));
@@ -217,12 +219,15 @@ decode_kernel(const float* __restrict__ h, const float* __restrict__ x_final, co
                   b.w * hv[7];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (lane == j) s = silu_f(d + w.bc[j]);
+        if (lane == (j & 31)) {
+            const float a = silu_f(d + w.bc[j]);
+            if (j < 32) s = a; else s_hi = a;
+        }
     }
     float* dst = is_lig ? out_lig + (size_t)node * (3 + w.nf) : out_pok + (size_t)(node - n_lig) * (3 + w.nf);
     float o = 0.f;
     for (int j = 0; j < w.hid; ++j) {
-        const float sj = __shfl_sync(0xffffffffu, s, j);
+        const float sj = __shfl_sync(0xffffffffu, j < 32 ? s : s_hi, j & 31);
         if (lane < w.nf) o = fmaf(w.w2[lane * w.hid + j], sj, o);
     }
     if (lane < w.nf) dst[3 + lane] = o + w.b2[lane];
@@ -250,11 +255,11 @@ decode_kernel(const float* __restrict__ h, const float* __restrict__ x_final, co
 __global__ void __launch_bounds__(128)
 sampler_step_kernel(const float* z_t, const float* eps, const float* noise, const float* xh_pok_in,
                     const float* __restrict__ coef /*[B][3]*/, const float* grad /*[N_l][3] or null*/, float lambda,
-                    const int* __restrict__ lig_ptr, const int* __restrict__ pok_ptr, int nf, float* z_out,
+                    const int* __restrict__ lig_ptr, const int* __restrict__ pok_ptr, int nf, int nf_pok, float* z_out,
                     float* xh_pok_out, unsigned* flags, int check_input_com) {   // z_out / xh_pok_out may alias the inputs (in place)
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    const int D = 3 + nf;
+    const int D = 3 + nf, Dp = 3 + nf_pok;      // row widths: ligand 3 + atom_nf, pocket 3 + residue_nf (20 for C-alpha pockets)
     const int l0 = lig_ptr[b], l1 = lig_ptr[b + 1];
     const float cz = coef[3 * b], ce = coef[3 * b + 1], cn = coef[3 * b + 2];
     __shared__ float red[4][8];
@@ -307,12 +312,12 @@ sampler_step_kernel(const float* z_t, const float* eps, const float* noise, cons
     }
     const int p0 = pok_ptr[b], p1 = pok_ptr[b + 1];
     for (int i = p0 + tid; i < p1; i += blockDim.x) {
-        const size_t o = (size_t)i * D;
+        const size_t o = (size_t)i * Dp;
         xh_pok_out[o] = xh_pok_in[o] - c0;
         xh_pok_out[o + 1] = xh_pok_in[o + 1] - c1;
         xh_pok_out[o + 2] = xh_pok_in[o + 2] - c2;
         if (xh_pok_out != xh_pok_in)
-            for (int d = 3; d < D; ++d) xh_pok_out[o + d] = xh_pok_in[o + d];
+            for (int d = 3; d < Dp; ++d) xh_pok_out[o + d] = xh_pok_in[o + d];
     }
 }
 

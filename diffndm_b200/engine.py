@@ -17,7 +17,7 @@ from typing import Dict, Mapping, Optional
 import numpy as np
 import torch
 
-from .weights import DynamicsConfig, expected_keys
+from .weights import COMPILED_HIDDEN_NF, DynamicsConfig, engine_table, expected_keys
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libdiffndm_b200.so')
 
@@ -117,11 +117,15 @@ class Engine:
         self.cfg = cfg
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.max_nodes, self.max_edges, self.max_samples = int(max_nodes), int(max_edges), int(max_samples)
-        if cfg.edge_embedding_dim or cfg.update_pocket_coords or not cfg.condition_time or cfg.reflection_equivariant \
+        if cfg.update_pocket_coords or not cfg.condition_time or cfg.reflection_equivariant \
                 or not cfg.attention or not cfg.tanh or cfg.inv_sublayers != 1:
-            raise NotImplementedError('engine implements the fullatom_cond denoiser: attention, tanh, cross-product '
-                                      'MLP, time conditioning, frozen pocket, no edge-type embedding')
-        c = DndmConfig(cfg.atom_nf, cfg.residue_nf, cfg.joint_nf, cfg.hidden_nf, cfg.n_layers,
+            raise NotImplementedError('engine implements the pocket-conditional denoisers: attention, tanh, cross-product '
+                                      'MLP, time conditioning, frozen pocket')
+        if cfg.hidden_nf > COMPILED_HIDDEN_NF:
+            raise NotImplementedError(f'hidden_nf = {cfg.hidden_nf}: the kernels are compiled for {COMPILED_HIDDEN_NF} hidden '
+                                      'channels; narrower networks are zero-padded (weights.engine_table), wider ones are not built')
+        # the device engine always runs at the compiled width; edge-type embeddings arrive folded (weights.engine_table)
+        c = DndmConfig(cfg.atom_nf, cfg.residue_nf, cfg.joint_nf, COMPILED_HIDDEN_NF, cfg.n_layers,
                        -1.0 if cfg.edge_cutoff_ligand is None else cfg.edge_cutoff_ligand,
                        -1.0 if cfg.edge_cutoff_pocket is None else cfg.edge_cutoff_pocket,
                        -1.0 if cfg.edge_cutoff_interaction is None else cfg.edge_cutoff_interaction,
@@ -147,10 +151,12 @@ class Engine:
     weights_version = 0          # bumped by load_weights: captured CUDA graphs hold pointers into the packed weights
 
     def load_weights(self, state: Mapping[str, object]):
+        """``state``: reference ``EGNNDynamics.state_dict()`` (tensors) or a dict of numpy arrays, in the shapes of
+        ``self.cfg`` (any hidden_nf <= 256, with or without the edge-type embedding); the device engine receives the
+        table ``weights.engine_table`` derives from it (zero-padded to the compiled width, embedding folded)."""
         self.weights_version += 1
-        """``state``: reference ``EGNNDynamics.state_dict()`` (tensors) or a dict of numpy arrays."""
-        keep, arr = [], (DndmWeight * len(expected_keys(self.cfg)))()
-        for i, (name, shape) in enumerate(expected_keys(self.cfg)):
+        host = {}
+        for name, shape in expected_keys(self.cfg):
             if name not in state:
                 raise KeyError(f'missing weight {name}')
             v = state[name]
@@ -158,8 +164,13 @@ class Engine:
             a = np.ascontiguousarray(a, dtype=np.float32)
             if tuple(a.shape) != tuple(shape):
                 raise ValueError(f'{name}: shape {a.shape} != expected {shape}')
+            host[name] = a
+        _, table = engine_table(self.cfg, host)
+        keep, arr = [], (DndmWeight * len(table))()
+        for i, (name, a) in enumerate(table.items()):
+            a = np.ascontiguousarray(a, dtype=np.float32)
             keep.append(a)
-            rows, cols = (shape[0], shape[1]) if len(shape) == 2 else (shape[0], 1)
+            rows, cols = (a.shape[0], a.shape[1]) if a.ndim == 2 else (a.shape[0], 1)
             arr[i] = DndmWeight(name.encode(), a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), rows, cols)
         _check(self.lib, self.lib.dndm_engine_load_weights(self._h, arr, len(keep)), 'dndm_engine_load_weights')
 
@@ -207,6 +218,9 @@ class Engine:
         grad = None if grad is None else _dev_f32(grad, 'grad')
         lig_mask = lig_mask.contiguous().long()
         pocket_mask = pocket_mask.contiguous().long()
+        if z_in.shape[1] != 3 + self.cfg.atom_nf or xh_pocket.shape[1] != 3 + self.cfg.residue_nf:
+            raise ValueError(f'sampler_step: rows must be [3 + {self.cfg.atom_nf}] (ligand) and [3 + {self.cfg.residue_nf}] (pocket) wide, '
+                             f'got {z_in.shape[1]} and {xh_pocket.shape[1]}')
         if z_out is None:
             z_out = torch.empty_like(z_in)
         if pocket_out is None:

@@ -163,6 +163,7 @@ class ConditionalSampler:
         self.T = timesteps
         self.n_dims = 3
         self.atom_nf = dynamics.cfg.atom_nf
+        self.residue_nf = dynamics.cfg.residue_nf      # 20 for C-alpha pockets (amino-acid one-hot), else = atom_nf
         self.norm_values = norm_values
         self.norm_biases = norm_biases
         self.check_every_step = check_every_step
@@ -284,7 +285,7 @@ class ConditionalSampler:
         B = int(n_samples)
         z = torch.zeros((x_lig.shape[0], 3 + self.atom_nf), device=self.device)
         z[:, :3] = x_lig
-        p = torch.zeros((x_pocket.shape[0], 3 + self.atom_nf), device=self.device)
+        p = torch.zeros((x_pocket.shape[0], 3 + self.residue_nf), device=self.device)
         p[:, :3] = x_pocket
         coef = self._const_rows((1.0, 0.0, 0.0), B)
         zo, po = self.engine.sampler_step(z, None, z, p, coef, lig_mask, pocket_mask, B)

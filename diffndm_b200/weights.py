@@ -46,8 +46,12 @@ class DynamicsConfig:
         return asdict(self)
 
 
+COMPILED_HIDDEN_NF = 256          # the width the CUDA kernels are written for (tile shapes, TMEM columns)
+N_EDGE_TYPES = 3                  # dynamics.py:118-124: 0 ligand-pocket, 1 ligand-ligand, 2 pocket-pocket
+
+
 def expected_keys(cfg: DynamicsConfig):
-    """(name, shape) of every parameter the engine consumes."""
+    """(name, shape) of every parameter the engine consumes (reference ``state_dict`` names)."""
     A, R, J, H = cfg.atom_nf, cfg.residue_nf, cfg.joint_nf, cfg.hidden_nf
     de = 2 + (cfg.edge_embedding_dim or 0)
     D = J + 1
@@ -78,7 +82,88 @@ def expected_keys(cfg: DynamicsConfig):
         # checkpoint carries both keys -- they are packed separately.
         out.append((p + 'coord_mlp.4.weight', (1, H)))
         out.append((p + 'cross_product_mlp.4.weight', (1, H)))
+    if cfg.edge_embedding_dim:
+        out.append(('edge_embedding.weight', (N_EDGE_TYPES, cfg.edge_embedding_dim)))      # dynamics.py:52-55 (nn.Embedding)
     return out
+
+
+EDGE_MLPS = ('gcl_0.edge_mlp', 'gcl_equiv.coord_mlp', 'gcl_equiv.cross_product_mlp')
+
+
+def engine_table(cfg: DynamicsConfig, state: Dict[str, np.ndarray]):
+    """The weight table the CUDA engine is loaded with, derived from a reference ``state_dict`` of ANY conditional
+    configuration with hidden_nf <= 256.  Two exact rewrites (fp64 where arithmetic is involved):
+
+    * **edge-type embedding** (``edge_embedding_dim``; dynamics.py:118-127, moad_fullatom_cond): the first Linear of every
+      edge MLP sees ``[h_i, h_j, radial (2), embedding(type)]``; the embedding part contributes one constant hidden vector
+      per edge type, ``W1[:, 2H+2:] @ E[type]``.  The table carries those three vectors per MLP
+      (``<mlp>.0.edge_type_bias`` [3, H]) and first-layer weights without the embedding columns; the edge kernel adds the
+      vector of the edge's type in its producers.
+    * **hidden width**: the kernels are compiled for 256 hidden channels.  A narrower network (moad: 192, *_ca_cond /
+      joint: 128) is embedded by zero-padding: every padded unit has zero weights and bias on both sides, SiLU(0) = 0 and
+      the residual stream keeps them at exactly 0, so the padded network computes the same function (the extra lanes cost
+      (256 / H)^2 of the dense work -- the price of not compiling a second set of tile shapes).
+
+    Returns (engine_cfg, table): ``engine_cfg`` is ``cfg`` with hidden_nf = 256 and edge_embedding_dim = None."""
+    H, Hc = cfg.hidden_nf, COMPILED_HIDDEN_NF
+    if H > Hc:
+        raise NotImplementedError(f'hidden_nf = {H} exceeds the compiled width {Hc}')
+    W = {k: np.asarray(v, np.float32) for k, v in state.items()}
+    out: Dict[str, np.ndarray] = {}
+    de_emb = cfg.edge_embedding_dim or 0
+    emb = np.asarray(W['edge_embedding.weight'], np.float64) if de_emb else None
+
+    def pad(a, rows=None, cols=None):
+        a = np.asarray(a, np.float32)
+        r = a.shape[0] if rows is None else rows
+        if a.ndim == 1:
+            o = np.zeros((r,), np.float32)
+            o[:a.shape[0]] = a
+            return o
+        c = a.shape[1] if cols is None else cols
+        o = np.zeros((r, c), np.float32)
+        o[:a.shape[0], :a.shape[1]] = a
+        return o
+
+    def cat_inputs(w):                      # [out, H | H (| extra)] -> [out_pad, Hc | Hc (| extra)]
+        extra = w.shape[1] - 2 * H
+        o = np.zeros((Hc, 2 * Hc + extra), np.float32)
+        o[:w.shape[0], :H] = w[:, :H]
+        o[:w.shape[0], Hc:Hc + H] = w[:, H:2 * H]
+        if extra:
+            o[:w.shape[0], 2 * Hc:] = w[:, 2 * H:]
+        return o
+
+    for k in ('atom_encoder', 'atom_decoder', 'residue_encoder', 'residue_decoder'):
+        for l in ('0', '2'):
+            for t in ('weight', 'bias'):
+                out[f'{k}.{l}.{t}'] = W[f'{k}.{l}.{t}']
+    out['egnn.embedding.weight'] = pad(W['egnn.embedding.weight'], rows=Hc)
+    out['egnn.embedding.bias'] = pad(W['egnn.embedding.bias'], rows=Hc)
+    out['egnn.embedding_out.weight'] = pad(W['egnn.embedding_out.weight'], cols=Hc)
+    out['egnn.embedding_out.bias'] = W['egnn.embedding_out.bias']
+    for i in range(cfg.n_layers):
+        p = f'egnn.e_block_{i}.'
+        for m in EDGE_MLPS:
+            w1 = W[p + m + '.0.weight']
+            if de_emb:
+                tb = (np.asarray(w1[:, 2 * H + 2:], np.float64) @ emb.T).T            # [3, H]
+                out[p + m + '.0.edge_type_bias'] = pad(tb.astype(np.float32), cols=Hc)
+                w1 = w1[:, :2 * H + 2]
+            out[p + m + '.0.weight'] = cat_inputs(w1)
+            out[p + m + '.0.bias'] = pad(W[p + m + '.0.bias'], rows=Hc)
+            out[p + m + '.2.weight'] = pad(W[p + m + '.2.weight'], rows=Hc, cols=Hc)
+            out[p + m + '.2.bias'] = pad(W[p + m + '.2.bias'], rows=Hc)
+        out[p + 'gcl_0.node_mlp.0.weight'] = cat_inputs(W[p + 'gcl_0.node_mlp.0.weight'])
+        out[p + 'gcl_0.node_mlp.0.bias'] = pad(W[p + 'gcl_0.node_mlp.0.bias'], rows=Hc)
+        out[p + 'gcl_0.node_mlp.2.weight'] = pad(W[p + 'gcl_0.node_mlp.2.weight'], rows=Hc, cols=Hc)
+        out[p + 'gcl_0.node_mlp.2.bias'] = pad(W[p + 'gcl_0.node_mlp.2.bias'], rows=Hc)
+        out[p + 'gcl_0.att_mlp.0.weight'] = pad(W[p + 'gcl_0.att_mlp.0.weight'], cols=Hc)
+        out[p + 'gcl_0.att_mlp.0.bias'] = W[p + 'gcl_0.att_mlp.0.bias']
+        out[p + 'gcl_equiv.coord_mlp.4.weight'] = pad(W[p + 'gcl_equiv.coord_mlp.4.weight'], cols=Hc)
+        out[p + 'gcl_equiv.cross_product_mlp.4.weight'] = pad(W[p + 'gcl_equiv.cross_product_mlp.4.weight'], cols=Hc)
+    from dataclasses import replace
+    return replace(cfg, hidden_nf=Hc, edge_embedding_dim=None), out
 
 
 def random_init(cfg: DynamicsConfig = DynamicsConfig(), seed: int = 0, coord_head_gain: float = 0.3,

@@ -75,7 +75,14 @@ void dndm_engine_destroy(DndmEngine* e);
 
 /* Replaces nn.Module.load_state_dict for `ddpm.dynamics.*`: packs private bf16 / fp32 device copies
  * (first-layer edge weights split per endpoint, encoder/decoder linears pre-composed).  Must be called again
- * whenever the caller's parameters change. */
+ * whenever the caller's parameters change.
+ * The table is in the shapes of DndmConfig (hidden_nf must be 256, the compiled width; first-layer edge weights
+ * [256, 2 * 256 + 2]).  A narrower reference network (hidden_nf 192 / 128) is loaded zero-padded, and the edge-type
+ * embedding of dynamics.py:118-127 folded into three optional entries per block,
+ *   "egnn.e_block_<i>.{gcl_0.edge_mlp, gcl_equiv.coord_mlp, gcl_equiv.cross_product_mlp}.0.edge_type_bias"  [3, 256]
+ *   = W1[:, 2H+2:] E[type]  (type 0 ligand-pocket, 1 ligand-ligand, 2 pocket-pocket),
+ * given for every edge MLP of every block or for none; both rewrites are exact and are what the Python binding
+ * (diffndm_b200/weights.py: engine_table) does with the reference's state_dict. */
 int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights, int32_t n_weights);
 
 /* EGNNDynamics.forward (dynamics.py:87-167), update_pocket_coords = False, condition_time = True.

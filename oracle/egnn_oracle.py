@@ -204,8 +204,8 @@ def equiv_forward(W, p, h, x, row, col, coord_diff, coord_cross, edge_attr, upda
 # ----------------------------------------------------------------------------
 def dynamics_forward(W: Dict[str, np.ndarray], xh_atoms, xh_residues, t, mask_atoms, mask_residues,
                      cfg: OracleConfig, dtype=np.float32, edges=None, trace: Optional[dict] = None):
-    """EGNNDynamics.forward (mode='egnn_dynamics', condition_time, update_pocket_coords=False,
-    edge_embedding_dim=None) -- dynamics.py:87-167.
+    """EGNNDynamics.forward (mode='egnn_dynamics', condition_time, update_pocket_coords=False; with the edge-type
+    embedding when the table carries ``edge_embedding.weight``) -- dynamics.py:87-167.
 
     ``W`` uses the reference state_dict key names.  ``dtype=np.float64``
     gives the "truth" run used to set tolerances.  ``edges`` may be injected (int64 [2,E]).
@@ -251,6 +251,10 @@ def dynamics_forward(W: Dict[str, np.ndarray], xh_atoms, xh_residues, t, mask_at
 
     # EGNN.forward, egnn_new.py:225-244
     r0, _ = coord2diff(x, row, col, 1)                                      # :228 (default norm_constant)
+    if 'edge_embedding.weight' in W:                                        # dynamics.py:118-127 (edge_embedding_dim, moad configs)
+        # 0: ligand-pocket, 1: ligand-ligand, 2: pocket-pocket; the learned embedding rides behind r0 (egnn_new.py:230-231)
+        etype = np.where((row < n_l) & (col < n_l), 1, np.where((row >= n_l) & (col >= n_l), 2, 0))
+        r0 = np.concatenate([r0, W['edge_embedding.weight'][etype]], axis=1)
     h = linear(h, W['egnn.embedding.weight'], W['egnn.embedding.bias'])     # :233
     x_cur = x
     if trace is not None:

@@ -83,7 +83,7 @@ def build_reference_model(cfg, weights, dtype=torch.float32, timesteps=500, unti
             normalization_factor=cfg.normalization_factor, aggregation_method='sum',
             edge_cutoff_ligand=cfg.edge_cutoff_ligand, edge_cutoff_pocket=cfg.edge_cutoff_pocket,
             edge_cutoff_interaction=cfg.edge_cutoff_interaction, update_pocket_coords=False,
-            reflection_equivariant=False, edge_embedding_dim=None)
+            reflection_equivariant=False, edge_embedding_dim=cfg.edge_embedding_dim)
         if untie_heads:
             for i in range(cfg.n_layers):
                 eq = dyn.egnn._modules[f'e_block_{i}']._modules['gcl_equiv']
