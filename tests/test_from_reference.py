@@ -67,6 +67,26 @@ def test_from_reference_on_the_real_reference_module(golden_weights, monkeypatch
     assert int(ddpm.T) == 500 and list(ddpm.norm_values) == [1, 4]
 
 
+@pytest.mark.skipif(not reference_available(), reason='/root/reference is only present in the build container')
+@pytest.mark.parametrize('name', ['moad192', 'narrow128', 'ca20'])
+def test_from_reference_recovers_the_other_configurations(name, monkeypatch):
+    """hidden_nf 192 + edge-type embedding + 4 / 7 A cutoffs (moad_fullatom_cond), 128 / joint 32 / five blocks, residue_nf 20:
+    every hyper-parameter is read back from the live reference module, the state dict (``edge_embedding.weight`` included)
+    is handed to the engine unchanged, and ``engine_table`` accepts it."""
+    from ref_loader import build_reference_model
+    from make_golden_widen import case_config
+    from diffndm_b200.weights import engine_table, expected_keys, random_init
+    cfg = case_config(name)
+    W = random_init(cfg, 7, 0.3)
+    dyn, _ = build_reference_model(cfg, W)
+    got_cfg, state = _from_reference_cpu(dyn, monkeypatch)
+    assert got_cfg == cfg
+    for key, shape in expected_keys(cfg):
+        assert tuple(state[key].shape) == tuple(shape) and np.array_equal(state[key], W[key]), key
+    ecfg, tab = engine_table(got_cfg, state)
+    assert ecfg.hidden_nf == 256 and (('egnn.e_block_0.gcl_0.edge_mlp.0.edge_type_bias' in tab) == bool(cfg.edge_embedding_dim))
+
+
 # ------------------------------------------------------------------------------------------------------------------------
 # GPU
 # ------------------------------------------------------------------------------------------------------------------------
