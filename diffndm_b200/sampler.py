@@ -113,11 +113,14 @@ class _GraphedReverseStep:
         self.lig_mask, self.pocket_mask = lig_mask, pocket_mask   # the graph reads these buffers on every replay
         self.t_buf = torch.zeros((B, 1), device=dev)
         self.coef_buf = torch.zeros((B, 3), device=dev)
+        # the captured kernels read the transform's tensors on every replay: the graph is valid for THIS transform object only
+        # (part of the cache key) and keeps it alive
+        self.transform = transform = sampler.eps_transform
 
         def body():
             eps, _ = eng.forward(self.z, self.xp, self.t_buf, lig_mask, pocket_mask, B, want_pocket=False)
-            if sampler.eps_transform is not None:
-                eps = sampler.eps_transform(eps, self.z, self.xp, self.t_buf, lig_mask, pocket_mask)
+            if transform is not None:
+                eps = transform(eps, self.z, self.xp, self.t_buf, lig_mask, pocket_mask)
             nz = torch.randn_like(self.z)
             eng.sampler_step(self.z, eps, nz, self.xp, self.coef_buf, lig_mask, pocket_mask, B, z_out=self.z,
                              pocket_out=self.xp, check_com=True)
@@ -133,9 +136,19 @@ class _GraphedReverseStep:
         # the body launches the two mask kernels inside the graph): a replay does not depend on what other calls left in
         # the engine's scratch buffers
         eng.set_static_masks(True)
+        # Capture through capture_begin / capture_end on the side stream instead of the `torch.cuda.graph` context manager: its
+        # __enter__ runs gc.collect() + torch.cuda.empty_cache(), and a job captures one graph per pocket shape while older
+        # graphs are evicted -- the cudaFree of their pools made a capture take 0.2 - 1.9 s now and then (10 ms otherwise).
+        # All graphs of a sampler share one private pool (they never replay concurrently and keep nothing in it between
+        # replays: the state buffers live outside), so an evicted graph's memory is reused, not returned to the driver.
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            body()
+        with torch.cuda.stream(side):
+            self.graph.capture_begin(pool=sampler.graph_pool)
+            try:
+                body()
+            finally:
+                self.graph.capture_end()
+        torch.cuda.current_stream().wait_stream(side)
         self.z.copy_(keep_z)
         self.xp.copy_(keep_p)
         torch.cuda.synchronize(dev)
@@ -168,7 +181,8 @@ class ConditionalSampler:
         self.norm_biases = norm_biases
         self.check_every_step = check_every_step
         self.overlap_scoring = True                # SPSA: score one half of a round on the host while the GPU denoises the other
-        self._graph_cache = {}                     # (weights version, B, N_l, N_p) -> _GraphedReverseStep
+        self._graph_cache = {}                     # (weights version, B, N_l, N_p, transform) -> _GraphedReverseStep
+        self.graph_pool = torch.cuda.graph_pool_handle()   # one private memory pool for every captured reverse step
         # optional device-side hook applied to every denoiser output: eps = f(eps, z, xh_pocket, t [B,1] on the device,
         # lig_mask, pocket_mask).  Capture-safe callables only (it runs inside the graphed reverse step as well).  Used by
         # the benchmarks for the synthetic score that stands in for trained weights (synthetic.PointMassScore).
@@ -466,10 +480,10 @@ class ConditionalSampler:
                     if gstep is None:
                         # graphs are kept across trajectories: the same pocket with the same ligand sizes (the usual
                         # "n_samples per pocket" loop) replays the graph captured for the first batch
-                        key = (self.engine.weights_version, B, int(z_lig.shape[0]), int(xh_pocket.shape[0]))
+                        key = (self.engine.weights_version, B, int(z_lig.shape[0]), int(xh_pocket.shape[0]), id(self.eps_transform))
                         gstep = self._graph_cache.get(key)
-                        if gstep is not None and torch.equal(gstep.lig_mask, lig_mask) and \
-                                torch.equal(gstep.pocket_mask, pocket_mask):
+                        if gstep is not None and gstep.transform is self.eps_transform and torch.equal(gstep.lig_mask, lig_mask) \
+                                and torch.equal(gstep.pocket_mask, pocket_mask):
                             gstep.z.copy_(z_lig)
                             gstep.xp.copy_(xh_pocket)
                         else:
