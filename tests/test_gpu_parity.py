@@ -744,6 +744,33 @@ def test_forward_high_degree_receivers_vs_oracle(dyn, dev, golden_weights):
     assert torch.equal(out_l, out2)                           # deterministic
 
 
+@pytest.mark.parametrize('n_lig,n_pok', [(1, 1), (11, 1), (16, 1), (23, 2), (16, 0)])
+def test_forward_tile_edge_cases_vs_oracle(dyn, dev, golden_weights, n_lig, n_pok):
+    """Edge counts around the 128-edge tile / 256-edge pair-iteration boundaries of the CTA-pair kernels: one sample whose
+    ligand is fully connected (n^2 edges incl. self loops) next to a far-away pocket of n_pok atoms -- E = 2 (one tile of a
+    single pair, its peer CTA all padding), 122 (< one tile), 257 (three tiles: the last pair iteration has ONE valid tile),
+    533 (five tiles), 256 with no pocket at all (exactly one pair iteration) -- against the fp64 oracle."""
+    rng = np.random.default_rng(100 + n_lig)
+    xl = rng.normal(size=(n_lig, 3)).astype(np.float32) * 2.0
+    hl = np.eye(10, dtype=np.float32)[rng.integers(0, 10, n_lig)] * 0.25
+    xh_lig = np.concatenate([xl, hl], 1)
+    xp = (rng.normal(size=(n_pok, 3)) + np.array([40.0, 0, 0])).astype(np.float32)      # beyond every cutoff from the ligand
+    hp = np.eye(10, dtype=np.float32)[rng.integers(0, 10, n_pok)] * 0.25
+    xh_pok = np.concatenate([xp, hp], 1).astype(np.float32).reshape(n_pok, 13)
+    lm, pm = np.zeros(n_lig, np.int64), np.zeros(n_pok, np.int64)
+    t = np.array([[0.4]], np.float32)
+    e = O.get_edges(lm, pm, xl, xp, CFG)
+    assert e.shape[1] >= n_lig * n_lig
+    ref, _ = O.dynamics_forward(golden_weights, xh_lig, xh_pok, t, lm, pm, CFG, dtype=np.float64, edges=e)
+    if n_pok == 0:                       # the reference has no such call; the engine accepts an empty pocket
+        out_l, _ = dyn.engine.forward(_t(xh_lig, dev), torch.zeros((0, 13), device=dev), _t(t, dev), _t(lm, dev),
+                                      torch.zeros((0,), dtype=torch.long, device=dev), 1, want_pocket=False)
+    else:
+        out_l, _ = dyn(_t(xh_lig, dev), _t(xh_pok, dev), _t(t, dev), _t(lm, dev), _t(pm, dev))
+    _check_eps(out_l.cpu().numpy(), ref)
+    assert dyn.engine.read_flags() & 5 == 0
+
+
 def test_graphed_sampling_matches_eager(dyn, dev):
     """sample_given_pocket with the reverse step replayed from a CUDA graph draws the same trajectory as the eager loop
     (the capture's dry runs do not consume the noise stream).  The pocket COM of the prior goes through torch's atomic
