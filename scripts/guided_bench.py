@@ -17,7 +17,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 n_p = int(sys.argv[2]) if len(sys.argv) > 2 else 330
 cfg = DynamicsConfig()
 fan = 20                                            # SPSA: 2k copies of the batch
-dyn = E.B200EGNNDynamics(cfg, random_init(cfg, 0, 1e-3), max_nodes=fan * B * (n_p + 50) + 1024,
+dyn = E.B200EGNNDynamics(cfg, random_init(cfg, 0, 0.3), max_nodes=fan * B * (n_p + 50) + 1024,
                          max_edges=fan * B * (n_p + 50) * 24, max_samples=fan * B).eval()
 px, pt = synthetic.synthetic_pocket(7, n_p)
 sizes = synthetic.synthetic_ligand_sizes(7, B)
@@ -25,6 +25,11 @@ onehot = np.eye(10, dtype=np.float32)[pt]
 pocket = {'x': torch.from_numpy(np.tile(px, (B, 1))), 'one_hot': torch.from_numpy(np.tile(onehot, (B, 1))),
           'size': torch.tensor([len(px)] * B), 'mask': torch.arange(B).repeat_interleave(len(px))}
 smp = ConditionalSampler(dyn, timesteps=500)
+# stationary workload: the exact score of a point-mass pose in the pocket keeps the ligands there, as a
+# trained model would; guidance copies of the batch reuse the pose rows
+pose = synthetic.synthetic_ligand_pose(7, sizes, px.mean(axis=0, dtype=np.float64))
+pose[:, :3] -= px[0]
+smp.eps_transform = synthetic.PointMassScore(pose, smp.gamma, len(px), smp.T, torch.device('cuda'))
 
 
 def reward(x, types, mask):                        # radius of gyration per molecule, one device reduction + one D2H
