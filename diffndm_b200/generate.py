@@ -31,6 +31,51 @@ def state_dict_from_checkpoint(ckpt, prefix: str = 'ddpm.dynamics.'):
     return state, dict(ckpt.get('hyper_parameters', {}) or {})
 
 
+def config_from_checkpoint(state: Mapping[str, object], hparams: Optional[Mapping[str, object]] = None):
+    """``(DynamicsConfig, pocket_representation, sampler_kwargs)`` of a reference checkpoint: the sizes are read
+    off the weight shapes (they cannot disagree with the tensors that will be loaded), cutoffs / normalisation / schedule from
+    ``hyper_parameters['egnn_params' / 'diffusion_params']`` (``LigandPocketDDPM.__init__``, lightning_modules.py:32-57,
+    138-174) where present -- a Namespace or a dict -- and from the crossdock_fullatom_cond defaults otherwise.  Covers every
+    pocket-conditional configuration under ``configs/``; a joint model (``mode != 'pocket_conditioning'``) is refused."""
+    from .weights import DynamicsConfig
+    hp = dict(hparams or {})
+    if hp.get('mode', 'pocket_conditioning') != 'pocket_conditioning':
+        raise NotImplementedError(f"mode {hp['mode']!r}: only pocket-conditional checkpoints are on the engine's path")
+
+    def shape(key):
+        v = state[key]
+        return tuple(v.shape)
+
+    def field(group, name, default):
+        g = hp.get(group)
+        if g is None:
+            return default
+        v = g.get(name, default) if isinstance(g, Mapping) else getattr(g, name, default)
+        return default if v is None and name not in ('edge_cutoff_ligand', 'edge_cutoff_pocket', 'edge_cutoff_interaction') else v
+
+    hidden, d_in = shape('egnn.embedding.weight')
+    n_layers = 1 + max(int(k.split('.')[1].split('_')[-1]) for k in state if k.startswith('egnn.e_block_'))
+    base = DynamicsConfig()
+    cfg = DynamicsConfig(
+        atom_nf=shape('atom_encoder.0.weight')[1], residue_nf=shape('residue_encoder.0.weight')[1], joint_nf=d_in - 1,
+        hidden_nf=hidden, n_layers=n_layers,
+        edge_embedding_dim=(shape('edge_embedding.weight')[1] if 'edge_embedding.weight' in state else None),
+        edge_cutoff_ligand=field('egnn_params', 'edge_cutoff_ligand', base.edge_cutoff_ligand),
+        edge_cutoff_pocket=field('egnn_params', 'edge_cutoff_pocket', base.edge_cutoff_pocket),
+        edge_cutoff_interaction=field('egnn_params', 'edge_cutoff_interaction', base.edge_cutoff_interaction),
+        norm_constant=float(field('egnn_params', 'norm_constant', base.norm_constant)),
+        normalization_factor=float(field('egnn_params', 'normalization_factor', base.normalization_factor)),
+        attention=bool(field('egnn_params', 'attention', True)), tanh=bool(field('egnn_params', 'tanh', True)),
+        reflection_equivariant=bool(field('egnn_params', 'reflection_equivariant', False)),
+        inv_sublayers=int(field('egnn_params', 'inv_sublayers', 1)))
+    rep = hp.get('pocket_representation') or ('CA' if cfg.residue_nf == 20 and cfg.atom_nf != 20 else 'full-atom')
+    sampler_kwargs = dict(timesteps=int(field('diffusion_params', 'diffusion_steps', 500)),
+                          noise_schedule=str(field('diffusion_params', 'diffusion_noise_schedule', 'polynomial_2')),
+                          noise_precision=float(field('diffusion_params', 'diffusion_noise_precision', 5.0e-4)),
+                          norm_values=tuple(field('diffusion_params', 'normalize_factors', (1.0, 4.0))))
+    return cfg, rep, sampler_kwargs
+
+
 class LigandGenerator:
     """The part of ``LigandPocketDDPM`` that ``generate_ligands.py`` / ``my_test.py`` / ``inpaint.py`` use at inference."""
 
@@ -50,6 +95,20 @@ class LigandGenerator:
         self.pockets = pocket_cache or ingest.PocketCache(self.pocket_type_encoder, self.device, pocket_representation)
         self.perception = BondPerception(sampler.engine, dataset_info)
         self.mol_builder = mol_builder
+
+    @classmethod
+    def from_checkpoint(cls, ckpt, dataset_info: Optional[Mapping[str, object]] = None, **kwargs) -> 'LigandGenerator':
+        """``LigandPocketDDPM.load_from_checkpoint`` (generate_ligands.py:57-58) for the engine: weights, sizes, cutoffs,
+        schedule and the ligand-size histogram all come out of the checkpoint (``config_from_checkpoint``).  ``dataset_info``
+        defaults to the crossdock / bindingmoad table -- the two share the vocabularies and bond tables the path reads
+        (constants.py:96-131, 169-187)."""
+        from .datasets import crossdock_dataset_info
+        from .engine import B200EGNNDynamics
+        state, hparams = state_dict_from_checkpoint(ckpt)
+        cfg, rep, sampler_kwargs = config_from_checkpoint(state, hparams)
+        dyn = B200EGNNDynamics(cfg, state).eval()
+        return cls(ConditionalSampler(dyn, **sampler_kwargs), dataset_info or crossdock_dataset_info(rep),
+                   size_histogram=hparams.get('node_histogram'), pocket_representation=rep, **kwargs)
 
     # lightning_modules.py:763-801 (kept as a method because callers use it as one)
     def prepare_pocket(self, biopython_residues, repeats: int = 1):

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from diffndm_b200.datasets import crossdock_dataset_info                     # noqa: E402
 from diffndm_b200.engine import B200EGNNDynamics                             # noqa: E402
-from diffndm_b200.generate import LigandGenerator, state_dict_from_checkpoint  # noqa: E402
+from diffndm_b200.generate import LigandGenerator  # noqa: E402
 from diffndm_b200.sampler import ConditionalSampler                          # noqa: E402
 from diffndm_b200.weights import DynamicsConfig, random_init                 # noqa: E402
 
@@ -57,21 +57,18 @@ def main(argv=None):
         torch.manual_seed(args.seed)
         torch.cuda.manual_seed(args.seed)
 
-    cfg = DynamicsConfig()
-    hist = None
-    if args.checkpoint is not None:
-        state, hparams = state_dict_from_checkpoint(args.checkpoint)
-        hist = hparams.get('node_histogram')
-    else:
-        state = random_init(cfg, args.random_init, 1e-3)
     reward_fn = None
     if args.reward:
         mod, fn = args.reward.split(':')
         reward_fn = getattr(importlib.import_module(mod), fn)
     if (args.SVDD or args.SPSA) and reward_fn is None:
         parser.error('--SVDD / --SPSA need --reward module:function (host chemistry stays external)')
-    dyn = B200EGNNDynamics(cfg, state).eval()
-    model = LigandGenerator(ConditionalSampler(dyn, timesteps=500), crossdock_dataset_info(), size_histogram=hist)
+    if args.checkpoint is not None:      # sizes, cutoffs, schedule and the size histogram come out of the checkpoint
+        model = LigandGenerator.from_checkpoint(args.checkpoint)
+    else:
+        cfg = DynamicsConfig()
+        dyn = B200EGNNDynamics(cfg, random_init(cfg, args.random_init, 1e-3)).eval()
+        model = LigandGenerator(ConditionalSampler(dyn, timesteps=500), crossdock_dataset_info())
     n = model.generate_to_sdf(args.pdbfile, args.outfile, n_samples=args.n_samples, batch_size=args.batch_size,
                               num_nodes_lig=args.num_nodes_lig, all_frags=args.all_frags, pocket_ids=args.resi_list,
                               ref_ligand=args.ref_ligand, sanitize=args.sanitize, relax_iter=(200 if args.relax else 0),

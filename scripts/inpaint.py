@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 from diffndm_b200 import output                                              # noqa: E402
 from diffndm_b200.datasets import crossdock_dataset_info                     # noqa: E402
 from diffndm_b200.engine import B200EGNNDynamics                             # noqa: E402
-from diffndm_b200.generate import LigandGenerator, state_dict_from_checkpoint  # noqa: E402
+from diffndm_b200.generate import LigandGenerator  # noqa: E402
 from diffndm_b200.sampler import ConditionalSampler                          # noqa: E402
 from diffndm_b200.weights import DynamicsConfig, random_init                 # noqa: E402
 
@@ -47,21 +47,18 @@ def main(argv=None):
     if args.seed is not None:
         torch.manual_seed(args.seed)
         torch.cuda.manual_seed(args.seed)
-    cfg = DynamicsConfig()
-    hist = None
-    if args.checkpoint is not None:
-        state, hparams = state_dict_from_checkpoint(args.checkpoint)
-        hist = hparams.get('node_histogram')
-    else:
-        state = random_init(cfg, args.random_init, 1e-3)
     reward_fn = None
     if args.reward:
         mod, fn = args.reward.split(':')
         reward_fn = getattr(importlib.import_module(mod), fn)
     if args.svdd and reward_fn is None:
         parser.error('--svdd needs --reward module:function (host chemistry stays external)')
-    dyn = B200EGNNDynamics(cfg, state).eval()
-    model = LigandGenerator(ConditionalSampler(dyn, timesteps=500), crossdock_dataset_info(), size_histogram=hist)
+    if args.checkpoint is not None:      # sizes, cutoffs, schedule and the size histogram come out of the checkpoint
+        model = LigandGenerator.from_checkpoint(args.checkpoint)
+    else:
+        cfg = DynamicsConfig()
+        dyn = B200EGNNDynamics(cfg, random_init(cfg, args.random_init, 1e-3)).eval()
+        model = LigandGenerator(ConditionalSampler(dyn, timesteps=500), crossdock_dataset_info())
     molecules = model.inpaint_ligand(args.pdbfile, args.n_samples, args.ref_ligand, args.fix_atoms, args.add_n_nodes,
                                      args.svdd, center=args.center, sanitize=args.sanitize, largest_frag=False,
                                      relax_iter=(200 if args.relax else 0), timesteps=args.timesteps,

@@ -143,3 +143,32 @@ def test_sampler_step_with_wider_pocket_rows():
     xh, xpo, lmo, pmo = smp.sample_given_pocket(pocket, sizes, timesteps=4)
     assert xh.shape == (len(c['lig_mask']), 13) and xpo.shape == (len(c['pocket_mask']), 23)
     assert torch.isfinite(xh).all() and torch.isfinite(xpo).all()
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_config_from_checkpoint_recovers_configuration(name):
+    """A Lightning checkpoint of the reference (``ddpm.dynamics.*`` state + ``hyper_parameters`` with ``egnn_params`` /
+    ``diffusion_params`` Namespaces, lightning_modules.py:32-57) gives back the configuration the weights were made for."""
+    from argparse import Namespace
+    from dataclasses import asdict
+    import torch
+    from diffndm_b200.generate import config_from_checkpoint, state_dict_from_checkpoint
+    cfg = case_config(name)
+    W = random_init(cfg, 7, 0.3)
+    egnn = Namespace(edge_cutoff_ligand=cfg.edge_cutoff_ligand, edge_cutoff_pocket=cfg.edge_cutoff_pocket,
+                     edge_cutoff_interaction=cfg.edge_cutoff_interaction, norm_constant=cfg.norm_constant,
+                     normalization_factor=cfg.normalization_factor, attention=True, tanh=True, reflection_equivariant=False,
+                     inv_sublayers=1)
+    diff = Namespace(diffusion_steps=500, diffusion_noise_schedule='polynomial_2', diffusion_noise_precision=5.0e-4,
+                     normalize_factors=[1, 4])
+    ckpt = {'state_dict': {'ddpm.dynamics.' + k: torch.from_numpy(v) for k, v in W.items()} | {'ddpm.gamma.gamma': torch.zeros(501)},
+            'hyper_parameters': {'egnn_params': egnn, 'diffusion_params': diff, 'mode': 'pocket_conditioning',
+                                 'node_histogram': np.ones((30, 400))}}
+    state, hp = state_dict_from_checkpoint(ckpt)
+    assert set(state) == set(W)
+    got, rep, kw = config_from_checkpoint(state, hp)
+    assert asdict(got) == asdict(cfg)
+    assert rep == ('CA' if cfg.residue_nf == 20 else 'full-atom')
+    assert kw == dict(timesteps=500, noise_schedule='polynomial_2', noise_precision=5.0e-4, norm_values=(1, 4))
+    with pytest.raises(NotImplementedError):
+        config_from_checkpoint(state, {'mode': 'joint'})
