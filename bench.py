@@ -352,25 +352,40 @@ def run_b200(args):
     lig_mask = torch.from_numpy(b['lig_mask']).to(dev)
     pocket_mask = torch.from_numpy(b['pocket_mask']).to(dev)
     z, xp = z0.clone(), p0.clone()
-    t_buf = torch.zeros(B, 1, device=dev)
-    coef_buf = torch.zeros(B, 3, device=dev)
+    # per-step scalars as in the sampler's graphed reverse step (sampler._GraphedReverseStep): row s of `table` = (t, step
+    # coefficients, the two scalars of the synthetic score) of step s; the captured step gathers row `s_dev` and decrements it
+    Bp = (B + 3) // 4 * 4
+    packed = torch.zeros(1, Bp + 3 * B + 4, device=dev)
+    t_buf = packed[0, :B].view(B, 1)
+    coef_buf = packed[0, Bp:Bp + 3 * B].view(B, 3)
+    s_dev = torch.zeros(1, dtype=torch.long, device=dev)
     eps = torch.zeros_like(z)
     noise = torch.zeros_like(z)
     # synthetic score (see make_inputs): 1/sigma_t and -alpha_t/sigma_t of step s -> s+1's t
     isig_tab = (1.0 / smp.sigma_tab[1:]).to(dev)
     nais_tab = (-smp.alpha_tab[1:] / smp.sigma_tab[1:]).to(dev)
     score = SyntheticScore(torch.from_numpy(b['x0_target']).to(dev), p0, lig_mask, n_p // B, B, dev)
+    score.isig = packed[:, Bp + 3 * B:Bp + 3 * B + 1]
+    score.nais = packed[:, Bp + 3 * B + 1:Bp + 3 * B + 2]
+    table = torch.zeros(T_STEPS, packed.shape[1], device=dev)
+    table[:, :B] = t_tab[:, None]
+    table[:, Bp:Bp + 3 * B] = coef_tab[:, None, :].expand(T_STEPS, B, 3).reshape(T_STEPS, 3 * B)
+    table[:, Bp + 3 * B] = isig_tab
+    table[:, Bp + 3 * B + 1] = nais_tab
+    next_s = [None]
 
     def body():
+        torch.index_select(table, 0, s_dev, out=packed)
+        s_dev.sub_(1)
         noise.normal_()
         eng.forward(z, xp, t_buf, lig_mask, pocket_mask, B, out_lig=eps, want_pocket=False)
         score.apply(eps, z, xp)
         eng.sampler_step(z, eps, noise, xp, coef_buf, lig_mask, pocket_mask, B, z_out=z, pocket_out=xp, check_com=True)
 
-    def set_step(s):
-        t_buf.copy_(t_tab[s].expand(B, 1))
-        coef_buf.copy_(coef_tab[s].expand(B, 3))
-        score.set_step(isig_tab[s], nais_tab[s])
+    def set_step(s):                 # a launch only when s is not the successor of the previous step
+        if next_s[0] != s:
+            s_dev.fill_(s)
+        next_s[0] = s - 1
 
     graph = None
     l0 = E.launch_count()
@@ -388,6 +403,7 @@ def run_b200(args):
         graph = torch.cuda.CUDAGraph()      # like the sampler's graphed reverse step (sampler._GraphedReverseStep)
         with torch.cuda.graph(graph):
             body()
+        next_s[0] = None                    # the dry runs moved the device-side step index
 
     def step(s):
         set_step(s)

@@ -220,6 +220,9 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     DndmEngine* e = new DndmEngine();
     e->cfg = *cfg;
     e->num_sms = prop.multiProcessorCount;
+    // experiment knob (scripts/two_stream_bench.py): size the persistent grids for fewer SMs, so that a second engine's
+    // kernels on another stream find free SMs
+    if (const char* v = getenv("DNDM_SMS")) { const int n = atoi(v); if (n >= 2 && n <= e->num_sms) e->num_sms = n & ~1; }
     g_num_sms = e->num_sms;
     const size_t N = (size_t)((cfg->max_nodes + 127) / 128) * 128, E = cfg->max_edges, B = cfg->max_samples;
     RET_IF(dev_alloc(&e->x0, N * 3)); RET_IF(dev_alloc(&e->xa, N * 3)); RET_IF(dev_alloc(&e->xb, N * 3));

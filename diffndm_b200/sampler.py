@@ -111,13 +111,26 @@ class _GraphedReverseStep:
         self.engine = eng
         self.z, self.xp = z_lig, xh_pocket                     # updated in place
         self.lig_mask, self.pocket_mask = lig_mask, pocket_mask   # the graph reads these buffers on every replay
-        self.t_buf = torch.zeros((B, 1), device=dev)
-        self.coef_buf = torch.zeros((B, 3), device=dev)
+        # Per-step scalars without per-step host work: row s of `table` holds (t, step coefficients) of step s already expanded
+        # over the samples; the captured step gathers row `s_idx` into `packed` -- t_buf / coef_buf are views of it -- and
+        # decrements `s_idx`, so a run of consecutive steps is one graph replay per step and nothing else (two expand-copies
+        # per step before: 28 us of a 1.65 ms step).  The host rewrites `s_idx` only when a step is not the successor of the
+        # previous replay (first step, after a guidance event).
+        Bp = (B + 3) // 4 * 4                                   # keeps coef_buf 16-byte aligned
+        self.table = torch.zeros((sampler.T, Bp + 3 * B), device=dev)
+        self.packed = torch.zeros((1, Bp + 3 * B), device=dev)
+        self.t_buf = self.packed[0, :B].view(B, 1)
+        self.coef_buf = self.packed[0, Bp:].view(B, 3)
+        self.s_idx = torch.zeros(1, dtype=torch.long, device=dev)
+        self._next_s = None
+        self._tables_of = None
         # the captured kernels read the transform's tensors on every replay: the graph is valid for THIS transform object only
         # (part of the cache key) and keeps it alive
         self.transform = transform = sampler.eps_transform
 
         def body():
+            torch.index_select(self.table, 0, self.s_idx, out=self.packed)
+            self.s_idx.sub_(1)
             eps, _ = eng.forward(self.z, self.xp, self.t_buf, lig_mask, pocket_mask, B, want_pocket=False)
             if transform is not None:
                 eps = transform(eps, self.z, self.xp, self.t_buf, lig_mask, pocket_mask)
@@ -130,7 +143,8 @@ class _GraphedReverseStep:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            body()                                             # warm-up outside capture (allocator, layout cache)
+            body()                                             # warm-up outside capture (allocator, layout cache); row 0 of the
+            self.s_idx.zero_()                                 # still empty table: all-zero scalars, state restored below
         torch.cuda.current_stream().wait_stream(side)
         # the captured step derives the per-sample offsets from the masks itself (cache reset -> the first prepare_batch of
         # the body launches the two mask kernels inside the graph): a replay does not depend on what other calls left in
@@ -156,11 +170,24 @@ class _GraphedReverseStep:
         eng.read_flags(consume=FLAG_COM_DRIFT)                 # the dry runs may have tripped the COM-drift flag (state restored
                                                                # above); NaN / overflow bits of earlier calls stay pending
 
-    def __call__(self, t_dev: torch.Tensor, coef_dev: torch.Tensor):
-        """t_dev: 0-d device tensor, coef_dev: [3] device tensor (same for every sample of an unguided step)."""
-        self.t_buf.copy_(t_dev.expand_as(self.t_buf))
-        self.coef_buf.copy_(coef_dev.expand_as(self.coef_buf))
+    def set_tables(self, t_all: torch.Tensor, coef_all: torch.Tensor):
+        """Per-step scalars of a trajectory: t_all [T'], coef_all [T', 3] (device, T' <= sampler.T; the same for every sample of
+        an unguided step).  Once per trajectory."""
+        if self._tables_of is t_all:
+            return
+        n, B = int(t_all.shape[0]), self.t_buf.shape[0]
+        assert n <= self.table.shape[0], 'more steps than the sampler was built for'
+        self.table[:n, :B] = t_all[:, None]
+        self.table[:n, self.packed.shape[1] - 3 * B:] = coef_all[:, None, :].expand(n, B, 3).reshape(n, 3 * B)
+        self._tables_of = t_all
+        self._next_s = None
+
+    def __call__(self, s: int):
+        """The reverse step s + 1 -> s with the scalars of table row s."""
+        if self._next_s != s:
+            self.s_idx.fill_(s)
         self.graph.replay()
+        self._next_s = s - 1
         self.engine.set_static_masks(True)      # host-side cache reset: the device scratch now holds THIS graph's layout
 
 
@@ -493,7 +520,8 @@ class ConditionalSampler:
                                 self._graph_cache.pop(next(iter(self._graph_cache)))
                             self._graph_cache[key] = gstep
                         z_lig, xh_pocket = gstep.z, gstep.xp
-                    gstep(t_all[s], coef_all[s])
+                        gstep.set_tables(t_all, coef_all)
+                    gstep(s)
                 else:
                     z_lig, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lig_mask, pocket_mask,
                                                                  noise=step_noise(int(lig_mask.numel())), n_samples=B)
