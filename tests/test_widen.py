@@ -172,3 +172,72 @@ def test_config_from_checkpoint_recovers_configuration(name):
     assert kw == dict(timesteps=500, noise_schedule='polynomial_2', noise_precision=5.0e-4, norm_values=(1, 4))
     with pytest.raises(NotImplementedError):
         config_from_checkpoint(state, {'mode': 'joint'})
+
+
+def _write_residue_pdb(path, centers, resnames, lig_xyz):
+    """One residue per centre: N / CA / C / O around it (CA exactly on the centre), plus a hetero ligand residue 900."""
+    offs = np.array([[-1.2, 0.4, 0.0], [0.0, 0.0, 0.0], [1.3, 0.5, 0.0], [1.9, 1.5, 0.4]], np.float32)
+    lines, k = [], 0
+    for r, (c, rn) in enumerate(zip(centers, resnames)):
+        for name, el, o in zip(['N', 'CA', 'C', 'O'], ['N', 'C', 'C', 'O'], offs):
+            k += 1
+            p = c + o
+            lines.append(f"ATOM  {k:5d}  {name:<3s} {rn} A{r + 1:4d}    {p[0]:8.3f}{p[1]:8.3f}{p[2]:8.3f}  1.00  0.00          {el:>2s}")
+    for j, p in enumerate(lig_xyz):
+        k += 1
+        lines.append(f"HETATM{k:5d}  C{j:<2d} LIG A 900    {p[0]:8.3f}{p[1]:8.3f}{p[2]:8.3f}  1.00  0.00           C")
+    with open(path, 'w') as f:
+        f.write('\n'.join(lines) + '\nEND\n')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_checkpoint_file_to_sdf(name, tmp_path):
+    """The script path for the other configurations: a Lightning-layout checkpoint FILE of the reference -> ``from_checkpoint``
+    (sizes off the weight shapes, cutoffs / schedule / size histogram off ``hyper_parameters``) -> PDB file -> SDF file on the
+    engine.  The loaded denoiser must be the one the weights describe: its forward equals the engine built directly from
+    (config, weights), bit for bit."""
+    from argparse import Namespace
+    import torch
+    from diffndm_b200 import output
+    from diffndm_b200.engine import B200EGNNDynamics
+    from diffndm_b200.generate import LigandGenerator
+    cfg = case_config(name)
+    W = random_init(cfg, 7, 0.3)
+    hist = np.zeros((30, 400))
+    hist[8:16, :] = 1.0
+    ckpt = {'state_dict': {'ddpm.dynamics.' + k: torch.from_numpy(v) for k, v in W.items()},
+            'hyper_parameters': {'egnn_params': Namespace(edge_cutoff_ligand=cfg.edge_cutoff_ligand, edge_cutoff_pocket=cfg.edge_cutoff_pocket,
+                                                          edge_cutoff_interaction=cfg.edge_cutoff_interaction, norm_constant=1.0,
+                                                          normalization_factor=100.0, attention=True, tanh=True,
+                                                          reflection_equivariant=False, inv_sublayers=1),
+                                 'diffusion_params': Namespace(diffusion_steps=500, diffusion_noise_schedule='polynomial_2',
+                                                               diffusion_noise_precision=5.0e-4, normalize_factors=[1, 4]),
+                                 'mode': 'pocket_conditioning', 'node_histogram': hist,
+                                 'pocket_representation': 'CA' if cfg.residue_nf == 20 else 'full-atom'}}
+    path = tmp_path / 'model.ckpt'
+    torch.save(ckpt, path)
+    gen = LigandGenerator.from_checkpoint(path)
+    assert gen.pocket_representation == ('CA' if cfg.residue_nf == 20 else 'full-atom')
+    assert gen.ddpm.dynamics.cfg.hidden_nf == cfg.hidden_nf and gen.ddpm.dynamics.cfg.edge_embedding_dim == cfg.edge_embedding_dim
+
+    rng = np.random.default_rng(11)
+    centers = (rng.normal(size=(40, 3)) * 5.0 + np.array([20.0, -8.0, 3.0])).astype(np.float32)
+    names = ['ALA', 'GLY', 'SER', 'LEU', 'ASP', 'LYS', 'PHE', 'CYS']
+    pdb = tmp_path / 'pocket.pdb'
+    _write_residue_pdb(pdb, np.round(centers, 3), [names[i % 8] for i in range(40)],
+                       centers.mean(0, keepdims=True) + np.array([[0, 0, 0], [1.4, 0, 0]], np.float32))
+    torch.manual_seed(3)
+    torch.cuda.manual_seed(3)
+    n = gen.generate_to_sdf(str(pdb), tmp_path / 'out.sdf', n_samples=4, batch_size=2, ref_ligand='A:900', timesteps=10)
+    mols = output.read_sdf(tmp_path / 'out.sdf')
+    assert n == 4 and len(mols) == 4 and all(np.isfinite(m.positions).all() for m in mols)
+
+    # same function as the engine built directly from (config, weights)
+    c = {k.split('/', 1)[1]: FX[k] for k in FX.files if k.startswith(name + '/')}
+    dev = torch.device('cuda', 0)
+    direct = B200EGNNDynamics(cfg, W).eval()
+    args = [torch.from_numpy(c[k]).to(dev) for k in ('xh_lig', 'xh_pocket', 't', 'lig_mask', 'pocket_mask')]
+    a, _ = gen.ddpm.dynamics(*args)
+    b, _ = direct(*args)
+    assert torch.equal(a, b)
