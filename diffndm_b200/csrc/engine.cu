@@ -30,6 +30,8 @@ static long long g_launches = 0;   // kernels of this library launched (or captu
 // Programmatic dependent launch for the weight-resident kernels (edge MLP, node GEMMs): their prologue -- barrier
 // init, TMEM allocation, the 64-128 KiB TMA load of the resident weights -- runs under the tail of the previous kernel
 // of the stream (see pdl_wait / pdl_trigger in common.cuh).  DNDM_PDL=0 in the environment turns the attribute off.
+// DNDM_PP_LISTS=0: every call scans all same-sample pocket atoms for every pocket row (the round-1 path; for A/B)
+static bool g_pp_lists = [] { const char* v = getenv("DNDM_PP_LISTS"); return !(v && v[0] == '0'); }();
 static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] == '0'); }();
 // GCL producers: all-bf16x2 first-layer pre-activation by default; DNDM_GCL_F32_RADIAL=1 selects the variant with fp32 radial
 // terms and activation (measured on the radial stress fixture: same error to two digits, 8 % slower -- see edge_mlp.cuh)
@@ -139,12 +141,13 @@ struct DndmEngine {
     int *ecol = nullptr, *erow = nullptr, *scalars = nullptr, *block_sums = nullptr;
     int *deg_act = nullptr, *rp_act = nullptr, *erow_c = nullptr, *ecol_c = nullptr;   // last-block compacted graph
     float* r0_c = nullptr;
+    PocketLists pp{};                            // pocket-pocket candidate lists (graph.cuh)
     unsigned* flags = nullptr;
     long long* mol_off = nullptr;                // [max_samples + 1] byte offsets of the per-molecule bond matrices
     // the radius graph only needs coordinates: it is built on a side stream while the main stream encodes the features
     float* xg = nullptr;                         // [N,3] coordinates gathered for the graph branch
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_last = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_last = nullptr, ev_join_pp = nullptr;
     // cached batch layout (dndm_set_static_masks)
     bool static_masks = false;
     const int64_t *last_lm = nullptr, *last_pm = nullptr;
@@ -237,12 +240,16 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(dev_alloc(&e->deg_act, N)); RET_IF(dev_alloc(&e->rp_act, N + 1)); RET_IF(dev_alloc(&e->erow_c, E + 1));
     RET_IF(dev_alloc(&e->ecol_c, E)); RET_IF(dev_alloc(&e->r0_c, E));
     RET_IF(dev_alloc(&e->flags, 1));
+    RET_IF(dev_alloc(&e->pp.canon, N * 3)); RET_IF(dev_alloc(&e->pp.ptr, B + 1)); RET_IF(dev_alloc(&e->pp.meta, 8));
+    RET_IF(dev_alloc(&e->pp.cand, N * PP_CAP)); RET_IF(dev_alloc(&e->pp.cnt, N));
+    CU_CHECK(cudaMemset(e->pp.meta, 0, 8 * sizeof(int)));
     RET_IF(dev_alloc(&e->xg, N * 3));
     RET_IF(dev_alloc(&e->mol_off, B + 1));
     CU_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_join_last, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&e->ev_join_pp, cudaEventDisableTiming));
     CU_CHECK(cudaMemset(e->flags, 0, 4));
     CU_CHECK(cudaMemset(e->hcat, 0, N * 512 * 2));
     CU_CHECK(cudaMemset(e->hid, 0, N * 256 * 2));
@@ -278,11 +285,12 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->msg, e->att, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
                     e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->deg_act, e->rp_act, e->erow_c,
-                    e->ecol_c, e->r0_c, e->flags, e->xg, e->mol_off};
+                    e->ecol_c, e->r0_c, e->flags, e->xg, e->mol_off, e->pp.canon, e->pp.ptr, e->pp.meta, e->pp.cand, e->pp.cnt};
     for (void* p : bufs) cudaFree(p);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_join_last) cudaEventDestroy(e->ev_join_last);
+    if (e->ev_join_pp) cudaEventDestroy(e->ev_join_pp);
     if (e->side) cudaStreamDestroy(e->side);
     delete e;
 }
@@ -595,17 +603,45 @@ static int build_last_block_edges(DndmEngine* e, int n_lig, int n_nodes, cudaStr
     return DNDM_OK;
 }
 
-static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, cudaStream_t st) {
+static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, int n_samples, cudaStream_t st) {
     GraphParams gp;
     gp.x = x; gp.lig_ptr = e->lig_ptr; gp.pok_ptr = e->pok_ptr; gp.node_sample = e->node_sample;
     gp.n_lig = n_lig; gp.n_nodes = n_nodes;
     auto sq = [](float c) { return c < 0.f ? -1.f : c * c; };
     gp.cut2_l = sq(e->cfg.edge_cutoff_ligand); gp.cut2_p = sq(e->cfg.edge_cutoff_pocket);
     gp.cut2_i = sq(e->cfg.edge_cutoff_interaction);
+    const int n_pocket = n_nodes - n_lig;
+    const bool lists = n_pocket > 0 && g_pp_lists;
+    PocketLists pl = e->pp;
+    if (!lists) pl.meta = nullptr;
+    if (lists) {
+        const int n = n_pocket > n_samples + 1 ? n_pocket : n_samples + 1;
+        pp_verify_kernel<<<(n + 255) / 256, 256, 0, st>>>(gp, pl, n_samples);
+        COUNT_LAUNCH(1);
+    }
     const int blocks = (n_nodes * 32 + 255) / 256;
-    graph_rows_kernel<false><<<blocks, 256, 0, st>>>(gp, e->deg, nullptr, nullptr, nullptr, nullptr, e->cfg.max_edges);
+    graph_rows_kernel<false><<<blocks, 256, 0, st>>>(gp, pl, e->deg, nullptr, nullptr, nullptr, nullptr, e->cfg.max_edges);
     RET_IF(exclusive_scan(e, e->deg, e->row_ptr, n_nodes, n_lig, 0, 1, st));
-    graph_rows_kernel<true><<<blocks, 256, 0, st>>>(gp, nullptr, e->row_ptr, e->ecol, e->erow, e->r0, e->cfg.max_edges);
+    graph_rows_kernel<true><<<blocks, 256, 0, st>>>(gp, pl, nullptr, e->row_ptr, e->ecol, e->erow, e->r0, e->cfg.max_edges);
+    COUNT_LAUNCH(2);
+    CU_CHECK(cudaGetLastError());
+    return DNDM_OK;
+}
+
+// after build_graph (and after whoever waits for the graph has been released): rebuild the pocket-pocket candidate lists if
+// this call found them missing or stale, then mark them as describing this call's layout
+static int refresh_pocket_lists(DndmEngine* e, const float* x, int n_lig, int n_nodes, int n_samples, cudaStream_t st) {
+    const int n_pocket = n_nodes - n_lig;
+    if (n_pocket <= 0 || !g_pp_lists) return DNDM_OK;
+    GraphParams gp;
+    gp.x = x; gp.lig_ptr = e->lig_ptr; gp.pok_ptr = e->pok_ptr; gp.node_sample = e->node_sample;
+    gp.n_lig = n_lig; gp.n_nodes = n_nodes;
+    auto sq = [](float c) { return c < 0.f ? -1.f : c * c; };
+    gp.cut2_l = sq(e->cfg.edge_cutoff_ligand); gp.cut2_p = sq(e->cfg.edge_cutoff_pocket);
+    gp.cut2_i = sq(e->cfg.edge_cutoff_interaction);
+    const long long threads = (long long)n_pocket * 32 > n_samples + 1 ? (long long)n_pocket * 32 : n_samples + 1;
+    pp_rebuild_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(gp, e->pp, n_samples);
+    pp_commit_kernel<<<1, 1, 0, st>>>(e->pp, n_lig, n_pocket, n_samples);
     COUNT_LAUNCH(2);
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
@@ -646,11 +682,15 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         gather_xyz_kernel<<<(N * 3 + 255) / 256, 256, 0, gs>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, e->xg);
         pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, gs>>>(e->xg, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
         COUNT_LAUNCH(2);
-        RET_IF(build_graph(e, e->xg, n_lig, N, gs));
+        RET_IF(build_graph(e, e->xg, n_lig, N, n_samples, gs));
         if (fork) CU_CHECK(cudaEventRecord(e->ev_join, gs));   // blocks 0..L-2 only need the full graph
         // the compacted edge list is first read by the LAST block: it keeps running on the side stream under block 0
         if (prune_last) RET_IF(build_last_block_edges(e, n_lig, N, gs));
         if (fork && prune_last) CU_CHECK(cudaEventRecord(e->ev_join_last, gs));
+        // off the critical path: the main stream only joins it at the very end of the call (so that the side stream is idle
+        // -- and, under capture, joined -- when the call returns)
+        RET_IF(refresh_pocket_lists(e, e->xg, n_lig, N, n_samples, gs));
+        if (fork) CU_CHECK(cudaEventRecord(e->ev_join_pp, gs));
     }
 
     // ---- feature branch: encoder + embedding, first-layer projections of block 0's edge model (pq columns [0,512)) ----
@@ -742,6 +782,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
                                      cudaMemcpyDeviceToDevice, st));
         CU_CHECK(cudaGetLastError());
     }
+    if (fork) CU_CHECK(cudaStreamWaitEvent(st, e->ev_join_pp, 0));
     // ---- embedding_out + decoders + velocity ----
     {
         const int n_out = out_pocket ? N : n_lig;
@@ -778,7 +819,8 @@ extern "C" int dndm_radius_graph(DndmEngine* e, const float* xh_lig, const float
     gather_xyz_kernel<<<(N * 3 + 255) / 256, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + e->cfg.atom_nf, 3 + e->cfg.residue_nf,
                                                            e->x0);
     COUNT_LAUNCH(1);
-    RET_IF(build_graph(e, e->x0, n_lig, N, st));
+    RET_IF(build_graph(e, e->x0, n_lig, N, n_samples, st));
+    RET_IF(refresh_pocket_lists(e, e->x0, n_lig, N, n_samples, st));
     int sc[2] = {0, 0};
     CU_CHECK(cudaMemcpyAsync(sc, e->scalars, 8, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
@@ -867,6 +909,7 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
             break;
         }
         case 4: src = e->scalars; bytes = 16; break;
+        case 7: src = e->pp.meta; bytes = 32; break;
 #ifdef DNDM_EK_TRACE
         case 6: {
             bytes = sizeof(g_wr_trace) < (size_t)dst_bytes ? sizeof(g_wr_trace) : dst_bytes;

@@ -27,10 +27,92 @@ DNDM_DEVICE float dist2_rn(float ax, float ay, float az, float bx, float by, flo
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// ---- pocket-pocket candidate lists --------------------------------------------------------------------------------
+// Inside a trajectory the pocket of a sample is a rigid body that only translates (conditional_model.py:529-533), and
+// pocket-pocket pairs are 84 % of the edges: scanning all ~330 same-sample pocket atoms for every pocket row, twice per
+// call (count, fill), was ~55 us of a 1.65 ms step and mostly exposed (the graph is on the critical path of block 0).  The
+// engine therefore keeps, per pocket row, the ascending list of same-sample pocket atoms within cutoff + PP_MARGIN, built
+// from the coordinates of some earlier call, and the row kernels run the EXACT test of the current call -- same arithmetic,
+// same order -- on that list only.  Nothing is promised by the caller: every call first verifies on the device that the
+// batch layout is the one the lists were built for and that every pocket atom still sits, relative to its sample's first
+// pocket atom, within PP_TOL of where it sat then (pp_verify_kernel); if not, this call scans everything as before and
+// rebuilds the lists afterwards (pp_rebuild_kernel, off the critical path).  A pair within the cutoff now was within
+// cutoff + 2 PP_TOL then, so the lists are a superset and the emitted edge set is bit-identical; the translation rounding of
+// a 500-step trajectory moves atoms by ~1e-4 A relative to each other.  All of it is device-side: it replays in a CUDA graph.
+constexpr int PP_CAP = 64;             // list capacity per row; a denser row has no list (0xFFFF) and scans everything
+constexpr float PP_TOL = 0.02f;        // A
+constexpr float PP_MARGIN = 0.1f;      // A  (> 2 PP_TOL + rounding)
+
+struct PocketLists {
+    float* canon;            // [n_pocket,3] pocket coordinates the lists were built from
+    int* ptr;                // [B+1] pok_ptr of that call
+    int* meta;               // [0] built, [1] stale (set by verify), [2] n_lig, [3] n_pocket, [4] n_samples of that call,
+                             // [5] list length used for the first pocket row by the last call (-1: scanned everything)
+    unsigned short* cand;    // [n_pocket][PP_CAP] candidate offsets within the sample's pocket range, ascending
+    unsigned short* cnt;     // [n_pocket]
+};
+
+__global__ void __launch_bounds__(256)
+pp_verify_kernel(GraphParams p, PocketLists c, int n_samples) {
+    if (c.meta[0] == 0) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_pocket = p.n_nodes - p.n_lig;
+    bool stale = false;
+    if (t == 0) stale = c.meta[2] != p.n_lig || c.meta[3] != n_pocket || c.meta[4] != n_samples;
+    if (t <= n_samples) stale |= c.ptr[t] != p.pok_ptr[t];
+    if (t < n_pocket) {
+        const int j = p.n_lig + t;
+        const int f = p.pok_ptr[p.node_sample[j]];           // the sample's first pocket atom (pocket-local index)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float d = (p.x[3 * j + k] - p.x[3 * (p.n_lig + f) + k]) - (c.canon[3 * t + k] - c.canon[3 * f + k]);
+            stale |= !(fabsf(d) <= PP_TOL);                  // NaN counts as moved
+        }
+    }
+    if (stale) c.meta[1] = 1;
+}
+
+// warp per pocket row; runs only when the lists are missing or stale
+__global__ void __launch_bounds__(256)
+pp_rebuild_kernel(GraphParams p, PocketLists c, int n_samples) {
+    if (c.meta[0] != 0 && c.meta[1] == 0) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g <= n_samples) c.ptr[g] = p.pok_ptr[g];
+    const int t = g >> 5, lane = threadIdx.x & 31;
+    if (t >= p.n_nodes - p.n_lig) return;
+    const int j = p.n_lig + t;
+    const int b = p.node_sample[j];
+    const int beg = p.pok_ptr[b], end = p.pok_ptr[b + 1];
+    const float xi = p.x[3 * j], yi = p.x[3 * j + 1], zi = p.x[3 * j + 2];
+    const float rc = sqrtf(fmaxf(p.cut2_p, 0.f)) + PP_MARGIN;
+    const float cand2 = rc * rc;
+    int count = 0;
+    for (int j0 = beg; j0 < end; j0 += 32) {
+        const int jl = j0 + lane;
+        bool ok = false;
+        if (jl < end) {
+            const float* q = p.x + 3 * (p.n_lig + jl);
+            ok = dist2_rn(xi, yi, zi, q[0], q[1], q[2]) <= cand2;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (pos < PP_CAP) c.cand[(size_t)t * PP_CAP + pos] = (unsigned short)(jl - beg);
+        }
+        count += __popc(m);
+    }
+    if (lane == 0) c.cnt[t] = (count > PP_CAP || end - beg > 65535 || p.cut2_p < 0.f) ? 0xFFFFu : (unsigned short)count;
+    if (lane < 3) c.canon[3 * t + lane] = p.x[3 * j + lane];
+}
+
+__global__ void pp_commit_kernel(PocketLists c, int n_lig, int n_pocket, int n_samples) {
+    c.meta[0] = 1; c.meta[1] = 0; c.meta[2] = n_lig; c.meta[3] = n_pocket; c.meta[4] = n_samples;
+}
+
 // One warp per row.  kFill=false: deg[i] = number of neighbours.  kFill=true: write col / erow / r0.
 template <bool kFill>
 __global__ void __launch_bounds__(256)
-graph_rows_kernel(GraphParams p, int* deg, const int* row_ptr, int* ecol, int* erow, float* r0, int max_edges) {
+graph_rows_kernel(GraphParams p, PocketLists c, int* deg, const int* row_ptr, int* ecol, int* erow, float* r0, int max_edges) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= p.n_nodes) return;
@@ -40,11 +122,50 @@ graph_rows_kernel(GraphParams p, int* deg, const int* row_ptr, int* ecol, int* e
     const float xi = p.x[3 * i], yi = p.x[3 * i + 1], zi = p.x[3 * i + 2];
     int out = kFill ? row_ptr[i] : 0;
     int count = 0;
+    auto emit = [&](bool ok, int j, float d2) {              // ballot compaction keeps ascending j
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (kFill) {
+            if (ok) {
+                const int pos = out + __popc(m & ((1u << lane) - 1u));
+                if (pos < max_edges) {
+                    ecol[pos] = j;
+                    erow[pos] = i;
+                    r0[pos] = d2;
+                }
+            }
+            out += __popc(m);
+        } else {
+            count += __popc(m);
+        }
+    };
+    // pocket row with a valid candidate list: the pocket part of the row is the exact test over the list
+    int n_list = -1;
+    if (!i_lig && c.meta != nullptr && c.meta[0] == 1 && c.meta[1] == 0 && p.cut2_p >= 0.f) {
+        const int n = c.cnt[i - p.n_lig];
+        if (n != 0xFFFF) n_list = n;
+    }
+    if (!kFill && i == p.n_lig && lane == 0 && c.meta != nullptr) c.meta[5] = n_list;   // introspection: did this call use the lists
 #pragma unroll 1
     for (int part = 0; part < 2; ++part) {
         const int beg = part == 0 ? p.lig_ptr[b] : p.n_lig + p.pok_ptr[b];
         const int end = part == 0 ? p.lig_ptr[b + 1] : p.n_lig + p.pok_ptr[b + 1];
         const float cut2 = part == 0 ? (i_lig ? p.cut2_l : p.cut2_i) : (i_lig ? p.cut2_i : p.cut2_p);
+        if (part == 1 && n_list >= 0) {
+            const unsigned short* lst = c.cand + (size_t)(i - p.n_lig) * PP_CAP;
+            for (int k0 = 0; k0 < n_list; k0 += 32) {
+                const int k = k0 + lane;
+                bool ok = false;
+                float d2 = 0.f;
+                int j = 0;
+                if (k < n_list) {
+                    j = beg + lst[k];
+                    d2 = dist2_rn(xi, yi, zi, p.x[3 * j], p.x[3 * j + 1], p.x[3 * j + 2]);
+                    ok = d2 <= cut2;
+                }
+                emit(ok, j, d2);
+            }
+            continue;
+        }
         for (int j0 = beg; j0 < end; j0 += 32) {
             const int j = j0 + lane;
             bool ok = false;
@@ -53,20 +174,7 @@ graph_rows_kernel(GraphParams p, int* deg, const int* row_ptr, int* ecol, int* e
                 d2 = dist2_rn(xi, yi, zi, p.x[3 * j], p.x[3 * j + 1], p.x[3 * j + 2]);
                 ok = (cut2 < 0.f) || (d2 <= cut2);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (kFill) {
-                if (ok) {
-                    const int pos = out + __popc(m & ((1u << lane) - 1u));
-                    if (pos < max_edges) {
-                        ecol[pos] = j;
-                        erow[pos] = i;
-                        r0[pos] = d2;
-                    }
-                }
-                out += __popc(m);
-            } else {
-                count += __popc(m);
-            }
+            emit(ok, j, d2);
         }
     }
     if (!kFill && lane == 0) deg[i] = count;

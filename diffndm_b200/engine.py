@@ -278,6 +278,12 @@ class Engine:
         """(E, E_ligand_receiver) of the last forward / radius_graph call (synchronises)."""
         return self.graph_stats_full()[:2]
 
+    def pocket_list_state(self):
+        """Introspection for tests: int32 [8] state of the pocket-pocket candidate lists (include/diffndm_b200.h, buffer 7)."""
+        t = torch.zeros(8, dtype=torch.int32, device=torch.device('cuda', self.device))
+        _check(self.lib, self.lib.dndm_debug_copy(self._h, 7, _ptr(t), 32, _stream()), 'dndm_debug_copy')
+        return t.cpu().tolist()
+
     def graph_stats_full(self):
         """(E, E_ligand_receiver, E_last_block): the third entry is the number of edges the last block aggregates when
         the pocket output is not requested (ligand receivers + their pocket senders); stale otherwise."""

@@ -119,6 +119,69 @@ def test_radius_graph_vs_oracle_ragged_random(dyn, dev):
         assert np.array_equal(e, ref)
 
 
+def test_radius_graph_pocket_lists_stay_bit_exact(dyn, dev):
+    """The pocket-pocket candidate lists (csrc/graph.cuh): calls 2..n on a batch whose pockets only translate are served
+    from the lists and must emit the oracle's edge list bit for bit -- with the ligands moved, with every sample's pocket
+    translated by its own vector, on a 1e-3 A grid (exact ties at the cutoff, as PDB coordinates produce).  A pocket that
+    deforms, another batch layout, or a row denser than the list capacity must fall back to the full scan (same result)."""
+    from diffndm_b200 import synthetic
+    eng = dyn.engine
+    rng = np.random.default_rng(17)
+    px, pt = synthetic.synthetic_pocket(61, 300)
+    px = np.round(px, 3).astype(np.float32)                           # PDB-like grid
+    sizes = np.array([12, 30, 7, 21])
+    B = len(sizes)
+    b = synthetic.make_batch(px, pt, sizes, 5)
+    n_p = len(px)
+
+    def edges(bb):
+        rp, col = eng.radius_graph(_t(bb['xh_lig'], dev), _t(bb['xh_pocket'], dev), _t(bb['lig_mask'], dev), _t(bb['pocket_mask'], dev), B)
+        ref = O.get_edges(bb['lig_mask'], bb['pocket_mask'], bb['xh_lig'][:, :3], bb['xh_pocket'][:, :3], CFG)
+        assert np.array_equal(_edges_from_csr(rp.cpu().numpy(), col.cpu().numpy()), ref)
+        return eng.pocket_list_state()
+
+    st = edges(b)                                                      # whatever an earlier test left: rebuilt for this layout now
+    assert st[0] == 1 and st[1] == 0 and st[2:5] == [int(sizes.sum()), B * n_p, B]
+    for step in range(6):                                              # rigid moves: per-sample translation, new ligand poses
+        shift = rng.normal(size=(B, 3)).astype(np.float32) * (0.3 if step < 5 else 40.0)
+        b['xh_pocket'][:, :3] = (b['xh_pocket'][:, :3].reshape(B, n_p, 3) - shift[:, None, :]).reshape(-1, 3)
+        b['xh_lig'][:, :3] += rng.normal(size=b['xh_lig'][:, :3].shape).astype(np.float32) * 0.5 - shift[b['lig_mask']]
+        st = edges(b)
+        assert st[5] >= 0, 'served from the lists'
+    # exact ties: a pocket on the 1e-3 grid whose pairs sit exactly on the cutoff (3-4-5 triangles), untranslated and translated
+    tie = b['xh_pocket'].copy()
+    base = np.zeros((n_p, 3), np.float32)
+    base[:, 0] = (np.arange(n_p) % 10) * 3.0
+    base[:, 1] = ((np.arange(n_p) // 10) % 6) * 4.0
+    base[:, 2] = (np.arange(n_p) // 60) * 5.0
+    for s in range(B):
+        tie[s * n_p:(s + 1) * n_p, :3] = base + np.float32(0.125 * s)
+    bt = dict(b, xh_pocket=tie)
+    st = edges(bt)
+    assert st[5] == -1, 'deformed pocket: lists are stale, the call scans everything'
+    st = edges(bt)
+    assert st[5] >= 0
+    bt['xh_pocket'] = tie.copy()
+    bt['xh_pocket'][:, :3] += np.float32(7.0)
+    assert edges(bt)[5] >= 0
+    # one atom moves by 0.05 A: stale; a row denser than the list capacity: that row scans everything, the others use their lists
+    bt['xh_pocket'][5, 0] += np.float32(0.05)
+    assert edges(bt)[5] == -1
+    dense = b['xh_pocket'].copy()
+    dense[:100, :3] = (rng.normal(size=(100, 3)) * 0.6).astype(np.float32)         # 100 atoms inside ~2 A: > 64 neighbours each
+    bd = dict(b, xh_pocket=dense)
+    edges(bd)
+    st = edges(bd)
+    assert st[0] == 1 and st[1] == 0 and st[5] == -1                  # first pocket row is one of the dense ones
+    # another layout (one sample fewer) and back
+    keep_l, keep_p = b['lig_mask'] < 3, b['pocket_mask'] < 3
+    b3 = {'xh_lig': b['xh_lig'][keep_l], 'xh_pocket': b['xh_pocket'][keep_p], 'lig_mask': b['lig_mask'][keep_l], 'pocket_mask': b['pocket_mask'][keep_p]}
+    rp, col = eng.radius_graph(_t(b3['xh_lig'], dev), _t(b3['xh_pocket'], dev), _t(b3['lig_mask'], dev), _t(b3['pocket_mask'], dev), 3)
+    ref = O.get_edges(b3['lig_mask'], b3['pocket_mask'], b3['xh_lig'][:, :3], b3['xh_pocket'][:, :3], CFG)
+    assert np.array_equal(_edges_from_csr(rp.cpu().numpy(), col.cpu().numpy()), ref) and eng.pocket_list_state()[5] == -1
+    assert edges(b)[5] == -1 and edges(b)[5] >= 0
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # (ii) forward: golden vectors from the reference (fp64 truth) + per-block trace vs the oracle
 # ---------------------------------------------------------------------------------------------------------------
