@@ -352,7 +352,7 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
             for (int j = 0; j < hid; ++j) {
                 double s = 0;
                 for (int m = 0; m < J; ++m) s += (double)emb_w[k * (J + 1) + m] * (double)w2[m * hid + j];
-                wc2[(size_t)k * hid + j] = (float)s;
+                wc2[(size_t)j * H + k] = (float)s;           // stored transposed [hid][256]: thread k's loads coalesce
             }
             double s = emb_b[k];
             for (int m = 0; m < J; ++m) s += (double)emb_w[k * (J + 1) + m] * (double)b2[m];

@@ -14,7 +14,7 @@ namespace dndm {
 struct EncoderWeights {
     const float* w1;    // [hid, nf]
     const float* b1;    // [hid]
-    const float* wc2;   // [256, hid]   = W_emb[:, :J] W_enc2
+    const float* wc2;   // [hid, 256]   = (W_emb[:, :J] W_enc2)^T -- transposed so that the 256 threads of a CTA read it coalesced
     const float* bc;    // [256]        = W_emb[:, :J] b_enc2 + b_emb
     const float* wt;    // [256]        = W_emb[:, J]
     int nf, hid;
@@ -64,7 +64,7 @@ encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ 
     if (k < nn) s_t[k] = t[t_len == 1 ? 0 : node_sample[first + k]];
     float wrow[ENC_MAX_HID];
 #pragma unroll
-    for (int j = 0; j < ENC_MAX_HID; ++j) wrow[j] = (j < hid) ? w.wc2[k * hid + j] : 0.f;
+    for (int j = 0; j < ENC_MAX_HID; ++j) wrow[j] = (j < hid) ? w.wc2[j * 256 + k] : 0.f;
     const float wt = w.wt[k], bc = w.bc[k];
     __syncthreads();
 
