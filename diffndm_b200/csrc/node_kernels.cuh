@@ -62,9 +62,11 @@ encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ 
     }
     for (int q = k; q < hid * nf; q += 256) s_w1[q / nf][q % nf] = w.w1[q];
     if (k < nn) s_t[k] = t[t_len == 1 ? 0 : node_sample[first + k]];
-    float wrow[ENC_MAX_HID];
+    // this thread's row of Wc2 as fp32 pairs (j, j + 1): phase 2 runs on FFMA2, two partial sums (even / odd j) per output
+    uint64_t wrow2[ENC_MAX_HID / 2];
 #pragma unroll
-    for (int j = 0; j < ENC_MAX_HID; ++j) wrow[j] = (j < hid) ? w.wc2[j * 256 + k] : 0.f;
+    for (int j = 0; j < ENC_MAX_HID; j += 2)
+        wrow2[j / 2] = f2_pack((j < hid) ? w.wc2[j * 256 + k] : 0.f, (j + 1 < hid) ? w.wc2[(j + 1) * 256 + k] : 0.f);
     const float wt = w.wt[k], bc = w.bc[k];
     __syncthreads();
 
@@ -85,15 +87,16 @@ encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ 
 
     // phase 2
     for (int i = 0; i < nn; ++i) {
-        float o = fmaf(wt, s_t[i], bc);
+        uint64_t acc = f2_pack(fmaf(wt, s_t[i], bc), 0.f);
 #pragma unroll
         for (int j = 0; j < ENC_MAX_HID; j += 4) {
-            const float4 sv = *reinterpret_cast<const float4*>(&s_hid[i][j]);
-            o = fmaf(wrow[j], sv.x, o);
-            o = fmaf(wrow[j + 1], sv.y, o);
-            o = fmaf(wrow[j + 2], sv.z, o);
-            o = fmaf(wrow[j + 3], sv.w, o);
+            const ulonglong2 sv = *reinterpret_cast<const ulonglong2*>(&s_hid[i][j]);      // (h_j, h_j+1), (h_j+2, h_j+3)
+            acc = f2_fma(wrow2[j / 2], sv.x, acc);
+            acc = f2_fma(wrow2[j / 2 + 1], sv.y, acc);
         }
+        float o_even, o_odd;
+        f2_unpack(acc, o_even, o_odd);
+        const float o = o_even + o_odd;
         const int node = first + i;
         h[(size_t)node * 256 + k] = o;
         hcat[(size_t)node * 512 + k] = __float2bfloat16_rn(o);
@@ -114,9 +117,21 @@ coord_update_kernel(const float* __restrict__ x_cur, float* __restrict__ x_next,
     const int lane = threadIdx.x & 31;
     pdl_trigger();                               // the next block's edge kernel sets up under this kernel
     if (i >= n_lig) return;
+    // Loads are issued in three dependency levels so that one warp's latency chain -- the whole kernel is a single partial
+    // wave of warps -- is three round trips instead of six: (1) row range, sample, own position; (2) the first 32 edges'
+    // sender / phi / psi and the sample's ranges; (3) sender positions and the sample's ligand positions.
+    const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
     const int b = node_sample[i];
-    // per-sample mean over ligand + pocket atoms of the CURRENT coordinates (coord2cross)
+    const float xi = x_cur[3 * i], yi = x_cur[3 * i + 1], zi = x_cur[3 * i + 2];
+    const int ef = e0 + lane;
+    const bool have = ef < e1;
+    const int jf = have ? ecol[ef] : i;
+    const float phf = have ? phi[ef] : 0.f, psf = have ? psi[ef] : 0.f;
     const int l0 = lig_ptr[b], l1 = lig_ptr[b + 1];
+    const float cnt = (float)((l1 - l0) + (pok_ptr[b + 1] - pok_ptr[b]));
+    const float psx = pocket_sum[3 * b], psy = pocket_sum[3 * b + 1], psz = pocket_sum[3 * b + 2];
+    const float xjf = x_cur[3 * jf], yjf = x_cur[3 * jf + 1], zjf = x_cur[3 * jf + 2];
+    // per-sample mean over ligand + pocket atoms of the CURRENT coordinates (coord2cross)
     float sx = 0.f, sy = 0.f, sz = 0.f;
     for (int j = l0 + lane; j < l1; j += 32) {
         sx += x_cur[3 * j]; sy += x_cur[3 * j + 1]; sz += x_cur[3 * j + 2];
@@ -127,26 +142,25 @@ coord_update_kernel(const float* __restrict__ x_cur, float* __restrict__ x_next,
         sy += __shfl_xor_sync(0xffffffffu, sy, o);
         sz += __shfl_xor_sync(0xffffffffu, sz, o);
     }
-    const float cnt = (float)((l1 - l0) + (pok_ptr[b + 1] - pok_ptr[b]));
-    const float mx = (sx + pocket_sum[3 * b]) / cnt, my = (sy + pocket_sum[3 * b + 1]) / cnt,
-                mz = (sz + pocket_sum[3 * b + 2]) / cnt;
-    const float xi = x_cur[3 * i], yi = x_cur[3 * i + 1], zi = x_cur[3 * i + 2];
+    const float mx = (sx + psx) / cnt, my = (sy + psy) / cnt, mz = (sz + psz) / cnt;
     const float ax = xi - mx, ay = yi - my, az = zi - mz;
     float tx = 0.f, ty = 0.f, tz = 0.f;
-    const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
-    for (int e = e0 + lane; e < e1; e += 32) {
-        const int j = ecol[e];
-        const float xj = x_cur[3 * j], yj = x_cur[3 * j + 1], zj = x_cur[3 * j + 2];
+    auto edge = [&](float xj, float yj, float zj, float ph, float ps) {
         const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
         const float r = dx * dx + dy * dy + dz * dz;
         const float inv = 1.0f / (sqrtf(r + 1e-8f) + norm_constant);
         const float bx = xj - mx, by = yj - my, bz = zj - mz;
         float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
         const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + norm_constant);
-        const float f = phi[e] * inv, gq = psi[e] * cinv;
+        const float f = ph * inv, gq = ps * cinv;
         tx += dx * f + cx * gq;
         ty += dy * f + cy * gq;
         tz += dz * f + cz * gq;
+    };
+    if (have) edge(xjf, yjf, zjf, phf, psf);
+    for (int e = ef + 32; e < e1; e += 32) {
+        const int j = ecol[e];
+        edge(x_cur[3 * j], x_cur[3 * j + 1], x_cur[3 * j + 2], phi[e], psi[e]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
