@@ -619,7 +619,7 @@ static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, in
         pp_verify_kernel<<<(n + 255) / 256, 256, 0, st>>>(gp, pl, n_samples);
         COUNT_LAUNCH(1);
     }
-    const int blocks = (n_nodes * 32 + 255) / 256;
+    const int blocks = ((n_lig + (n_pocket + GR_ROWS - 1) / GR_ROWS) * 32 + 255) / 256;    // a warp per ligand row, per GR_ROWS pocket rows
     graph_rows_kernel<false><<<blocks, 256, 0, st>>>(gp, pl, e->deg, nullptr, nullptr, nullptr, nullptr, e->cfg.max_edges);
     RET_IF(exclusive_scan(e, e->deg, e->row_ptr, n_nodes, n_lig, 0, 1, st));
     graph_rows_kernel<true><<<blocks, 256, 0, st>>>(gp, pl, nullptr, e->row_ptr, e->ecol, e->erow, e->r0, e->cfg.max_edges);

@@ -109,75 +109,79 @@ __global__ void pp_commit_kernel(PocketLists c, int n_lig, int n_pocket, int n_s
     c.meta[0] = 1; c.meta[1] = 0; c.meta[2] = n_lig; c.meta[3] = n_pocket; c.meta[4] = n_samples;
 }
 
-// One warp per row.  kFill=false: deg[i] = number of neighbours.  kFill=true: write col / erow / r0.
+// kFill=false: deg[i] = number of neighbours.  kFill=true: write col / erow / r0.
+// A ligand row scans its whole sample (~350 candidates): one warp per row.  A pocket row with a candidate list tests ~23
+// ligand atoms + ~20 listed pocket atoms: a whole warp per row spent most of its ~200 instructions on per-row set-up (7.4 M +
+// 9.0 M warp instructions per call for 35 k rows), so GR_ROWS pocket rows share a warp -- each row's 8 lanes stride its
+// candidates, the warp ballot is cut into the row's byte, and the compaction keeps ascending order exactly as before.
+constexpr int GR_ROWS = 4;
+
 template <bool kFill>
 __global__ void __launch_bounds__(256)
-graph_rows_kernel(GraphParams p, PocketLists c, int* deg, const int* row_ptr, int* ecol, int* erow, float* r0, int max_edges) {
+graph_rows_kernel(GraphParams p, PocketLists c, int* __restrict__ deg, const int* __restrict__ row_ptr, int* __restrict__ ecol,
+                  int* __restrict__ erow, float* __restrict__ r0, int max_edges) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= p.n_nodes) return;
-    const int i = warp;
+    const float* __restrict__ x = p.x;
+    // warps [0, n_lig): one ligand row each; then GR_ROWS pocket rows per warp
+    const bool lig_warp = warp < p.n_lig;
+    const int L = lig_warp ? 32 : 32 / GR_ROWS;                      // lanes per row (warp-uniform)
+    const int g = lane / L, sl = lane % L;
+    const int i_raw = lig_warp ? warp : p.n_lig + (warp - p.n_lig) * GR_ROWS + g;
+    if ((lig_warp ? warp : p.n_lig + (warp - p.n_lig) * GR_ROWS) >= p.n_nodes) return;
+    const bool row_ok = i_raw < p.n_nodes;
+    const int i = row_ok ? i_raw : p.n_nodes - 1;                    // idle groups of the last warp: harmless reads, emit nothing
     const int b = p.node_sample[i];
     const bool i_lig = i < p.n_lig;
-    const float xi = p.x[3 * i], yi = p.x[3 * i + 1], zi = p.x[3 * i + 2];
+    const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
     int out = kFill ? row_ptr[i] : 0;
     int count = 0;
-    auto emit = [&](bool ok, int j, float d2) {              // ballot compaction keeps ascending j
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (kFill) {
-            if (ok) {
-                const int pos = out + __popc(m & ((1u << lane) - 1u));
-                if (pos < max_edges) {
-                    ecol[pos] = j;
-                    erow[pos] = i;
-                    r0[pos] = d2;
-                }
-            }
-            out += __popc(m);
-        } else {
-            count += __popc(m);
-        }
-    };
     // pocket row with a valid candidate list: the pocket part of the row is the exact test over the list
     int n_list = -1;
     if (!i_lig && c.meta != nullptr && c.meta[0] == 1 && c.meta[1] == 0 && p.cut2_p >= 0.f) {
         const int n = c.cnt[i - p.n_lig];
         if (n != 0xFFFF) n_list = n;
     }
-    if (!kFill && i == p.n_lig && lane == 0 && c.meta != nullptr) c.meta[5] = n_list;   // introspection: did this call use the lists
-#pragma unroll 1
-    for (int part = 0; part < 2; ++part) {
-        const int beg = part == 0 ? p.lig_ptr[b] : p.n_lig + p.pok_ptr[b];
-        const int end = part == 0 ? p.lig_ptr[b + 1] : p.n_lig + p.pok_ptr[b + 1];
-        const float cut2 = part == 0 ? (i_lig ? p.cut2_l : p.cut2_i) : (i_lig ? p.cut2_i : p.cut2_p);
-        if (part == 1 && n_list >= 0) {
-            const unsigned short* lst = c.cand + (size_t)(i - p.n_lig) * PP_CAP;
-            for (int k0 = 0; k0 < n_list; k0 += 32) {
-                const int k = k0 + lane;
-                bool ok = false;
-                float d2 = 0.f;
-                int j = 0;
-                if (k < n_list) {
-                    j = beg + lst[k];
-                    d2 = dist2_rn(xi, yi, zi, p.x[3 * j], p.x[3 * j + 1], p.x[3 * j + 2]);
-                    ok = d2 <= cut2;
-                }
-                emit(ok, j, d2);
-            }
-            continue;
-        }
-        for (int j0 = beg; j0 < end; j0 += 32) {
-            const int j = j0 + lane;
+    if (!kFill && row_ok && i == p.n_lig && sl == 0 && c.meta != nullptr) c.meta[5] = n_list;   // introspection: did this call use the lists
+    const unsigned row_bits = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
+    // candidates k = 0 .. n - 1 of this row, candidate index -> atom through `atom(k)`, ascending
+    auto scan = [&](int n, float cut2, auto atom) {
+        const int n_max = __reduce_max_sync(0xffffffffu, row_ok ? n : 0);
+#pragma unroll 2
+        for (int k0 = 0; k0 < n_max; k0 += L) {
+            const int k = k0 + sl;
             bool ok = false;
             float d2 = 0.f;
-            if (j < end) {
-                d2 = dist2_rn(xi, yi, zi, p.x[3 * j], p.x[3 * j + 1], p.x[3 * j + 2]);
+            int j = 0;
+            if (row_ok && k < n) {
+                j = atom(k);
+                d2 = dist2_rn(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2]);
                 ok = (cut2 < 0.f) || (d2 <= cut2);
             }
-            emit(ok, j, d2);
+            const unsigned m = (__ballot_sync(0xffffffffu, ok) >> (g * L)) & row_bits;
+            if (kFill) {
+                if (ok) {
+                    const int pos = out + __popc(m & ((1u << sl) - 1u));
+                    if (pos < max_edges) {
+                        ecol[pos] = j;
+                        erow[pos] = i;
+                        r0[pos] = d2;
+                    }
+                }
+                out += __popc(m);
+            } else {
+                count += __popc(m);
+            }
         }
-    }
-    if (!kFill && lane == 0) deg[i] = count;
+    };
+    const int lb = p.lig_ptr[b], pb = p.n_lig + p.pok_ptr[b];
+    scan(p.lig_ptr[b + 1] - lb, i_lig ? p.cut2_l : p.cut2_i, [&](int k) { return lb + k; });
+    // rows with and without a list can share a warp, and `scan` is warp-collective: every lane walks through both pocket
+    // scans, a row takes part in one of them (the other has n = 0 for it)
+    const unsigned short* __restrict__ lst = c.cand + (size_t)(i_lig ? 0 : i - p.n_lig) * PP_CAP;
+    scan(n_list >= 0 ? n_list : 0, p.cut2_p, [&](int k) { return pb + (int)lst[k]; });
+    scan(n_list >= 0 ? 0 : p.pok_ptr[b + 1] - p.pok_ptr[b], i_lig ? p.cut2_i : p.cut2_p, [&](int k) { return pb + k; });
+    if (!kFill && row_ok && sl == 0) deg[i] = count;
 }
 
 // Exclusive scan of deg[0..n) -> row_ptr[0..n] in three small launches (reduce / scan of block sums / rescan):
