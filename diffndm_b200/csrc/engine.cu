@@ -359,10 +359,34 @@ extern "C" int dndm_engine_load_weights(DndmEngine* e, const DndmWeight* weights
             bc[k] = (float)s;
             wt[k] = emb_w[k * (J + 1) + J];
         }
-        float *d1, *d2, *d3, *d4, *d5;
+        // one-hot inputs (every pocket atom / residue): the whole encoder is a table lookup.  tb[s][type][k] = the embedding of
+        // enc2(SiLU(enc1(v_s e_type))) without the time term, evaluated in fp64 from the reference's own formula, for the two
+        // scales a one-hot row arrives in: v = 1 (raw) and v = 1/4 (after ConditionalDDPM.normalize with the normalize_factors
+        // [1, 4] of every config, en_diffusion.py:885-900); any other row takes the general path
+        std::vector<float> tb((size_t)2 * nf * H);
+        std::vector<double> enc(J);
+        for (int sc = 0; sc < 2; ++sc) {
+            const double v = sc == 0 ? 1.0 : 0.25;
+            for (int ty = 0; ty < nf; ++ty) {
+                for (int m = 0; m < J; ++m) {
+                    double s = b2[m];
+                    for (int j = 0; j < hid; ++j) {
+                        const double a = (double)b1[j] + v * (double)w1[j * nf + ty];
+                        s += (double)w2[m * hid + j] * (a / (1.0 + std::exp(-a)));
+                    }
+                    enc[m] = s;
+                }
+                for (int k = 0; k < H; ++k) {
+                    double s = emb_b[k];
+                    for (int m = 0; m < J; ++m) s += (double)emb_w[k * (J + 1) + m] * enc[m];
+                    tb[((size_t)sc * nf + ty) * H + k] = (float)s;
+                }
+            }
+        }
+        float *d1, *d2, *d3, *d4, *d5, *d6;
         RET_IF(upload(e, hw1, &d1)); RET_IF(upload(e, hb1, &d2)); RET_IF(upload(e, wc2, &d3));
-        RET_IF(upload(e, bc, &d4)); RET_IF(upload(e, wt, &d5));
-        *ew = EncoderWeights{d1, d2, d3, d4, d5, nf, hid};
+        RET_IF(upload(e, bc, &d4)); RET_IF(upload(e, wt, &d5)); RET_IF(upload(e, tb, &d6));
+        *ew = EncoderWeights{d1, d2, d3, d4, d5, d6, nf, hid};
         return DNDM_OK;
     };
     RET_IF(pack_encoder("atom_encoder", A, &e->enc_l));
@@ -696,7 +720,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     // ---- feature branch: encoder + embedding, first-layer projections of block 0's edge model (pq columns [0,512)) ----
     {
         ProfScope ps(e, PROF_NODE, st);
-        const int lig_ctas = (n_lig + ENC_NODES_PER_CTA - 1) / ENC_NODES_PER_CTA;
+        const int lig_ctas = (n_lig + ENC_LIG_NODES_PER_CTA - 1) / ENC_LIG_NODES_PER_CTA;
         const int pok_ctas = (n_pocket + ENC_NODES_PER_CTA - 1) / ENC_NODES_PER_CTA;
         if (2 * A <= 32 && 2 * R <= 32)
             encode_embed_kernel<32><<<lig_ctas + pok_ctas, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len,

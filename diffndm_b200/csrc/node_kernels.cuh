@@ -17,6 +17,7 @@ struct EncoderWeights {
     const float* wc2;   // [hid, 256]   = (W_emb[:, :J] W_enc2)^T -- transposed so that the 256 threads of a CTA read it coalesced
     const float* bc;    // [256]        = W_emb[:, :J] b_enc2 + b_emb
     const float* wt;    // [256]        = W_emb[:, J]
+    const float* tb;    // [2, nf, 256] the encoder + embedding of the scaled one-hot input v e_type (v = 1, 1/4), without the time term
     int nf, hid;
 };
 
@@ -25,7 +26,8 @@ struct EncoderWeights {
 // Phase 2: thread k keeps its row of Wc2 (<= 32 floats), w_t and bc in registers and walks the nodes; the hidden
 // activations are warp-broadcast 128-bit shared loads, the stores are fully coalesced (fp32 h and the bf16 copy).
 // CTAs [0, lig_ctas) take ligand atoms, the rest pocket atoms (different encoder weights).
-constexpr int ENC_NODES_PER_CTA = 64;
+constexpr int ENC_NODES_PER_CTA = 64;       // pocket CTAs (table lookups: bound by their stores)
+constexpr int ENC_LIG_NODES_PER_CTA = 16;   // ligand CTAs run the general path, a serial loop over the CTA's nodes: keep it short
 constexpr int ENC_MAX_NF = 32;
 
 // kMaxHid: compile-time bound of the encoders' hidden width 2 * nf (32 for the full-atom vocabularies, 64 for the 20 amino
@@ -40,10 +42,12 @@ encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ 
     __shared__ float s_in[ENC_NODES_PER_CTA][ENC_MAX_NF + 4];
     __shared__ float s_w1[ENC_MAX_HID][ENC_MAX_NF + 1];
     __shared__ float s_t[ENC_NODES_PER_CTA];
+    __shared__ int s_type[ENC_NODES_PER_CTA];
     const bool is_lig = (int)blockIdx.x < lig_ctas;
     const EncoderWeights& w = is_lig ? wl : wp;
-    const int first = is_lig ? blockIdx.x * ENC_NODES_PER_CTA : n_lig + (blockIdx.x - lig_ctas) * ENC_NODES_PER_CTA;
-    const int last = min(first + ENC_NODES_PER_CTA, is_lig ? n_lig : n_nodes);
+    const int npc = is_lig ? ENC_LIG_NODES_PER_CTA : ENC_NODES_PER_CTA;
+    const int first = is_lig ? blockIdx.x * npc : n_lig + (blockIdx.x - lig_ctas) * npc;
+    const int last = min(first + npc, is_lig ? n_lig : n_nodes);
     const int nn = last - first;
     const int k = threadIdx.x;
     const int hid = w.hid, nf = w.nf;
@@ -60,20 +64,46 @@ encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ 
             x0[3 * node + c] = v; xa[3 * node + c] = v; xb[3 * node + c] = v;
         }
     }
-    for (int q = k; q < hid * nf; q += 256) s_w1[q / nf][q % nf] = w.w1[q];
     if (k < nn) s_t[k] = t[t_len == 1 ? 0 : node_sample[first + k]];
+    __syncthreads();
+    // A node whose features are a one-hot row (times 1 or 1/4) -- every pocket atom / residue -- takes its embedding from the table
+    // (h = tb[type] + w_t t): 256 FMAs per node instead of 8 192.  The decision is per node, so a node's result does not
+    // depend on which other nodes share its CTA.
+    int my_general = 0;
+    if (k < nn) {
+        int ty = -1, nonzero = 0;
+        float val = 0.f;
+        for (int q = 0; q < nf; ++q) {
+            const float v = s_in[k][3 + q];
+            if (v != 0.0f) { ty = q; val = v; ++nonzero; }         // NaN counts as a non-zero that matches no table
+        }
+        const int sc = val == 1.0f ? 0 : (val == 0.25f ? 1 : -1);
+        s_type[k] = (nonzero == 1 && sc >= 0) ? sc * nf + ty : -1;
+        my_general = s_type[k] < 0;
+    }
+    const bool any_general = __syncthreads_or(my_general);
+    const float wt = w.wt[k], bc = w.bc[k];
+    if (!any_general) {
+        for (int i = 0; i < nn; ++i) {
+            const float o = fmaf(wt, s_t[i], __ldg(w.tb + s_type[i] * 256 + k));
+            const int node = first + i;
+            h[(size_t)node * 256 + k] = o;
+            hcat[(size_t)node * 512 + k] = __float2bfloat16_rn(o);
+        }
+        return;
+    }
+    for (int q = k; q < hid * nf; q += 256) s_w1[q / nf][q % nf] = w.w1[q];
     // this thread's row of Wc2 as fp32 pairs (j, j + 1): phase 2 runs on FFMA2, two partial sums (even / odd j) per output
     uint64_t wrow2[ENC_MAX_HID / 2];
 #pragma unroll
     for (int j = 0; j < ENC_MAX_HID; j += 2)
         wrow2[j / 2] = f2_pack((j < hid) ? w.wc2[j * 256 + k] : 0.f, (j + 1 < hid) ? w.wc2[(j + 1) * 256 + k] : 0.f);
-    const float wt = w.wt[k], bc = w.bc[k];
     __syncthreads();
 
-    // phase 1: thread -> (node i = k % 64, units j = k / 64 + 4 u)
+    // phase 1: thread -> (node i = k % npc, units j = k / npc + (256 / npc) u)
     {
-        const int i = k & (ENC_NODES_PER_CTA - 1);
-        for (int j = k / ENC_NODES_PER_CTA; j < ENC_MAX_HID; j += 256 / ENC_NODES_PER_CTA) {
+        const int i = k & (npc - 1);
+        for (int j = k / npc; j < ENC_MAX_HID; j += 256 / npc) {
             float a = 0.f;
             if (i < nn && j < hid) {
                 a = w.b1[j];
@@ -87,16 +117,21 @@ encode_embed_kernel(const float* __restrict__ xh_lig, const float* __restrict__ 
 
     // phase 2
     for (int i = 0; i < nn; ++i) {
-        uint64_t acc = f2_pack(fmaf(wt, s_t[i], bc), 0.f);
+        float o;
+        if (s_type[i] >= 0) {
+            o = fmaf(wt, s_t[i], __ldg(w.tb + s_type[i] * 256 + k));
+        } else {
+            uint64_t acc = f2_pack(fmaf(wt, s_t[i], bc), 0.f);
 #pragma unroll
-        for (int j = 0; j < ENC_MAX_HID; j += 4) {
-            const ulonglong2 sv = *reinterpret_cast<const ulonglong2*>(&s_hid[i][j]);      // (h_j, h_j+1), (h_j+2, h_j+3)
-            acc = f2_fma(wrow2[j / 2], sv.x, acc);
-            acc = f2_fma(wrow2[j / 2 + 1], sv.y, acc);
+            for (int j = 0; j < ENC_MAX_HID; j += 4) {
+                const ulonglong2 sv = *reinterpret_cast<const ulonglong2*>(&s_hid[i][j]);      // (h_j, h_j+1), (h_j+2, h_j+3)
+                acc = f2_fma(wrow2[j / 2], sv.x, acc);
+                acc = f2_fma(wrow2[j / 2 + 1], sv.y, acc);
+            }
+            float o_even, o_odd;
+            f2_unpack(acc, o_even, o_odd);
+            o = o_even + o_odd;
         }
-        float o_even, o_odd;
-        f2_unpack(acc, o_even, o_odd);
-        const float o = o_even + o_odd;
         const int node = first + i;
         h[(size_t)node * 256 + k] = o;
         hcat[(size_t)node * 512 + k] = __float2bfloat16_rn(o);
