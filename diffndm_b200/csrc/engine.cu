@@ -627,7 +627,10 @@ static int build_last_block_edges(DndmEngine* e, int n_lig, int n_nodes, cudaStr
     return DNDM_OK;
 }
 
-static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, int n_samples, cudaStream_t st) {
+// xh_lig / xh_pocket: the call's inputs (rows of 3 + atom_nf / 3 + residue_nf floats); x: [N,3] scratch the coordinates are
+// gathered into (read by the row kernels and by refresh_pocket_lists)
+static int build_graph(DndmEngine* e, const float* xh_lig, const float* xh_pocket, float* x, int n_lig, int n_nodes,
+                       int n_samples, cudaStream_t st) {
     GraphParams gp;
     gp.x = x; gp.lig_ptr = e->lig_ptr; gp.pok_ptr = e->pok_ptr; gp.node_sample = e->node_sample;
     gp.n_lig = n_lig; gp.n_nodes = n_nodes;
@@ -638,9 +641,10 @@ static int build_graph(DndmEngine* e, const float* x, int n_lig, int n_nodes, in
     const bool lists = n_pocket > 0 && g_pp_lists;
     PocketLists pl = e->pp;
     if (!lists) pl.meta = nullptr;
-    if (lists) {
-        const int n = n_pocket > n_samples + 1 ? n_pocket : n_samples + 1;
-        pp_verify_kernel<<<(n + 255) / 256, 256, 0, st>>>(gp, pl, n_samples);
+    {
+        const int n = n_nodes > n_samples + 1 ? n_nodes : n_samples + 1;
+        gather_verify_kernel<<<(n + 255) / 256, 256, 0, st>>>(xh_lig, xh_pocket, 3 + e->cfg.atom_nf, 3 + e->cfg.residue_nf, gp, pl,
+                                                            n_samples, x);
         COUNT_LAUNCH(1);
     }
     const int blocks = ((n_lig + (n_pocket + GR_ROWS - 1) / GR_ROWS) * 32 + 255) / 256;    // a warp per ligand row, per GR_ROWS pocket rows
@@ -674,8 +678,7 @@ static int refresh_pocket_lists(DndmEngine* e, const float* x, int n_lig, int n_
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void gather_xyz_kernel(const float* xh_lig, const float* xh_pok, int n_lig, int n_nodes, int ld_lig, int ld_pok,
-                                  float* x);
+
 
 extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float* xh_pocket, const float* t, int32_t t_len,
                                  const int64_t* lig_mask, const int64_t* pocket_mask, int32_t n_lig, int32_t n_pocket,
@@ -703,10 +706,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     }
     {
         ProfScope ps(e, PROF_GRAPH, gs);
-        gather_xyz_kernel<<<(N * 3 + 255) / 256, 256, 0, gs>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, e->xg);
-        pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, gs>>>(e->xg, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
-        COUNT_LAUNCH(2);
-        RET_IF(build_graph(e, e->xg, n_lig, N, n_samples, gs));
+        RET_IF(build_graph(e, xh_lig, xh_pocket, e->xg, n_lig, N, n_samples, gs));
         if (fork) CU_CHECK(cudaEventRecord(e->ev_join, gs));   // blocks 0..L-2 only need the full graph
         // the compacted edge list is first read by the LAST block: it keeps running on the side stream under block 0
         if (prune_last) RET_IF(build_last_block_edges(e, n_lig, N, gs));
@@ -730,7 +730,10 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
             encode_embed_kernel<64><<<lig_ctas + pok_ctas, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + A, 3 + R, t, t_len,
                                                                          e->node_sample, e->enc_l, e->enc_p, lig_ctas, e->x0, e->xa,
                                                                          e->xb, e->h, e->hcat);
-        COUNT_LAUNCH(1);
+        // per-sample sums of the (frozen) pocket coordinates for coord2cross: reads the coordinates the encoder just assembled;
+        // on this stream, where the head of the step has slack (the graph branch is the longer one)
+        pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, st>>>(e->x0, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
+        COUNT_LAUNCH(2);
     }
     float* x_cur = e->xa;
     float* x_next = e->xb;
@@ -825,13 +828,6 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
 // ------------------------------------------------------------------------------------------------
 // radius graph on its own
 // ------------------------------------------------------------------------------------------------
-__global__ void gather_xyz_kernel(const float* xh_lig, const float* xh_pok, int n_lig, int n_nodes, int ld_lig, int ld_pok,
-                                  float* x) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes * 3) return;
-    const int node = i / 3, d = i % 3;
-    x[i] = node < n_lig ? xh_lig[(size_t)node * ld_lig + d] : xh_pok[(size_t)(node - n_lig) * ld_pok + d];
-}
 
 extern "C" int dndm_radius_graph(DndmEngine* e, const float* xh_lig, const float* xh_pocket, const int64_t* lig_mask,
                                  const int64_t* pocket_mask, int32_t n_lig, int32_t n_pocket, int32_t n_samples,
@@ -840,10 +836,7 @@ extern "C" int dndm_radius_graph(DndmEngine* e, const float* xh_lig, const float
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     RET_IF(prepare_batch(e, lig_mask, pocket_mask, n_lig, n_pocket, n_samples, st));
     const int N = n_lig + n_pocket;
-    gather_xyz_kernel<<<(N * 3 + 255) / 256, 256, 0, st>>>(xh_lig, xh_pocket, n_lig, N, 3 + e->cfg.atom_nf, 3 + e->cfg.residue_nf,
-                                                           e->x0);
-    COUNT_LAUNCH(1);
-    RET_IF(build_graph(e, e->x0, n_lig, N, n_samples, st));
+    RET_IF(build_graph(e, xh_lig, xh_pocket, e->x0, n_lig, N, n_samples, st));
     RET_IF(refresh_pocket_lists(e, e->x0, n_lig, N, n_samples, st));
     int sc[2] = {0, 0};
     CU_CHECK(cudaMemcpyAsync(sc, e->scalars, 8, cudaMemcpyDeviceToHost, st));

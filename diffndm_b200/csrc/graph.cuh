@@ -35,7 +35,7 @@ DNDM_DEVICE float dist2_rn(float ax, float ay, float az, float bx, float by, flo
 // from the coordinates of some earlier call, and the row kernels run the EXACT test of the current call -- same arithmetic,
 // same order -- on that list only.  Nothing is promised by the caller: every call first verifies on the device that the
 // batch layout is the one the lists were built for and that every pocket atom still sits, relative to its sample's first
-// pocket atom, within PP_TOL of where it sat then (pp_verify_kernel); if not, this call scans everything as before and
+// pocket atom, within PP_TOL of where it sat then (gather_verify_kernel); if not, this call scans everything as before and
 // rebuilds the lists afterwards (pp_rebuild_kernel, off the critical path).  A pair within the cutoff now was within
 // cutoff + 2 PP_TOL then, so the lists are a superset and the emitted edge set is bit-identical; the translation rounding of
 // a 500-step trajectory moves atoms by ~1e-4 A relative to each other.  All of it is device-side: it replays in a CUDA graph.
@@ -52,21 +52,29 @@ struct PocketLists {
     unsigned short* cnt;     // [n_pocket]
 };
 
+// Gathers the coordinates of all nodes ([ligand ; pocket] rows of the two input tensors) into x [N,3] for the graph branch
+// and, in the same pass, checks the candidate lists against this call: thread = node.
 __global__ void __launch_bounds__(256)
-pp_verify_kernel(GraphParams p, PocketLists c, int n_samples) {
-    if (c.meta[0] == 0) return;
+gather_verify_kernel(const float* __restrict__ xh_lig, const float* __restrict__ xh_pok, int ld_lig, int ld_pok, GraphParams p,
+                     PocketLists c, int n_samples, float* __restrict__ x) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_pocket = p.n_nodes - p.n_lig;
+    if (t < p.n_nodes) {
+        const float* src = t < p.n_lig ? xh_lig + (size_t)t * ld_lig : xh_pok + (size_t)(t - p.n_lig) * ld_pok;
+        x[3 * t] = src[0]; x[3 * t + 1] = src[1]; x[3 * t + 2] = src[2];
+    }
+    if (c.meta == nullptr || c.meta[0] == 0) return;
     bool stale = false;
     if (t == 0) stale = c.meta[2] != p.n_lig || c.meta[3] != n_pocket || c.meta[4] != n_samples;
     if (t <= n_samples) stale |= c.ptr[t] != p.pok_ptr[t];
     if (t < n_pocket) {
-        const int j = p.n_lig + t;
-        const int f = p.pok_ptr[p.node_sample[j]];           // the sample's first pocket atom (pocket-local index)
+        const int f = p.pok_ptr[p.node_sample[p.n_lig + t]];    // the sample's first pocket atom (pocket-local index)
+        const float* me = xh_pok + (size_t)t * ld_pok;
+        const float* first = xh_pok + (size_t)f * ld_pok;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float d = (p.x[3 * j + k] - p.x[3 * (p.n_lig + f) + k]) - (c.canon[3 * t + k] - c.canon[3 * f + k]);
-            stale |= !(fabsf(d) <= PP_TOL);                  // NaN counts as moved
+            const float d = (me[k] - first[k]) - (c.canon[3 * t + k] - c.canon[3 * f + k]);
+            stale |= !(fabsf(d) <= PP_TOL);                      // NaN counts as moved
         }
     }
     if (stale) c.meta[1] = 1;
