@@ -164,7 +164,7 @@ struct DndmEngine {
     int last_n_lig = 0, last_n_nodes = 0;
     float* x_final = nullptr;
     // trace
-    float *h_trace = nullptr, *x_trace = nullptr;
+    float *h_trace = nullptr, *x_trace = nullptr, *h0_snap = nullptr;
     int max_trace_nodes = 0;
     // per-section CUDA-event profiling (off by default; never used under graph capture)
     bool profile = false;
@@ -285,7 +285,7 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->msg, e->att, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
                     e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->deg_act, e->rp_act, e->erow_c,
-                    e->ecol_c, e->r0_c, e->flags, e->xg, e->mol_off, e->pp.canon, e->pp.ptr, e->pp.meta, e->pp.cand, e->pp.cnt};
+                    e->ecol_c, e->r0_c, e->flags, e->xg, e->mol_off, e->h0_snap, e->pp.canon, e->pp.ptr, e->pp.meta, e->pp.cand, e->pp.cnt};
     for (void* p : bufs) cudaFree(p);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -734,6 +734,8 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         // on this stream, where the head of the step has slack (the graph branch is the longer one)
         pocket_sum_kernel<<<(n_samples * 32 + 255) / 256, 256, 0, st>>>(e->x0, e->pok_ptr, n_lig, n_samples, e->pocket_sum);
         COUNT_LAUNCH(2);
+        if (e->h0_snap && N <= e->max_trace_nodes)
+            CU_CHECK(cudaMemcpyAsync(e->h0_snap, e->h, (size_t)N * 256 * 4, cudaMemcpyDeviceToDevice, st));
     }
     float* x_cur = e->xa;
     float* x_next = e->xb;
@@ -927,6 +929,9 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
         }
         case 4: src = e->scalars; bytes = 16; break;
         case 7: src = e->pp.meta; bytes = 32; break;
+        case 8:
+            if (!e->h0_snap) return set_err(DNDM_EINVAL, "buffer 8 (h_0) exists only while a trace is set");
+            src = e->h0_snap; bytes = N * 256 * 4; break;
 #ifdef DNDM_EK_TRACE
         case 6: {
             bytes = sizeof(g_wr_trace) < (size_t)dst_bytes ? sizeof(g_wr_trace) : dst_bytes;
@@ -979,6 +984,9 @@ extern "C" int dndm_get_profile(DndmEngine* e, double* ms_per_category, int32_t*
 extern "C" int dndm_set_trace(DndmEngine* e, float* h_trace, float* x_trace, int32_t max_trace_nodes) {
     if (!e) return set_err(DNDM_EINVAL, "null argument");
     e->h_trace = h_trace; e->x_trace = x_trace; e->max_trace_nodes = max_trace_nodes;
+    // while a trace is on, the encoder output h_0 of every forward is kept as well (dndm_debug_copy buffer 8)
+    if (e->h0_snap) { cudaFree(e->h0_snap); e->h0_snap = nullptr; }
+    if (h_trace && max_trace_nodes > 0) RET_IF(dev_alloc(&e->h0_snap, (size_t)max_trace_nodes * 256));
     return DNDM_OK;
 }
 

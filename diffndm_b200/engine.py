@@ -278,6 +278,12 @@ class Engine:
         """(E, E_ligand_receiver) of the last forward / radius_graph call (synchronises)."""
         return self.graph_stats_full()[:2]
 
+    def debug_h0(self, n_nodes: int):
+        """Encoder + embedding output h_0 [n_nodes, 256] of the last forward (kept only while a trace is set)."""
+        t = torch.empty((n_nodes, 256), dtype=torch.float32, device=torch.device('cuda', self.device))
+        _check(self.lib, self.lib.dndm_debug_copy(self._h, 8, _ptr(t), t.numel() * 4, _stream()), 'dndm_debug_copy')
+        return t
+
     def pocket_list_state(self):
         """Introspection for tests: int32 [8] state of the pocket-pocket candidate lists (include/diffndm_b200.h, buffer 7)."""
         t = torch.zeros(8, dtype=torch.int32, device=torch.device('cuda', self.device))

@@ -219,6 +219,32 @@ def test_forward_vs_reference_golden(dyn, dev, name, golden_weights):
     dyn.engine.clear_trace()
 
 
+def test_encoder_table_matches_general_path(dyn, dev):
+    """One-hot pocket rows take encoder + embedding from the per-type table (fp64 at weight load, csrc/node_kernels.cuh);
+    the same rows with a 1e-30 in one of their zero entries are not one-hot any more and run the general path.  The embedded
+    features h_0 of the two calls (read back through the trace) agree to fp32 rounding, for raw rows and for rows divided by
+    the normalize factor 4."""
+    c = FWD_CASES['synth60_b3']
+    N = len(c['lig_mask']) + len(c['pocket_mask'])
+    n_l = len(c['lig_mask'])
+    pocket = c['xh_pocket'].copy()
+    hot = pocket[:, 3:].argmax(1)
+    for scale in (1.0, 0.25):
+        pocket[:, 3:] = 0.0
+        pocket[np.arange(len(pocket)), 3 + hot] = scale
+        almost = pocket.copy()
+        almost[np.arange(len(pocket)), 3 + (hot + 1) % pocket[:, 3:].shape[1]] = 1e-30
+        hs = []
+        for xp in (pocket, almost):
+            dyn.engine.set_trace(N)
+            dyn(_t(c['xh_lig'], dev), _t(xp, dev), _t(c['t'], dev), _t(c['lig_mask'], dev), _t(c['pocket_mask'], dev))
+            hs.append(dyn.engine.debug_h0(N))
+            dyn.engine.clear_trace()
+        a, b = hs[0][n_l:N].cpu().numpy(), hs[1][n_l:N].cpu().numpy()
+        assert np.abs(a - b).max() < 2e-6 * max(1.0, np.abs(b).max()), (scale, np.abs(a - b).max())
+        assert np.array_equal(hs[0][:n_l].cpu().numpy(), hs[1][:n_l].cpu().numpy())      # ligand rows: same path, same bits
+
+
 def test_forward_scalar_time_matches_per_sample_time(dyn, dev):
     c = FWD_CASES['synth60_b3']
     a, _ = dyn(_t(c['xh_lig'], dev), _t(c['xh_pocket'], dev), _t(c['t'], dev), _t(c['lig_mask'], dev), _t(c['pocket_mask'], dev))
