@@ -32,6 +32,8 @@ static long long g_launches = 0;   // kernels of this library launched (or captu
 // of the stream (see pdl_wait / pdl_trigger in common.cuh).  DNDM_PDL=0 in the environment turns the attribute off.
 // DNDM_PP_LISTS=0: every call scans all same-sample pocket atoms for every pocket row (the round-1 path; for A/B)
 static bool g_pp_lists = [] { const char* v = getenv("DNDM_PP_LISTS"); return !(v && v[0] == '0'); }();
+// DNDM_PRUNE2=0: only the last block is pruned (A/B)
+static bool g_prune2 = [] { const char* v = getenv("DNDM_PRUNE2"); return !(v && v[0] == '0'); }();
 static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] == '0'); }();
 // GCL producers: all-bf16x2 first-layer pre-activation by default; DNDM_GCL_F32_RADIAL=1 selects the variant with fp32 radial
 // terms and activation (measured on the radial stress fixture: same error to two digits, 8 % slower -- see edge_mlp.cuh)
@@ -141,6 +143,8 @@ struct DndmEngine {
     int *ecol = nullptr, *erow = nullptr, *scalars = nullptr, *block_sums = nullptr;
     int *deg_act = nullptr, *rp_act = nullptr, *erow_c = nullptr, *ecol_c = nullptr;   // last-block compacted graph
     float* r0_c = nullptr;
+    int *deg_act2 = nullptr, *rp_act2 = nullptr, *erow_c2 = nullptr, *ecol_c2 = nullptr;   // ... and the block before it (two hops)
+    float* r0_c2 = nullptr;
     PocketLists pp{};                            // pocket-pocket candidate lists (graph.cuh)
     unsigned* flags = nullptr;
     long long* mol_off = nullptr;                // [max_samples + 1] byte offsets of the per-molecule bond matrices
@@ -239,6 +243,8 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 4)); RET_IF(dev_alloc(&e->block_sums, 1024));
     RET_IF(dev_alloc(&e->deg_act, N)); RET_IF(dev_alloc(&e->rp_act, N + 1)); RET_IF(dev_alloc(&e->erow_c, E + 1));
     RET_IF(dev_alloc(&e->ecol_c, E)); RET_IF(dev_alloc(&e->r0_c, E));
+    RET_IF(dev_alloc(&e->deg_act2, N)); RET_IF(dev_alloc(&e->rp_act2, N + 1)); RET_IF(dev_alloc(&e->erow_c2, E + 1));
+    RET_IF(dev_alloc(&e->ecol_c2, E)); RET_IF(dev_alloc(&e->r0_c2, E));
     RET_IF(dev_alloc(&e->flags, 1));
     RET_IF(dev_alloc(&e->pp.canon, N * 3)); RET_IF(dev_alloc(&e->pp.ptr, B + 1)); RET_IF(dev_alloc(&e->pp.meta, 8));
     RET_IF(dev_alloc(&e->pp.cand, N * PP_CAP)); RET_IF(dev_alloc(&e->pp.cnt, N));
@@ -285,7 +291,7 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->msg, e->att, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
                     e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->deg_act, e->rp_act, e->erow_c,
-                    e->ecol_c, e->r0_c, e->flags, e->xg, e->mol_off, e->h0_snap, e->pp.canon, e->pp.ptr, e->pp.meta, e->pp.cand, e->pp.cnt};
+                    e->ecol_c, e->r0_c, e->deg_act2, e->rp_act2, e->erow_c2, e->ecol_c2, e->r0_c2, e->flags, e->xg, e->mol_off, e->h0_snap, e->pp.canon, e->pp.ptr, e->pp.meta, e->pp.cand, e->pp.cnt};
     for (void* p : bufs) cudaFree(p);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -623,6 +629,15 @@ static int build_last_block_edges(DndmEngine* e, int n_lig, int n_nodes, cudaStr
     compact_edges_kernel<<<(n_nodes * 32 + 255) / 256, 256, 0, st>>>(e->row_ptr, e->rp_act, e->erow, e->ecol, e->r0, n_nodes,
                                                                      e->erow_c, e->ecol_c, e->r0_c);
     COUNT_LAUNCH(1);
+    if (e->cfg.n_layers >= 2) {                // the block before the last: receivers of the last block + all their senders
+        mark_senders_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol_c, e->deg, e->deg_act, e->scalars, 2, n_nodes, e->deg_act2, 0);
+        mark_senders_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol_c, e->deg, e->deg_act, e->scalars, 2, n_nodes, e->deg_act2, 1);
+        COUNT_LAUNCH(2);
+        RET_IF(exclusive_scan(e, e->deg_act2, e->rp_act2, n_nodes, n_lig, 3, -1, st));
+        compact_edges_kernel<<<(n_nodes * 32 + 255) / 256, 256, 0, st>>>(e->row_ptr, e->rp_act2, e->erow, e->ecol, e->r0, n_nodes,
+                                                                         e->erow_c2, e->ecol_c2, e->r0_c2);
+        COUNT_LAUNCH(1);
+    }
     CU_CHECK(cudaGetLastError());
     return DNDM_OK;
 }
@@ -748,11 +763,15 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
     if (fork) CU_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));   // join: the edge kernels need the graph
     for (int l = 0; l < e->cfg.n_layers; ++l) {
         LayerWeights& L = e->layers[l];
+        // exact dead-work elimination (graph.cuh): the last block aggregates for the ligand rows and their pocket senders only,
+        // the block before it for those and all their senders
         const bool pruned = prune_last && (l + 1 == e->cfg.n_layers);
-        if (pruned && fork) CU_CHECK(cudaStreamWaitEvent(st, e->ev_join_last, 0));
+        const bool pruned2 = prune_last && g_prune2 && e->cfg.n_layers >= 2 && (l + 2 == e->cfg.n_layers);
+        if ((pruned2 || (pruned && !(g_prune2 && e->cfg.n_layers >= 2))) && fork) CU_CHECK(cudaStreamWaitEvent(st, e->ev_join_last, 0));
         // ---- GCL edge model + attention + deterministic aggregation ----
-        EdgeGraph g{pruned ? e->erow_c : e->erow, pruned ? e->ecol_c : e->ecol, pruned ? e->r0_c : e->r0, x_cur,
-                    e->scalars + (pruned ? 2 : 0), n_lig, 1536, e->msg, e->att};
+        EdgeGraph g{pruned ? e->erow_c : (pruned2 ? e->erow_c2 : e->erow), pruned ? e->ecol_c : (pruned2 ? e->ecol_c2 : e->ecol),
+                    pruned ? e->r0_c : (pruned2 ? e->r0_c2 : e->r0), x_cur, e->scalars + (pruned ? 2 : (pruned2 ? 3 : 0)), n_lig, 1536,
+                    e->msg, e->att};
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, L.et_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
@@ -764,7 +783,8 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         }
         {
             ProfScope ps(e, PROF_NODE, st);
-            segment_reduce_kernel<<<node_blocks, 256, 0, st>>>(e->msg, e->att, pruned ? e->rp_act : e->row_ptr, N, e->hcat);
+            segment_reduce_kernel<<<node_blocks, 256, 0, st>>>(e->msg, e->att, pruned ? e->rp_act : (pruned2 ? e->rp_act2 : e->row_ptr), N,
+                                                               e->hcat);
         }
         COUNT_LAUNCH(2);
         // ---- node MLP with residual + node projections: this block's coordinate heads (sender parts for every node, receiver

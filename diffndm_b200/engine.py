@@ -298,6 +298,13 @@ class Engine:
         e, el, ea, _ = t.cpu().tolist()
         return e, el, ea
 
+    def graph_stats_pruned(self):
+        """(E, E_ligand_receiver, E_last_block, E_second_to_last_block) of the last forward without pocket output: the edges the
+        last two blocks aggregate over (exact dead-work elimination, csrc/graph.cuh); stale otherwise."""
+        t = torch.zeros(4, dtype=torch.int32, device=torch.device('cuda', self.device))
+        _check(self.lib, self.lib.dndm_debug_copy(self._h, 4, _ptr(t), 16, _stream()), 'dndm_debug_copy')
+        return tuple(t.cpu().tolist())
+
 
 def launch_count() -> int:
     """Kernels of libdiffndm_b200 launched (or captured) by this process so far."""
