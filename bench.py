@@ -453,9 +453,8 @@ def run_b200(args):
     flags = eng.read_flags()
     if flags & (E.FLAG_EDGE_OVERFLOW | E.FLAG_NAN):
         raise RuntimeError(f'engine flags {flags} during the timed region')
-    E_edges, E_lig, E_last, E_prev = eng.graph_stats_pruned()
-    if os.environ.get('DNDM_PRUNE2') == '0' or cfg.n_layers < 2:
-        E_prev = E_edges
+    E_edges, E_lig, E_levels = eng.graph_stats_pruned()         # edges of the trailing (pruned) blocks, last block first
+    E_last = E_levels[0]
     # the workload is only valid while the ligands sit in the pocket: ligand-receiver edges (ligand-ligand + ligand<-pocket)
     # and the last block's edge list (ligand receivers + their pocket senders) as shares of all edges.  The real 3rfm
     # complex (286 pocket atoms, 23-atom ligands) has 0.13 / ~0.2-0.3; ligands that left the pocket give 0.09 / 0.10.
@@ -494,10 +493,10 @@ def run_b200(args):
         peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed per launch)'
         if peak is None:
             peak, peak_src = 1590.0, 'fallback (B200_PROFILING.md)'
-        # six launches per forward: four over all E edges, the last two over the E_prev / E_last edges that still matter
+        # six launches per forward: the trailing ones over the pruned edge lists E_levels, the others over all E edges
         # (exact dead-work elimination); achieved = executed FLOP of all timed launches / their total time
         n_layers = cfg.n_layers
-        edges_timed = (g_n // n_layers) * ((n_layers - 2) * E_edges + E_prev + E_last)
+        edges_timed = (g_n // n_layers) * ((n_layers - len(E_levels)) * E_edges + sum(E_levels))
         t_launch = g_ms / max(g_n, 1) * 1e-3
         achieved = edges_timed * EXEC_FLOP_PER_EDGE_GCL / (g_ms * 1e-3) / 1e12
         # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of this
@@ -515,7 +514,7 @@ def run_b200(args):
                 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': peak_src, 'limiter': 'XU pipe (MUFU.TANH for two SiLU per edge and channel + F2FP packs) and issue slots: see DESIGN.md section 5',
                 'us_per_launch': t_launch * 1e6, 'edges_per_launch': edges_timed / max(g_n, 1), 'edges': E_edges,
-                'edges_last_block': E_last, 'edges_second_to_last_block': E_prev,
+                'edges_last_block': E_last, 'edges_trailing_blocks': E_levels,
                 'flop_per_edge_executed': EXEC_FLOP_PER_EDGE_GCL,
                 'achieved_reference_equivalent': (g_n // n_layers) * n_layers * E_edges * REF_FLOP_PER_EDGE_GCL / (g_ms * 1e-3) / 1e12,
                 'step_share_ms': {k: v[0] / n_prof for k, v in prof.items()}}
@@ -643,7 +642,7 @@ def run_b200(args):
     if rank == 0:
         cfgd = workload_config(B)
         cfgd.update({'pocket_atoms_rank0': n_p // B, 'ligand_atoms_rank0': n_l, 'nodes': N, 'edges': E_edges,
-                     'ligand_receiver_edges': E_lig, 'edges_last_block': E_last, 'edges_second_to_last_block': E_prev,
+                     'ligand_receiver_edges': E_lig, 'edges_last_block': E_last, 'edges_trailing_blocks': E_levels,
                      'ligand_receiver_share': E_lig / E_edges, 'last_block_share': E_last / E_edges,
                      'trajectory_window_s': window, 'cuda_graph': graph is not None,
                      'score': 'eps_net + (z_t - alpha_t x_0)/sigma_t, x_0 = synthetic ligand pose in the pocket (random-init '

@@ -32,8 +32,9 @@ static long long g_launches = 0;   // kernels of this library launched (or captu
 // of the stream (see pdl_wait / pdl_trigger in common.cuh).  DNDM_PDL=0 in the environment turns the attribute off.
 // DNDM_PP_LISTS=0: every call scans all same-sample pocket atoms for every pocket row (the round-1 path; for A/B)
 static bool g_pp_lists = [] { const char* v = getenv("DNDM_PP_LISTS"); return !(v && v[0] == '0'); }();
-// DNDM_PRUNE2=0: only the last block is pruned (A/B)
-static bool g_prune2 = [] { const char* v = getenv("DNDM_PRUNE2"); return !(v && v[0] == '0'); }();
+// DNDM_PRUNE_LEVELS=<n>: how many trailing blocks run on a pruned edge list (1 = the last block only; default 2; maximum 3 --
+// three hops from the ligand cover 0.99 E of a 330-atom pocket and 0.85 E of a 600-atom one: measured equal within noise)
+static int g_prune_levels = [] { const char* v = getenv("DNDM_PRUNE_LEVELS"); const int n = v ? atoi(v) : 2; return n < 1 ? 1 : n; }();
 static bool g_pdl = [] { const char* v = getenv("DNDM_PDL"); return !(v && v[0] == '0'); }();
 // GCL producers: all-bf16x2 first-layer pre-activation by default; DNDM_GCL_F32_RADIAL=1 selects the variant with fp32 radial
 // terms and activation (measured on the radial stress fixture: same error to two digits, 8 % slower -- see edge_mlp.cuh)
@@ -141,10 +142,11 @@ struct DndmEngine {
     __nv_bfloat16 *hcat = nullptr, *hid = nullptr;
     int *node_sample = nullptr, *lig_ptr = nullptr, *pok_ptr = nullptr, *deg = nullptr, *row_ptr = nullptr;
     int *ecol = nullptr, *erow = nullptr, *scalars = nullptr, *block_sums = nullptr;
-    int *deg_act = nullptr, *rp_act = nullptr, *erow_c = nullptr, *ecol_c = nullptr;   // last-block compacted graph
-    float* r0_c = nullptr;
-    int *deg_act2 = nullptr, *rp_act2 = nullptr, *erow_c2 = nullptr, *ecol_c2 = nullptr;   // ... and the block before it (two hops)
-    float* r0_c2 = nullptr;
+    // compacted graphs of the last PRUNE_LEVELS blocks (exact dead-work elimination, graph.cuh): level k = 0 is the last block
+    // (receivers: ligand atoms + their pocket senders), level k the block k before it (level k-1's receivers + all their senders)
+    static constexpr int PRUNE_LEVELS = 3;
+    int *deg_act[PRUNE_LEVELS] = {}, *rp_act[PRUNE_LEVELS] = {}, *erow_c[PRUNE_LEVELS] = {}, *ecol_c[PRUNE_LEVELS] = {};
+    float* r0_c[PRUNE_LEVELS] = {};
     PocketLists pp{};                            // pocket-pocket candidate lists (graph.cuh)
     unsigned* flags = nullptr;
     long long* mol_off = nullptr;                // [max_samples + 1] byte offsets of the per-molecule bond matrices
@@ -240,11 +242,11 @@ extern "C" int dndm_engine_create(const DndmConfig* cfg, DndmEngine** out) {
     RET_IF(dev_alloc(&e->hcat, N * 512)); RET_IF(dev_alloc(&e->hid, N * 256));
     RET_IF(dev_alloc(&e->node_sample, N)); RET_IF(dev_alloc(&e->lig_ptr, B + 1)); RET_IF(dev_alloc(&e->pok_ptr, B + 1));
     RET_IF(dev_alloc(&e->deg, N)); RET_IF(dev_alloc(&e->row_ptr, N + 1));
-    RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 4)); RET_IF(dev_alloc(&e->block_sums, 1024));
-    RET_IF(dev_alloc(&e->deg_act, N)); RET_IF(dev_alloc(&e->rp_act, N + 1)); RET_IF(dev_alloc(&e->erow_c, E + 1));
-    RET_IF(dev_alloc(&e->ecol_c, E)); RET_IF(dev_alloc(&e->r0_c, E));
-    RET_IF(dev_alloc(&e->deg_act2, N)); RET_IF(dev_alloc(&e->rp_act2, N + 1)); RET_IF(dev_alloc(&e->erow_c2, E + 1));
-    RET_IF(dev_alloc(&e->ecol_c2, E)); RET_IF(dev_alloc(&e->r0_c2, E));
+    RET_IF(dev_alloc(&e->ecol, E)); RET_IF(dev_alloc(&e->erow, E + 1)); RET_IF(dev_alloc(&e->scalars, 8)); RET_IF(dev_alloc(&e->block_sums, 1024));
+    for (int k = 0; k < DndmEngine::PRUNE_LEVELS; ++k) {
+        RET_IF(dev_alloc(&e->deg_act[k], N)); RET_IF(dev_alloc(&e->rp_act[k], N + 1)); RET_IF(dev_alloc(&e->erow_c[k], E + 1));
+        RET_IF(dev_alloc(&e->ecol_c[k], E)); RET_IF(dev_alloc(&e->r0_c[k], E));
+    }
     RET_IF(dev_alloc(&e->flags, 1));
     RET_IF(dev_alloc(&e->pp.canon, N * 3)); RET_IF(dev_alloc(&e->pp.ptr, B + 1)); RET_IF(dev_alloc(&e->pp.meta, 8));
     RET_IF(dev_alloc(&e->pp.cand, N * PP_CAP)); RET_IF(dev_alloc(&e->pp.cnt, N));
@@ -290,9 +292,11 @@ extern "C" void dndm_engine_destroy(DndmEngine* e) {
     free_weights(e);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     void* bufs[] = {e->x0, e->xa, e->xb, e->h, e->pq, e->msg, e->att, e->r0, e->phi, e->psi, e->pocket_sum, e->hcat,
-                    e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->deg_act, e->rp_act, e->erow_c,
-                    e->ecol_c, e->r0_c, e->deg_act2, e->rp_act2, e->erow_c2, e->ecol_c2, e->r0_c2, e->flags, e->xg, e->mol_off, e->h0_snap, e->pp.canon, e->pp.ptr, e->pp.meta, e->pp.cand, e->pp.cnt};
+                    e->hid, e->node_sample, e->lig_ptr, e->pok_ptr, e->deg, e->row_ptr, e->ecol, e->erow, e->scalars, e->block_sums, e->flags, e->xg, e->mol_off, e->h0_snap, e->pp.canon, e->pp.ptr, e->pp.meta, e->pp.cand, e->pp.cnt};
     for (void* p : bufs) cudaFree(p);
+    for (int k = 0; k < DndmEngine::PRUNE_LEVELS; ++k) {
+        cudaFree(e->deg_act[k]); cudaFree(e->rp_act[k]); cudaFree(e->erow_c[k]); cudaFree(e->ecol_c[k]); cudaFree(e->r0_c[k]);
+    }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_join_last) cudaEventDestroy(e->ev_join_last);
@@ -620,22 +624,29 @@ static int exclusive_scan(DndmEngine* e, const int* deg, int* out, int n, int n_
     return DNDM_OK;
 }
 
-// compacted edge list of the receivers the LAST block still needs (ligand atoms + their pocket senders)
+// scalars: [0] E, [1] E of the ligand rows, [2 + k] E of pruning level k
+static int prune_levels(const DndmEngine* e) {
+    const int by_env = g_prune_levels, by_depth = e->cfg.n_layers;
+    const int n = by_env < by_depth ? by_env : by_depth;
+    return n < DndmEngine::PRUNE_LEVELS ? n : DndmEngine::PRUNE_LEVELS;
+}
+
+// compacted edge lists of the receivers the last blocks still need
 static int build_last_block_edges(DndmEngine* e, int n_lig, int n_nodes, cudaStream_t st) {
-    mark_active_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol, e->deg, e->scalars, n_lig, n_nodes, e->deg_act, 0);
-    mark_active_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol, e->deg, e->scalars, n_lig, n_nodes, e->deg_act, 1);
+    mark_active_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol, e->deg, e->scalars, n_lig, n_nodes, e->deg_act[0], 0);
+    mark_active_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol, e->deg, e->scalars, n_lig, n_nodes, e->deg_act[0], 1);
     COUNT_LAUNCH(2);
-    RET_IF(exclusive_scan(e, e->deg_act, e->rp_act, n_nodes, n_lig, 2, -1, st));
-    compact_edges_kernel<<<(n_nodes * 32 + 255) / 256, 256, 0, st>>>(e->row_ptr, e->rp_act, e->erow, e->ecol, e->r0, n_nodes,
-                                                                     e->erow_c, e->ecol_c, e->r0_c);
-    COUNT_LAUNCH(1);
-    if (e->cfg.n_layers >= 2) {                // the block before the last: receivers of the last block + all their senders
-        mark_senders_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol_c, e->deg, e->deg_act, e->scalars, 2, n_nodes, e->deg_act2, 0);
-        mark_senders_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol_c, e->deg, e->deg_act, e->scalars, 2, n_nodes, e->deg_act2, 1);
-        COUNT_LAUNCH(2);
-        RET_IF(exclusive_scan(e, e->deg_act2, e->rp_act2, n_nodes, n_lig, 3, -1, st));
-        compact_edges_kernel<<<(n_nodes * 32 + 255) / 256, 256, 0, st>>>(e->row_ptr, e->rp_act2, e->erow, e->ecol, e->r0, n_nodes,
-                                                                         e->erow_c2, e->ecol_c2, e->r0_c2);
+    for (int k = 0; k < prune_levels(e); ++k) {
+        if (k > 0) {               // level k-1's receivers + all their senders
+            mark_senders_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol_c[k - 1], e->deg, e->deg_act[k - 1], e->scalars, 1 + k, n_nodes,
+                                                                e->deg_act[k], 0);
+            mark_senders_kernel<<<e->num_sms * 2, 256, 0, st>>>(e->ecol_c[k - 1], e->deg, e->deg_act[k - 1], e->scalars, 1 + k, n_nodes,
+                                                                e->deg_act[k], 1);
+            COUNT_LAUNCH(2);
+        }
+        RET_IF(exclusive_scan(e, e->deg_act[k], e->rp_act[k], n_nodes, n_lig, 2 + k, -1, st));
+        compact_edges_kernel<<<(n_nodes * 32 + 255) / 256, 256, 0, st>>>(e->row_ptr, e->rp_act[k], e->erow, e->ecol, e->r0, n_nodes,
+                                                                         e->erow_c[k], e->ecol_c[k], e->r0_c[k]);
         COUNT_LAUNCH(1);
     }
     CU_CHECK(cudaGetLastError());
@@ -765,13 +776,14 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         LayerWeights& L = e->layers[l];
         // exact dead-work elimination (graph.cuh): the last block aggregates for the ligand rows and their pocket senders only,
         // the block before it for those and all their senders
-        const bool pruned = prune_last && (l + 1 == e->cfg.n_layers);
-        const bool pruned2 = prune_last && g_prune2 && e->cfg.n_layers >= 2 && (l + 2 == e->cfg.n_layers);
-        if ((pruned2 || (pruned && !(g_prune2 && e->cfg.n_layers >= 2))) && fork) CU_CHECK(cudaStreamWaitEvent(st, e->ev_join_last, 0));
+        // pruning level of this block: 0 for the last block, 1 for the one before it, ...; -1 = all edges
+        const int lvl_raw = e->cfg.n_layers - 1 - l;
+        const int lvl = (prune_last && lvl_raw < prune_levels(e)) ? lvl_raw : -1;
+        const bool pruned = lvl >= 0;
+        if (pruned && lvl == prune_levels(e) - 1 && fork) CU_CHECK(cudaStreamWaitEvent(st, e->ev_join_last, 0));   // first pruned block
         // ---- GCL edge model + attention + deterministic aggregation ----
-        EdgeGraph g{pruned ? e->erow_c : (pruned2 ? e->erow_c2 : e->erow), pruned ? e->ecol_c : (pruned2 ? e->ecol_c2 : e->ecol),
-                    pruned ? e->r0_c : (pruned2 ? e->r0_c2 : e->r0), x_cur, e->scalars + (pruned ? 2 : (pruned2 ? 3 : 0)), n_lig, 1536,
-                    e->msg, e->att};
+        EdgeGraph g{pruned ? e->erow_c[lvl] : e->erow, pruned ? e->ecol_c[lvl] : e->ecol, pruned ? e->r0_c[lvl] : e->r0, x_cur,
+                    e->scalars + (pruned ? 2 + lvl : 0), n_lig, 1536, e->msg, e->att};
         EdgeProblem pe{e->pq, e->pq + 256, L.w1e_e, L.et_e, nullptr, L.att_bias, inv_norm};
         {
             ProfScope ps(e, PROF_GCL, st);
@@ -783,8 +795,7 @@ extern "C" int dndm_egnn_forward(DndmEngine* e, const float* xh_lig, const float
         }
         {
             ProfScope ps(e, PROF_NODE, st);
-            segment_reduce_kernel<<<node_blocks, 256, 0, st>>>(e->msg, e->att, pruned ? e->rp_act : (pruned2 ? e->rp_act2 : e->row_ptr), N,
-                                                               e->hcat);
+            segment_reduce_kernel<<<node_blocks, 256, 0, st>>>(e->msg, e->att, pruned ? e->rp_act[lvl] : e->row_ptr, N, e->hcat);
         }
         COUNT_LAUNCH(2);
         // ---- node MLP with residual + node projections: this block's coordinate heads (sender parts for every node, receiver
@@ -947,7 +958,7 @@ extern "C" int64_t dndm_debug_copy(DndmEngine* e, int32_t what, void* dst, int64
             src = e->ecol; bytes = (int64_t)sc[0] * 4;
             break;
         }
-        case 4: src = e->scalars; bytes = 16; break;
+        case 4: src = e->scalars; bytes = 32; break;
         case 7: src = e->pp.meta; bytes = 32; break;
         case 8:
             if (!e->h0_snap) return set_err(DNDM_EINVAL, "buffer 8 (h_0) exists only while a trace is set");

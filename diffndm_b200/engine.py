@@ -299,11 +299,14 @@ class Engine:
         return e, el, ea
 
     def graph_stats_pruned(self):
-        """(E, E_ligand_receiver, E_last_block, E_second_to_last_block) of the last forward without pocket output: the edges the
-        last two blocks aggregate over (exact dead-work elimination, csrc/graph.cuh); stale otherwise."""
-        t = torch.zeros(4, dtype=torch.int32, device=torch.device('cuda', self.device))
-        _check(self.lib, self.lib.dndm_debug_copy(self._h, 4, _ptr(t), 16, _stream()), 'dndm_debug_copy')
-        return tuple(t.cpu().tolist())
+        """(E, E_ligand_receiver, [E of the last block, of the block before it, ...]) of the last forward without pocket output:
+        the edges the trailing blocks aggregate over (exact dead-work elimination, csrc/graph.cuh; DNDM_PRUNE_LEVELS of them
+        -- default 2, at most 3 and at most n_layers); stale otherwise."""
+        t = torch.zeros(8, dtype=torch.int32, device=torch.device('cuda', self.device))
+        _check(self.lib, self.lib.dndm_debug_copy(self._h, 4, _ptr(t), 32, _stream()), 'dndm_debug_copy')
+        v = t.cpu().tolist()
+        levels = max(1, min(int(os.environ.get('DNDM_PRUNE_LEVELS', 2)), 3, self.cfg.n_layers))
+        return v[0], v[1], v[2:2 + levels]
 
 
 def launch_count() -> int:

@@ -124,7 +124,7 @@ int dndm_read_flags(DndmEngine* e, uint32_t* flags_host, void* stream);
 /* Introspection used by tests and the benchmark (not part of the reference surface):
  * copies an internal buffer of the LAST forward to a DEVICE destination.
  *   what: 0 = h [n_nodes,256] fp32, 1 = x [n_nodes,3] fp32 (final coordinates), 2 = row_ptr int32 [n_nodes+1],
- *         3 = col int32 [E], 4 = scalars int32 [4] (E, E_ligand_rows, E_last_block, E_second_to_last_block),
+ *         3 = col int32 [E], 4 = scalars int32 [8] (E, E_ligand_rows, E of the last block, of the block before it, of the one before that, reserved),
  *         8 = h_0 [n_nodes,256] fp32, the encoder + embedding output of the last forward (kept only while dndm_set_trace is on),
  *         7 = state of the pocket-pocket candidate lists int32 [8] (built, stale, n_lig, n_pocket, n_samples of the call they
  *             describe, list length the last call used for its first pocket row or -1 if it scanned everything)
