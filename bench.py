@@ -236,6 +236,8 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.samples = []          # (time, sm_mhz, set(reasons))
+        self.power = []            # (time, board power in W)
+        self.power_limit = None
         self.smax = None
         self.stop_flag = False
         self.proc = None
@@ -251,6 +253,10 @@ class ClockSampler:
             self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.nv = pynvml
             self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:
+                pass
             self.mode = 'nvml'
             self.th = threading.Thread(target=self._poll_nvml, daemon=True)
             self.th.start()
@@ -279,6 +285,10 @@ class ClockSampler:
                 mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = int(get_reasons(self.h))
                 self.samples.append((time.time(), mhz, {n for n, b in bits.items() if r & b}))
+                try:            # board power next to the clock: a clock below max at ~the power limit explains itself
+                    self.power.append((time.time(), nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+                except Exception:
+                    pass
             except Exception:
                 pass
             time.sleep(0.01)
@@ -308,8 +318,12 @@ class ClockSampler:
             if t0 <= ts <= t1:
                 sm.append(mhz)
                 reasons |= rs
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.smax, 'reasons': sorted(reasons),
-                'samples': len(sm), 'source': self.mode}
+        out = {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.smax, 'reasons': sorted(reasons),
+               'samples': len(sm), 'source': self.mode}
+        pw = [w for ts, w in self.power if t0 <= ts <= t1]
+        if pw:                     # NVML's power reading is a ~1 s running average: it lags a 0.2 s window
+            out.update({'power_w_max': max(pw), 'power_limit_w': self.power_limit})
+        return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
